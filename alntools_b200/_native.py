@@ -1,0 +1,212 @@
+"""ctypes binding of libecb200.so (C ABI declared in include/ecb200.h).
+
+The library is built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).  There is no CPU
+implementation behind this module: if the shared object is missing or no B200 is visible the
+constructors raise.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libecb200.so")
+
+ECB_OPT_RESULT_ON_DEVICE = 1
+ECB_OPT_TABLE_SLOTS = 2
+ECB_OPT_PAIR_SLOTS = 3
+ECB_OPT_GRID_CTAS = 4
+ECB_OPT_WARP_AGGREGATE = 5
+ECB_OPT_VERIFY_KEYS = 6
+
+ECB_ERR_EMPTY = -5
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+class EcbResult(ctypes.Structure):
+    _fields_ = [
+        ("n_ec", ctypes.c_int64), ("nnz_a", ctypes.c_int64),
+        ("a_indptr", _i32p), ("a_indices", _i32p), ("a_data", _i32p),
+        ("n_samples", ctypes.c_int64), ("nnz_n", ctypes.c_int64),
+        ("n_indptr", _i32p), ("n_indices", _i32p), ("n_data", _i32p),
+        ("cell_order", _i32p),
+        ("n_reads", ctypes.c_int64), ("n_alignments", ctypes.c_int64),
+    ]
+
+
+class EcbStats(ctypes.Structure):
+    _fields_ = [
+        ("group_ms", ctypes.c_double), ("harvest_ms", ctypes.c_double),
+        ("push_ms", ctypes.c_double), ("finalize_ms", ctypes.c_double),
+        ("kernel_launches", ctypes.c_int64), ("table_slots", ctypes.c_int64),
+        ("table_used", ctypes.c_int64), ("table_grows", ctypes.c_int64),
+        ("overflow_reads", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
+        ("d2h_bytes", ctypes.c_int64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+# every symbol include/ecb200.h declares, with its ctypes signature
+SIGNATURES = {
+    "ecb_version": (ctypes.c_int, []),
+    "ecb_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, ctypes.c_int64]),
+    "ecb_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
+    "ecb_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ecb_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
+    "ecb_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(EcbResult)]),
+    "ecb_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "ecb_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(EcbStats)]),
+    "ecb_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "ecb_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+class EcbError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "libecb200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def load_library(path=None):
+    """dlopen libecb200.so and attach signatures.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback for the EC build)" % p)
+    lib = ctypes.CDLL(p)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(x):
+    """Address of a numpy array / torch tensor / raw int; keeps nothing alive."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.int32 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError("columns must be C-contiguous int32 arrays")
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):  # torch tensor (host pinned or device); plumbing only
+        import torch
+        if x.dtype != torch.int32 or not x.is_contiguous():
+            raise TypeError("columns must be contiguous int32 tensors")
+        return x.data_ptr()
+    raise TypeError("unsupported column type %r" % type(x))
+
+
+def _on_device(x):
+    return bool(getattr(x, "is_cuda", False))
+
+
+class EcBuilder(object):
+    """One context = one GPU.  push() columns, finalize() -> dict of numpy int32 arrays."""
+
+    def __init__(self, n_targets, n_haps, with_cells=False, alignments_hint=0, device=0, **options):
+        self._lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        rc = self._lib.ecb_create(ctypes.byref(self._ctx), device, int(n_targets), int(n_haps),
+                                  1 if with_cells else 0, int(alignments_hint))
+        if rc != 0:
+            raise EcbError(rc, self._lib.ecb_last_error(None).decode())
+        self.with_cells = bool(with_cells)
+        self._result_on_device = False
+        for key, value in options.items():
+            self.set_option(key, value)
+
+    _OPTIONS = {"result_on_device": ECB_OPT_RESULT_ON_DEVICE, "table_slots": ECB_OPT_TABLE_SLOTS,
+                "pair_slots": ECB_OPT_PAIR_SLOTS, "grid_ctas": ECB_OPT_GRID_CTAS,
+                "warp_aggregate": ECB_OPT_WARP_AGGREGATE, "verify_keys": ECB_OPT_VERIFY_KEYS}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EcbError(rc, self._lib.ecb_last_error(self._ctx).decode())
+
+    def set_option(self, name, value):
+        self._check(self._lib.ecb_set_option(self._ctx, self._OPTIONS[name], int(value)))
+        if name == "result_on_device":
+            self._result_on_device = bool(value)
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.ecb_set_stream(self._ctx, cuda_stream))
+
+    def push(self, read_group, target_idx, hap_idx, cell_idx=None, order_base=0, drop_last_group=False,
+             n=None):
+        if n is None:
+            n = int(read_group.shape[0])
+        dev = _on_device(read_group)
+        self._check(self._lib.ecb_push(self._ctx, _ptr(read_group), _ptr(target_idx), _ptr(hap_idx),
+                                       _ptr(cell_idx), n, int(order_base), 1 if drop_last_group else 0,
+                                       1 if dev else 0))
+
+    def finalize_raw(self, min_cell_count=0):
+        res = EcbResult()
+        self._check(self._lib.ecb_finalize(self._ctx, int(min_cell_count), ctypes.byref(res)))
+        return res
+
+    def finalize(self, min_cell_count=0):
+        """Returns dict(a_indptr, a_indices, a_data, n_indptr, n_indices, n_data[, cell_order]) as
+        numpy int32 COPIES plus scalar sizes."""
+        if self._result_on_device:
+            raise RuntimeError("finalize() needs host results; use finalize_raw() with result_on_device")
+        res = self.finalize_raw(min_cell_count)
+
+        def arr(ptr, n):
+            if n == 0:
+                return np.zeros(0, dtype=np.int32)
+            return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+        out = {
+            "n_ec": res.n_ec, "nnz_a": res.nnz_a, "n_samples": res.n_samples, "nnz_n": res.nnz_n,
+            "n_reads": res.n_reads, "n_alignments": res.n_alignments,
+            "a_indptr": arr(res.a_indptr, res.n_ec + 1),
+            "a_indices": arr(res.a_indices, res.nnz_a),
+            "a_data": arr(res.a_data, res.nnz_a),
+            "n_indptr": arr(res.n_indptr, res.n_samples + 1),
+            "n_indices": arr(res.n_indices, res.nnz_n),
+            "n_data": arr(res.n_data, res.nnz_n),
+        }
+        if self.with_cells:
+            out["cell_order"] = arr(res.cell_order, res.n_samples)
+        return out
+
+    def reset(self):
+        self._check(self._lib.ecb_reset(self._ctx))
+
+    def stats(self):
+        st = EcbStats()
+        self._check(self._lib.ecb_get_stats(self._ctx, ctypes.byref(st)))
+        return st.as_dict()
+
+    def close(self):
+        if self._ctx:
+            self._lib.ecb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

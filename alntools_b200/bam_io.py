@@ -41,6 +41,12 @@ def bam_record_bytes(qname, flag, tid, pos=0, next_tid=-1, next_pos=-1):
     return struct.pack("<i", len(core)) + core
 
 
+def _write_blocks(fh, payload, block_payload, level):
+    """BGZF blocks hold at most 64 KiB: split long payloads (e.g. a 200k-reference header)."""
+    for off in range(0, len(payload), block_payload):
+        fh.write(bgzf_block(payload[off:off + block_payload], level))
+
+
 def write_bam(filename, references, alignments, block_payload=60000, level=6):
     """Write a BAM file.
 
@@ -49,7 +55,7 @@ def write_bam(filename, references, alignments, block_payload=60000, level=6):
     The header is placed in its own BGZF block so alignments start on a block boundary.
     """
     with open(filename, "wb") as fh:
-        fh.write(bgzf_block(bam_header_bytes(references), level))
+        _write_blocks(fh, bam_header_bytes(references), min(block_payload, 60000), level)
         buf = []
         size = 0
         for aln in alignments:
@@ -96,7 +102,7 @@ def write_bam_columns(filename, references, qname_ids, flags, tids, name_fmt="re
     flat = raw.reshape(-1)
     per_block = max(1, block_payload // rec_len) * rec_len
     with open(filename, "wb") as fh:
-        fh.write(bgzf_block(bam_header_bytes(references), level))
+        _write_blocks(fh, bam_header_bytes(references), 60000, level)
         for off in range(0, flat.size, per_block):
             fh.write(bgzf_block(flat[off:off + per_block].tobytes(), level))
         fh.write(BGZF_EOF)

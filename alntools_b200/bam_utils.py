@@ -1,0 +1,98 @@
+"""Single-sample bam2ec / bam2emase converter: same signature as alntools/bam_utils.convert
+(bam_utils.py:512), with the grouping, counting, ordering and matrix build on the GPU.
+
+Call stack: convert -> header tables (host) -> column emitter (host decode + filters + name compare)
+-> EcBuilder.push (H2D + sm_100a kernels) -> EcBuilder.finalize (CSR A, CSC N) -> EC file writer.
+"""
+import multiprocessing
+import os
+import time
+
+import numpy as np
+
+from . import bin_utils, emase, emitter, utils
+from ._native import EcBuilder
+from .header import TargetTables
+
+LOG = utils.get_logger()
+
+
+def _job_plan(num_chunks, number_processes):
+    """bam_utils.py:530-544."""
+    num_processes = multiprocessing.cpu_count() if number_processes <= 0 else number_processes
+    if num_chunks <= 0:
+        num_chunks = num_processes
+    elif num_chunks > 1000:
+        LOG.info("Modifying number of chunks from {} to 1000".format(num_chunks))
+        num_chunks = 1000
+    return num_chunks, min(num_processes, num_chunks)
+
+
+def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_processes=-1, temp_dir=None,
+            range_filename=None, sample=None, target_filename=None, device=0):
+    """Convert a name-grouped BAM file into an EC binary file and/or an EMASE file.
+
+    Arguments keep the reference's meaning.  num_chunks / number_processes only shape the host decode
+    (the EC file does not depend on them, as in the reference); temp_dir is unused because no
+    temporary BAM is written.  `device` selects the GPU.
+    """
+    start_time = time.time()
+    if range_filename is not None:
+        raise NotImplementedError("--rangefile is not part of the GPU EC path yet")
+    num_chunks, num_processes = _job_plan(num_chunks, number_processes)
+    if sample is None:                                        # bam_utils.py:552-554
+        sample = os.path.basename(bam_filename)
+        LOG.info("Sample not supplied, using filename: {}".format(sample))
+
+    LOG.info("Parsing file information ...")
+    temp_time = time.time()
+    header, records = emitter.read_bam(bam_filename)
+    tables = TargetTables(header.references, header.lengths, target_filename)
+    LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
+                                                        utils.format_time(start_time, time.time())))
+
+    temp_time = time.time()
+    cols = emitter.emit_single(records, tables)
+    LOG.info("Columns emitted in {}".format(utils.format_time(temp_time, time.time())))
+    if cols.valid_alignments == 0:
+        # the reference ends up with zero ECs and APM() raises (Sparse3DMatrix.py:45-46)
+        raise RuntimeError("The shape must be a tuple of three positive integers.")
+
+    temp_time = time.time()
+    with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False,
+                   alignments_hint=cols.valid_alignments, device=device) as builder:
+        builder.push(cols.read_group, cols.target_idx, cols.hap_idx, order_base=0)
+        res = builder.finalize()
+    LOG.info("All results combined in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
+                                                                 utils.format_time(start_time, time.time())))
+    LOG.info("# Valid Alignments: {:,}".format(cols.valid_alignments))
+    LOG.info("# Main Targets: {:,}".format(tables.num_targets))
+    LOG.info("# Haplotypes: {:,}".format(tables.num_haplotypes))
+    LOG.info("# Equivalence Classes: {:,}".format(res["n_ec"]))
+    LOG.info("# Unique Reads: {:,}".format(res["n_reads"]))
+
+    a_csr = (res["a_indptr"], res["a_indices"], res["a_data"])
+    n_csc = (res["n_indptr"], res["n_indices"], res["n_data"])
+    target_names = list(tables.main_targets.keys())
+    if emase_filename:
+        LOG.info("Saving to {}...".format(emase_filename))
+        try:
+            os.remove(emase_filename)
+        except OSError:
+            pass
+        emase.save_emase(emase_filename, "bam2ec", (tables.num_targets, tables.num_haplotypes, res["n_ec"]),
+                         tables.haplotypes, target_names, tables.lengths, [sample], a_csr, n_csc,
+                         incidence_only=True)
+    if ec_filename:
+        LOG.info("Saving to {}...".format(ec_filename))
+        try:
+            os.remove(ec_filename)
+        except OSError:
+            pass
+        temp_time = time.time()
+        bin_utils.ecsave2_arrays(ec_filename, tables.haplotypes, target_names, tables.lengths, [sample],
+                                 a_csr, n_csc)
+        LOG.info("{} created in {}, total time: {}".format(ec_filename,
+                                                           utils.format_time(temp_time, time.time()),
+                                                           utils.format_time(start_time, time.time())))
+    return res

@@ -1,0 +1,83 @@
+"""Per-cell (multisample) bam2ec / bam2emase converter: same signature as
+alntools/bam_utils_multisample.convert (bam_utils_multisample.py:357).  One BAM file per task, the
+cell id is field 14 of the '|||'-split read name, the last read of every file is dropped (:306-308),
+cells below the minimum count and ECs left without cells are removed (:595-636).
+"""
+import glob
+import os
+import time
+
+from . import bin_utils, emase, emitter, utils
+from ._native import EcBuilder
+from .header import TargetTables
+
+LOG = utils.get_logger()
+
+
+def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename=None, device=0):
+    """The reference's convert() after its glob: files are merged in the given order
+    (bam_utils_multisample.py:503-560)."""
+    start_time = time.time()
+    header, _ = emitter.read_bam(bam_files[0])                # tables from the first file only (:399)
+    tables = TargetTables(header.references, header.lengths, target_filename)
+    cell_ids = {}
+    per_file = []
+    total_valid = 0
+    for bam_file in bam_files:
+        _, records = emitter.read_bam(bam_file)
+        cols = emitter.emit_multisample(records, tables, cell_ids)
+        per_file.append(cols)
+        total_valid += cols.valid_alignments
+    cell_names = [None] * len(cell_ids)
+    for name, idx in cell_ids.items():
+        cell_names[idx] = name
+
+    with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
+                   alignments_hint=total_valid, device=device) as builder:
+        base = 0
+        for cols in per_file:
+            builder.push(cols.read_group, cols.target_idx, cols.hap_idx, cols.cell_idx, order_base=base,
+                         drop_last_group=True)
+            base += cols.valid_alignments
+        res = builder.finalize(minimum_count)
+
+    LOG.info("Number of alignments: {:,}".format(total_valid))
+    LOG.info("Number of main targets: {:,}".format(tables.num_targets))
+    LOG.info("Number of haplotypes: {:,}".format(tables.num_haplotypes))
+    LOG.info("Number of ECs after filtering : {:,}".format(res["n_ec"]))
+    LOG.info("Number of cells after filtering: {:,}".format(res["n_samples"]))
+    sample_names = [cell_names[c] for c in res["cell_order"].tolist()]
+    a_csr = (res["a_indptr"], res["a_indices"], res["a_data"])
+    n_csc = (res["n_indptr"], res["n_indices"], res["n_data"])
+    target_names = list(tables.main_targets.keys())
+    if emase_filename:
+        try:
+            os.remove(emase_filename)
+        except OSError:
+            pass
+        emase.save_emase(emase_filename, "Multisample APM",
+                         (tables.num_targets, tables.num_haplotypes, res["n_ec"]), tables.haplotypes,
+                         target_names, tables.lengths, sample_names, a_csr, n_csc, incidence_only=False)
+    if ec_filename:
+        try:
+            os.remove(ec_filename)
+        except OSError:
+            pass
+        bin_utils.ecsave2_arrays(ec_filename, tables.haplotypes, target_names, tables.lengths, sample_names,
+                                 a_csr, n_csc)
+        LOG.info("{} created, total time: {}".format(ec_filename, utils.format_time(start_time, time.time())))
+    return res
+
+
+def convert(bam_filename, ec_filename, emase_filename, num_chunks, minimum_count, number_processes, temp_dir,
+            range_filename, target_filename, device=0):
+    if os.path.isfile(bam_filename):                          # :375-377
+        LOG.error('bam file must be a directory')
+        return None
+    bam_files = glob.glob(os.path.join(bam_filename, "*.bam"))  # :379 (filesystem order, as the reference)
+    if len(bam_files) == 0:
+        LOG.error('No bam files found in directory: {}'.format(bam_filename))
+        return None
+    if range_filename is not None:
+        raise NotImplementedError("--rangefile is not part of the GPU EC path yet")
+    return convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename, device)

@@ -1,0 +1,90 @@
+"""EC binary file (format 2) writer/reader fed by device-built arrays.
+
+Byte layout = alntools/bin_utils.ecsave2 (bin_utils.py:105-277): every integer a little-endian int32,
+strings raw UTF-8 with an int32 length prefix, no padding:
+    2 | H | H x [len, bytes] | T | T x [len, bytes, H x length] | S | S x [len, bytes]
+    | A (CSR, E x T): len(indptr)=E+1, nnz, indptr, indices, data (haplotype bitmask)
+    | N (CSC, E x S): len(indptr)=S+1, nnz, indptr, indices (EC ids), data (counts)
+The reference packs every array with struct.pack('<{n}i', *arr) (one Python int per element);
+ndarray.astype('<i4').tobytes() yields the same bytes.
+"""
+import struct
+
+import numpy as np
+
+
+def _i32(arr):
+    return np.ascontiguousarray(arr, dtype="<i4").tobytes()
+
+
+def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names, a_csr, n_csc):
+    """a_csr / n_csc: (indptr, indices, data) int32 arrays."""
+    with open(ec_filename, "wb") as fh:
+        fh.write(struct.pack("<i", 2))
+        fh.write(struct.pack("<i", len(haplotypes)))
+        for hap in haplotypes:
+            fh.write(struct.pack("<i", len(hap)))
+            fh.write(hap.encode("utf-8"))
+        lengths = np.asarray(lengths).astype(int)
+        fh.write(struct.pack("<i", len(target_names)))
+        parts = []
+        for idx, name in enumerate(target_names):
+            parts.append(struct.pack("<i", len(name)))
+            parts.append(name.encode("utf-8"))
+            parts.append(_i32(lengths[idx, :len(haplotypes)]))
+        fh.write(b"".join(parts))
+        fh.write(struct.pack("<i", len(sample_names)))
+        parts = []
+        for sample in sample_names:
+            parts.append(struct.pack("<i", len(sample)))
+            parts.append(sample.encode("utf-8"))
+        fh.write(b"".join(parts))
+        for indptr, indices, data in (a_csr, n_csc):
+            fh.write(struct.pack("<i", len(indptr)))
+            fh.write(struct.pack("<i", len(indices)))
+            fh.write(_i32(indptr))
+            fh.write(_i32(indices))
+            fh.write(_i32(data))
+
+
+def ecload_arrays(ec_filename):
+    """Inverse of ecsave2_arrays (what bin_utils.ecload :32-102 / bin_file.ECFile :99-402 parse)."""
+    with open(ec_filename, "rb") as fh:
+        buf = fh.read()
+    pos = [0]
+
+    def i32():
+        v = struct.unpack_from("<i", buf, pos[0])[0]
+        pos[0] += 4
+        return v
+
+    def text():
+        n = i32()
+        s = buf[pos[0]:pos[0] + n].decode("utf-8")
+        pos[0] += n
+        return s
+
+    def arr(n):
+        a = np.frombuffer(buf, dtype="<i4", count=n, offset=pos[0]).copy()
+        pos[0] += 4 * n
+        return a
+
+    fmt = i32()
+    if fmt != 2:
+        raise ValueError("only EC format 2 is supported, found %d" % fmt)
+    haplotypes = [text() for _ in range(i32())]
+    n_targets = i32()
+    targets = []
+    lengths = np.zeros((n_targets, len(haplotypes)), dtype=np.int32)
+    for t in range(n_targets):
+        targets.append(text())
+        lengths[t] = arr(len(haplotypes))
+    samples = [text() for _ in range(i32())]
+    mats = []
+    for _ in range(2):
+        n_ptr, nnz = i32(), i32()
+        mats.append((arr(n_ptr), arr(nnz), arr(nnz)))
+    if pos[0] != len(buf):
+        raise ValueError("trailing bytes in EC file")
+    return {"haplotypes": haplotypes, "targets": targets, "lengths": lengths, "samples": samples,
+            "a": mats[0], "n": mats[1]}

@@ -1,0 +1,831 @@
+// ecb_api.cu — context management and the C ABI of libecb200.so (see include/ecb200.h).
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ecb200.h"
+#include "ecb_common.cuh"
+#include "ecb_scan.cuh"
+#include "ecb_group.cuh"
+#include "ecb_harvest.cuh"
+#include "ecb_finalize.cuh"
+#include "ecb_sort.cuh"
+#include "ecb_cells.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct ecb_timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace
+
+struct ecb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int n_targets = 0, n_haps = 0, with_cells = 0;
+  int64_t hint = 0;
+  // options
+  int result_on_device = 0;
+  int64_t opt_table_slots = 0, opt_pair_slots = 0, opt_grid = 0;
+  int warp_aggregate = 1;
+  int verify_keys = 0;
+  // EC table
+  DevBuf table;
+  u32 table_slots = 0;
+  DevBuf ec_slot, ec_rep, row_len, row_off;  // [table_slots] u32 each
+  DevBuf arena;                              // uint2 pairs
+  u64 arena_used = 0;
+  DevBuf long_list;
+  // triple table (cells)
+  DevBuf ttable;
+  u32 ttable_slots = 0;
+  u32 n_triples = 0;
+  // counters
+  EcbCounters* d_ctr = nullptr;
+  EcbCounters* h_ctr = nullptr;  // pinned mirror
+  u32 n_ec = 0;                  // host copy after the last sync
+  // staging
+  DevBuf st_rg, st_tg, st_hp, st_cell;
+  DevBuf overflow_bits;
+  DevBuf scan_partials;  // u64 block sums + 1 total
+  // push bookkeeping
+  u64 min_base = ~0ull, max_end = 0;
+  int64_t n_alignments = 0;
+  u32 push_count = 0;
+  // finalize scratch + results (device)
+  DevBuf bitmap, word_rank, first_rel, ecid_of, ec_keep;
+  DevBuf r_a_indptr, r_a_indices, r_a_data, r_n_indptr, r_n_indices, r_n_data, r_cell_order;
+  // cells scratch
+  CellScratch cells;
+  // host (pinned) results
+  void* h_res = nullptr;
+  size_t h_res_bytes = 0;
+  // stats
+  ecb_stats stats{};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool long_attr_set = false;
+  std::string err;
+};
+
+namespace {
+
+int fail(ecb_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, ECB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                                       \
+  } while (0)
+
+#define CKR(expr)            \
+  do {                       \
+    int r_ = (expr);         \
+    if (r_ != ECB_OK) return r_; \
+  } while (0)
+
+#define LAUNCH_CHECK(name)                                                                          \
+  do {                                                                                              \
+    c->stats.kernel_launches++;                                                                     \
+    cudaError_t e_ = cudaGetLastError();                                                            \
+    if (e_ != cudaSuccess) return fail(c, ECB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+int ensure(ecb_ctx* c, DevBuf& b, size_t bytes, bool preserve = false) {
+  if (bytes <= b.bytes) return ECB_OK;
+  size_t want = std::max(bytes, b.bytes + b.bytes / 2);
+  want = (want + 255) & ~(size_t)255;
+  void* np = nullptr;
+  CK(cudaMalloc(&np, want));
+  if (preserve && b.p && b.bytes) CK(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream));
+  if (b.p) {
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(b.p));
+  }
+  b.p = np;
+  b.bytes = want;
+  return ECB_OK;
+}
+
+void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+u32 pow2_ceil(u64 v) {
+  u64 p = 1;
+  while (p < v) p <<= 1;
+  return (u32)std::min<u64>(p, 1ull << 31);
+}
+
+int grid_for(u64 items, int per_block, int cap) {
+  u64 g = (items + per_block - 1) / per_block;
+  return (int)std::max<u64>(1, std::min<u64>(g, (u64)cap));
+}
+
+int sync_counters(ecb_ctx* c) {
+  CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(EcbCounters), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stats.d2h_bytes += sizeof(EcbCounters);
+  return ECB_OK;
+}
+
+int check_device_error(ecb_ctx* c) {
+  const u32 e = c->h_ctr->error;
+  if (!e) return ECB_OK;
+  if (e & ECB_DEVERR_VALUE_RANGE)
+    return fail(c, ECB_ERR_INVALID, "target_idx/hap_idx outside [0,%d) x [0,%d)", c->n_targets, c->n_haps);
+  if (e & ECB_DEVERR_READ_TOO_LONG)
+    return fail(c, ECB_ERR_LIMIT, "a read has more than %d alignments", ECB_MAX_READ_ALIGNMENTS);
+  if (e & ECB_DEVERR_VERIFY) return fail(c, ECB_ERR_LIMIT, "128-bit key collision detected by verification");
+  return fail(c, ECB_ERR_LIMIT, "device error bits 0x%x", e);
+}
+
+// Device-wide exclusive scan (in may alias out).  total_out (host) may be NULL.
+template <bool POPC>
+int device_scan(ecb_ctx* c, const u32* in, u32* out, u64 n, u32 base_offset, u64* total_out) {
+  const u32 n_blocks = (u32)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+  CKR(ensure(c, c->scan_partials, ((size_t)n_blocks + 2) * sizeof(u64)));
+  u64* partials = (u64*)c->scan_partials.p;
+  u64* d_total = partials + n_blocks;
+  if (n_blocks == 0) {
+    if (total_out) *total_out = 0;
+    return ECB_OK;
+  }
+  scan_block_sums_kernel<POPC><<<n_blocks, SCAN_THREADS, 0, c->stream>>>(in, n, partials);
+  LAUNCH_CHECK("scan_block_sums");
+  scan_partials_kernel<<<1, 1024, 0, c->stream>>>(partials, n_blocks, d_total);
+  LAUNCH_CHECK("scan_partials");
+  scan_apply_kernel<POPC><<<n_blocks, SCAN_THREADS, 0, c->stream>>>(in, n, partials, out, base_offset);
+  LAUNCH_CHECK("scan_apply");
+  if (total_out) {
+    CK(cudaMemcpyAsync(total_out, d_total, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += sizeof(u64);
+  }
+  return ECB_OK;
+}
+
+int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
+  CKR(ensure(c, c->ec_slot, (size_t)slots * 4, preserve));
+  CKR(ensure(c, c->ec_rep, (size_t)slots * 4, preserve));
+  CKR(ensure(c, c->row_len, (size_t)slots * 4, preserve));
+  CKR(ensure(c, c->row_off, (size_t)slots * 4, preserve));
+  CKR(ensure(c, c->long_list, (size_t)slots * 4, false));
+  return ECB_OK;
+}
+
+int init_table(ecb_ctx* c) {
+  u64 want = c->opt_table_slots > 0 ? (u64)c->opt_table_slots : std::max<u64>(1u << 16, (u64)c->hint / 16);
+  c->table_slots = std::max<u32>(1u << 10, pow2_ceil(want));
+  CKR(ensure(c, c->table, (size_t)c->table_slots * sizeof(EcbEntry)));
+  CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
+  CKR(alloc_ec_arrays(c, c->table_slots, false));
+  if (c->with_cells) {
+    u64 tw = c->opt_pair_slots > 0 ? (u64)c->opt_pair_slots : std::max<u64>(1u << 16, (u64)c->hint / 2);
+    c->ttable_slots = std::max<u32>(1u << 10, pow2_ceil(tw));
+    CKR(ensure(c, c->ttable, (size_t)c->ttable_slots * sizeof(EcbEntry)));
+    CK(cudaMemsetAsync(c->ttable.p, 0xFF, (size_t)c->ttable_slots * sizeof(EcbEntry), c->stream));
+  }
+  CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(EcbCounters), c->stream));
+  memset(c->h_ctr, 0, sizeof(EcbCounters));
+  c->n_ec = 0;
+  c->n_triples = 0;
+  c->arena_used = 0;
+  return ECB_OK;
+}
+
+// Rebuild the (file, EC, cell) table with `new_slots` slots; remap (device, by old EC slot) may be NULL.
+int rebuild_triple_table(ecb_ctx* c, u32 new_slots, const u32* remap) {
+  DevBuf nt;
+  CKR(ensure(c, nt, (size_t)new_slots * sizeof(EcbEntry)));
+  CK(cudaMemsetAsync(nt.p, 0xFF, (size_t)new_slots * sizeof(EcbEntry), c->stream));
+  ecb_triple_remap_kernel<<<grid_for(c->ttable_slots, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+      (const EcbEntry*)c->ttable.p, c->ttable_slots, (EcbEntry*)nt.p, new_slots - 1, remap);
+  LAUNCH_CHECK("triple_remap");
+  CK(cudaStreamSynchronize(c->stream));
+  release(c->ttable);
+  c->ttable = nt;
+  c->ttable_slots = new_slots;
+  return ECB_OK;
+}
+
+int grow_table(ecb_ctx* c, u32 new_slots) {
+  DevBuf nt;
+  CKR(ensure(c, nt, (size_t)new_slots * sizeof(EcbEntry)));
+  CK(cudaMemsetAsync(nt.p, 0xFF, (size_t)new_slots * sizeof(EcbEntry), c->stream));
+  CKR(alloc_ec_arrays(c, new_slots, true));
+  DevBuf remap;
+  if (c->with_cells) CKR(ensure(c, remap, (size_t)c->table_slots * 4));
+  ecb_rehash_kernel<<<grid_for(c->table_slots, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+      (const EcbEntry*)c->table.p, c->table_slots, (EcbEntry*)nt.p, new_slots - 1, (u32*)c->ec_slot.p,
+      (u32*)remap.p, c->d_ctr);
+  LAUNCH_CHECK("rehash");
+  CK(cudaStreamSynchronize(c->stream));
+  release(c->table);
+  c->table = nt;
+  c->table_slots = new_slots;
+  c->stats.table_grows++;
+  if (c->with_cells) {
+    CKR(rebuild_triple_table(c, c->ttable_slots, (const u32*)remap.p));
+    release(remap);
+  }
+  return ECB_OK;
+}
+
+GroupParams make_group_params(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int32_t* hp,
+                              const int32_t* cell, int64_t n, int64_t order_base, int drop_last, u32 push_id) {
+  GroupParams P{};
+  P.rg = rg; P.tg = tg; P.hp = hp; P.cell = cell;
+  P.n = (int)n;
+  P.order_base = (u64)order_base;
+  P.drop_last = drop_last;
+  P.warp_aggregate = c->warp_aggregate;
+  P.n_targets = c->n_targets;
+  P.n_haps = c->n_haps;
+  P.table = (EcbEntry*)c->table.p;
+  P.mask = c->table_slots - 1;
+  P.ec_slot = (u32*)c->ec_slot.p;
+  P.ec_rep = (u32*)c->ec_rep.p;
+  P.ctr = c->d_ctr;
+  P.overflow_bits = (u32*)c->overflow_bits.p;
+  P.ttable = (EcbEntry*)c->ttable.p;
+  P.tmask = c->ttable_slots ? c->ttable_slots - 1 : 0;
+  P.push_id = push_id;
+  return P;
+}
+
+int group_resident_ctas(ecb_ctx* c) {
+  int per_sm = 0;
+  cudaError_t e = c->with_cells
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<true>, ECB_TILE_THREADS, 0)
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<false>, ECB_TILE_THREADS, 0);
+  if (e != cudaSuccess || per_sm < 1) per_sm = 2;
+  return per_sm * c->sm_count;
+}
+
+int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int32_t* hp, int64_t n, u32 e0,
+                     u32 e1) {
+  if (e1 <= e0) return ECB_OK;
+  HarvestParams H{};
+  H.rg = rg; H.tg = tg; H.hp = hp; H.n = (int)n;
+  H.ec_rep = (const u32*)c->ec_rep.p;
+  H.e0 = e0; H.e1 = e1;
+  H.row_len = (u32*)c->row_len.p;
+  H.row_off = (u32*)c->row_off.p;
+  H.long_list = (u32*)c->long_list.p;
+  H.ctr = c->d_ctr;
+  const u32 n_new = e1 - e0;
+  const int g = grid_for((u64)n_new * 32, 256, c->sm_count * 8);
+  ecb_harvest_count_kernel<<<g, 256, 0, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_count");
+  u64 total = 0;
+  if (c->arena_used > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
+  CKR(device_scan<false>(c, H.row_len + e0, H.row_off + e0, n_new, (u32)c->arena_used, &total));
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
+  if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
+  CKR(ensure(c, c->arena, (size_t)(c->arena_used + total) * sizeof(uint2), true));
+  H.arena = (uint2*)c->arena.p;
+  ecb_harvest_fill_kernel<<<g, 256, 0, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_fill");
+  const u32 n_long = c->h_ctr->n_long;
+  if (n_long) {
+    if (!c->long_attr_set) {
+      CK(cudaFuncSetAttribute(ecb_harvest_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              HARVEST_LONG_MAX * 4));
+      c->long_attr_set = true;
+    }
+    ecb_harvest_long_kernel<<<grid_for(n_long, 1, c->sm_count * 3), 256, HARVEST_LONG_MAX * 4, c->stream>>>(H, n_long);
+    LAUNCH_CHECK("harvest_long");
+    CK(cudaMemsetAsync(&c->d_ctr->n_long, 0, sizeof(u32), c->stream));
+  }
+  c->arena_used += total;
+  return ECB_OK;
+}
+
+
+// Stable LSD radix sort of n (key, value) pairs on the low `bits` key bits.  Input in sort_k[0]/
+// sort_v[0]; returns which ping-pong buffer holds the result.
+int radix_sort(ecb_ctx* c, u32 n, int bits, int* result_buf) {
+  CellScratch& S = c->cells;
+  *result_buf = 0;
+  if (n == 0) return ECB_OK;
+  const u32 n_tiles = (n + SORT_TILE - 1) / SORT_TILE;
+  CKR(ensure(c, S.sort_k[1], (size_t)n * 8));
+  CKR(ensure(c, S.sort_v[1], (size_t)n * 4));
+  CKR(ensure(c, S.hist, (size_t)n_tiles * 256 * 4));
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    sort_hist_kernel<<<n_tiles, SORT_THREADS, 0, c->stream>>>((const u64*)S.sort_k[cur].p, n, shift, (u32*)S.hist.p, n_tiles);
+    LAUNCH_CHECK("sort_hist");
+    CKR(device_scan<false>(c, (const u32*)S.hist.p, (u32*)S.hist.p, (u64)n_tiles * 256, 0, nullptr));
+    sort_scatter_kernel<<<n_tiles, SORT_THREADS, 0, c->stream>>>((const u64*)S.sort_k[cur].p, (const u32*)S.sort_v[cur].p,
+                                                                   n, shift, (const u32*)S.hist.p, n_tiles,
+                                                                   (u64*)S.sort_k[cur ^ 1].p, (u32*)S.sort_v[cur ^ 1].p);
+    LAUNCH_CHECK("sort_scatter");
+    cur ^= 1;
+  }
+  *result_buf = cur;
+  return ECB_OK;
+}
+
+int bits_for(u64 v) {
+  int b = 1;
+  while (b < 64 && (v >> b)) ++b;
+  return b;
+}
+
+CellParams make_cell_params(ecb_ctx* c, const CellResult* cr) {
+  CellScratch& S = c->cells;
+  CellParams P{};
+  P.ttable = (const EcbEntry*)c->ttable.p;
+  P.t_slots = c->ttable_slots;
+  P.ec_table = (const EcbEntry*)c->table.p;
+  P.fe_table = (EcbEntry*)S.fe_table.p;
+  P.fe_mask = S.fe_slots - 1;
+  P.pair_table = (EcbEntry*)S.pair_table.p;
+  P.pair_mask = S.pair_slots - 1;
+  P.cell_key = (u64*)S.cell_key.p;
+  P.cell_total = (u64*)S.cell_total.p;
+  P.cell_new = (int32_t*)S.cell_new.p;
+  P.ec_keep = (u32*)c->ec_keep.p;
+  P.ecid_of = (const u32*)c->ecid_of.p;
+  P.min_base = c->min_base;
+  P.n_cells = (u32)cr->n_cells;
+  P.ctr = c->d_ctr;
+  return P;
+}
+
+// Cell order, minimum-count filter and the ec_keep flags (bam_utils_multisample.py:503-636).
+int cells_prepare(ecb_ctx* c, int64_t min_cell_count, CellResult* cr) {
+  CellScratch& S = c->cells;
+  if (c->max_end - c->min_base > 0xFFFFFFFFull)
+    return fail(c, ECB_ERR_LIMIT, "per-cell mode needs the pushed order range to span less than 2^32 positions");
+  if (c->n_triples == 0) return fail(c, ECB_ERR_EMPTY, "no (EC, cell) counts were recorded");
+  const u64 min_count = min_cell_count <= 0 ? 1ull : (u64)min_cell_count;  // :596-597
+  S.fe_slots = std::max<u32>(1024u, pow2_ceil((u64)c->n_triples * 2));
+  S.pair_slots = S.fe_slots;
+  CKR(ensure(c, S.fe_table, (size_t)S.fe_slots * sizeof(EcbEntry)));
+  CKR(ensure(c, S.pair_table, (size_t)S.pair_slots * sizeof(EcbEntry)));
+  CK(cudaMemsetAsync(S.fe_table.p, 0xFF, (size_t)S.fe_slots * sizeof(EcbEntry), c->stream));
+  CK(cudaMemsetAsync(S.pair_table.p, 0xFF, (size_t)S.pair_slots * sizeof(EcbEntry), c->stream));
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[0], 0, sizeof(u32), c->stream));
+  CKR(ensure(c, c->ec_keep, (size_t)c->n_ec * 4));
+  CK(cudaMemsetAsync(c->ec_keep.p, 0, (size_t)c->n_ec * 4, c->stream));
+
+  CellParams P = make_cell_params(c, cr);
+  const int g_t = grid_for(c->ttable_slots, 256, c->sm_count * 8);
+  cells_pass1_kernel<<<g_t, 256, 0, c->stream>>>(P);
+  LAUNCH_CHECK("cells_pass1");
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
+  const u32 n_cells = c->h_ctr->scratch[0];
+  if (n_cells == 0 || n_cells > 0x7FFFFFFFu) return fail(c, ECB_ERR_INVALID, "invalid cell ids (negative?)");
+  cr->n_cells = n_cells;
+  CKR(ensure(c, S.cell_key, (size_t)n_cells * 8));
+  CKR(ensure(c, S.cell_total, (size_t)n_cells * 8));
+  CKR(ensure(c, S.cell_new, (size_t)n_cells * 4));
+  CKR(ensure(c, c->r_cell_order, (size_t)n_cells * 4));
+  CK(cudaMemsetAsync(S.cell_key.p, 0xFF, (size_t)n_cells * 8, c->stream));
+  CK(cudaMemsetAsync(S.cell_total.p, 0, (size_t)n_cells * 8, c->stream));
+  P = make_cell_params(c, cr);
+  cells_pass2_kernel<<<g_t, 256, 0, c->stream>>>(P);
+  LAUNCH_CHECK("cells_pass2");
+
+  // order the cells by their nested first-occurrence key
+  CKR(ensure(c, S.sort_k[0], (size_t)n_cells * 8));
+  CKR(ensure(c, S.sort_v[0], (size_t)n_cells * 4));
+  const int g_c = grid_for(n_cells, 256, c->sm_count * 8);
+  cells_sort_input_kernel<<<g_c, 256, 0, c->stream>>>((const u64*)S.cell_key.p, n_cells, (u64*)S.sort_k[0].p, (u32*)S.sort_v[0].p);
+  LAUNCH_CHECK("cells_sort_input");
+  int rb = 0;
+  CKR(radix_sort(c, n_cells, 64, &rb));
+  CKR(ensure(c, S.flags, (size_t)n_cells * 4));
+  CKR(ensure(c, S.offsets, (size_t)n_cells * 4));
+  cells_keep_flags_kernel<<<g_c, 256, 0, c->stream>>>((const u64*)S.sort_k[rb].p, (const u32*)S.sort_v[rb].p, n_cells,
+                                                      (const u64*)S.cell_total.p, min_count, (u32*)S.flags.p);
+  LAUNCH_CHECK("cells_keep_flags");
+  u64 n_kept = 0;
+  CKR(device_scan<false>(c, (const u32*)S.flags.p, (u32*)S.offsets.p, n_cells, 0, &n_kept));
+  CKR(check_device_error(c));
+  if (n_kept == 0) return fail(c, ECB_ERR_EMPTY, "no cell reaches the minimum count %llu", (unsigned long long)min_count);
+  cr->n_kept_cells = (int64_t)n_kept;
+  cells_assign_kernel<<<g_c, 256, 0, c->stream>>>((const u64*)S.sort_k[rb].p, (const u32*)S.sort_v[rb].p, n_cells,
+                                                  (const u64*)S.cell_total.p, min_count, (const u32*)S.offsets.p,
+                                                  (int32_t*)S.cell_new.p, (int32_t*)c->r_cell_order.p);
+  LAUNCH_CHECK("cells_assign");
+  cells_ec_keep_kernel<<<grid_for(S.pair_slots, 256, c->sm_count * 8), 256, 0, c->stream>>>(P);
+  LAUNCH_CHECK("cells_ec_keep");
+  return ECB_OK;
+}
+
+// N matrix (CSC) from the kept (EC, cell) pairs (bam_utils_multisample.py:737-747,783-791).
+int cells_emit(ecb_ctx* c, CellResult* cr, const u32* ecid_of, u64 n_ec_final) {
+  CellScratch& S = c->cells;
+  CellParams P = make_cell_params(c, cr);
+  P.ecid_of = ecid_of;
+  const int g_p = grid_for(S.pair_slots, 256, c->sm_count * 8);
+  CKR(ensure(c, S.flags, (size_t)S.pair_slots * 4));
+  CKR(ensure(c, S.offsets, (size_t)S.pair_slots * 4));
+  cells_pair_flags_kernel<<<g_p, 256, 0, c->stream>>>(P, (u32*)S.flags.p);
+  LAUNCH_CHECK("cells_pair_flags");
+  u64 nnz = 0;
+  CKR(device_scan<false>(c, (const u32*)S.flags.p, (u32*)S.offsets.p, S.pair_slots, 0, &nnz));
+  if (nnz == 0 || nnz > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "N matrix has %llu non-zeros", (unsigned long long)nnz);
+  cr->nnz_n = (int64_t)nnz;
+  CKR(ensure(c, S.sort_k[0], (size_t)nnz * 8));
+  CKR(ensure(c, S.sort_v[0], (size_t)nnz * 4));
+  cells_pair_emit_kernel<<<g_p, 256, 0, c->stream>>>(P, (const u32*)S.flags.p, (const u32*)S.offsets.p,
+                                                     (u64*)S.sort_k[0].p, (u32*)S.sort_v[0].p);
+  LAUNCH_CHECK("cells_pair_emit");
+  int rb = 0;
+  CKR(radix_sort(c, (u32)nnz, 32 + bits_for((u64)cr->n_kept_cells), &rb));
+  (void)n_ec_final;
+  CKR(ensure(c, c->r_n_indptr, (size_t)(cr->n_kept_cells + 1) * 4));
+  CKR(ensure(c, c->r_n_indices, (size_t)nnz * 4));
+  CKR(ensure(c, c->r_n_data, (size_t)nnz * 4));
+  cells_csc_kernel<<<grid_for(nnz, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+      (const u64*)S.sort_k[rb].p, (const u32*)S.sort_v[rb].p, (u32)nnz, (u32)cr->n_kept_cells,
+      (int32_t*)c->r_n_indptr.p, (int32_t*)c->r_n_indices.p, (int32_t*)c->r_n_data.p);
+  LAUNCH_CHECK("cells_csc");
+  return ECB_OK;
+}
+
+void cells_release(ecb_ctx* c) {
+  CellScratch& S = c->cells;
+  DevBuf* bufs[] = {&S.fe_table, &S.pair_table, &S.cell_key, &S.cell_total, &S.cell_new, &S.sort_k[0], &S.sort_k[1],
+                    &S.sort_v[0], &S.sort_v[1], &S.hist, &S.flags, &S.offsets};
+  for (DevBuf* b : bufs) release(*b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ecb_version(void) { return 1000; }
+
+const char* ecb_last_error(const ecb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_cells, int64_t alignments_hint) {
+  ecb_ctx* c = nullptr;
+  if (!out) return fail(c, ECB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_targets < 1 || n_targets > ECB_MAX_TARGETS) return fail(c, ECB_ERR_INVALID, "n_targets %d outside [1, 2^26]", n_targets);
+  if (n_haps < 1 || n_haps > ECB_MAX_HAPS) return fail(c, ECB_ERR_INVALID, "n_haps %d outside [1, 31]", n_haps);
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(c, ECB_ERR_NO_DEVICE, "no CUDA device is visible; libecb200 has no CPU path");
+  if (device < 0 || device >= count) return fail(c, ECB_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(c, ECB_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(c, ECB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  ecb_ctx* ctx = new ecb_ctx();
+  c = ctx;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  c->n_targets = n_targets;
+  c->n_haps = n_haps;
+  c->with_cells = with_cells ? 1 : 0;
+  c->hint = std::max<int64_t>(alignments_hint, 0);
+  auto bail = [&](int code) {
+    g_create_error = c->err;
+    ecb_destroy(c);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaSetDevice failed"); return bail(ECB_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaStreamCreate failed"); return bail(ECB_ERR_CUDA); }
+  c->stream = c->own_stream;
+  for (auto& e : c->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaEventCreate failed"); return bail(ECB_ERR_CUDA); }
+  if (cudaMalloc(&c->d_ctr, sizeof(EcbCounters)) != cudaSuccess || cudaMallocHost(&c->h_ctr, sizeof(EcbCounters)) != cudaSuccess) {
+    fail(c, ECB_ERR_CUDA, "counter allocation failed");
+    return bail(ECB_ERR_CUDA);
+  }
+  *out = c;
+  return ECB_OK;
+}
+
+int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
+  if (!c) return ECB_ERR_INVALID;
+  switch (option) {
+    case ECB_OPT_RESULT_ON_DEVICE: c->result_on_device = value ? 1 : 0; break;
+    case ECB_OPT_TABLE_SLOTS:
+      if (c->table_slots) return fail(c, ECB_ERR_STATE, "table already allocated");
+      c->opt_table_slots = value; break;
+    case ECB_OPT_PAIR_SLOTS:
+      if (c->ttable_slots) return fail(c, ECB_ERR_STATE, "table already allocated");
+      c->opt_pair_slots = value; break;
+    case ECB_OPT_GRID_CTAS: c->opt_grid = value; break;
+    case ECB_OPT_WARP_AGGREGATE: c->warp_aggregate = value ? 1 : 0; break;
+    case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
+    default: return fail(c, ECB_ERR_INVALID, "unknown option %d", option);
+  }
+  return ECB_OK;
+}
+
+int ecb_set_stream(ecb_ctx* c, void* cuda_stream) {
+  if (!c) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  return ECB_OK;
+}
+
+int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, const int32_t* hap_idx,
+             const int32_t* cell_idx, int64_t n, int64_t order_base, int drop_last_group, int on_device) {
+  if (!c) return ECB_ERR_INVALID;
+  if (n < 0 || order_base < 0) return fail(c, ECB_ERR_INVALID, "negative n or order_base");
+  if (n > 0x7FFFFFFFll - 4 * ECB_TILE) return fail(c, ECB_ERR_LIMIT, "a push is limited to 2^31-4096 alignments; split it");
+  if (n > 0 && (!read_group || !target_idx || !hap_idx)) return fail(c, ECB_ERR_INVALID, "NULL column");
+  if (c->with_cells && n > 0 && !cell_idx) return fail(c, ECB_ERR_INVALID, "context has cells but cell_idx is NULL");
+  if (!c->with_cells && cell_idx) return fail(c, ECB_ERR_INVALID, "cell_idx given but context was created without cells");
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots) CKR(init_table(c));
+  const u32 push_id = c->push_count++;
+  if (n == 0) return ECB_OK;
+
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  const int32_t *rg = read_group, *tg = target_idx, *hp = hap_idx, *cell = cell_idx;
+  const size_t col_bytes = (size_t)n * 4;
+  auto misaligned = [](const void* p) { return ((uintptr_t)p & 15) != 0; };
+  const bool stage = !on_device || misaligned(rg) || misaligned(tg) || misaligned(hp);
+  if (stage) {
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    CKR(ensure(c, c->st_rg, col_bytes));
+    CKR(ensure(c, c->st_tg, col_bytes));
+    CKR(ensure(c, c->st_hp, col_bytes));
+    CK(cudaMemcpyAsync(c->st_rg.p, rg, col_bytes, kind, c->stream));
+    CK(cudaMemcpyAsync(c->st_tg.p, tg, col_bytes, kind, c->stream));
+    CK(cudaMemcpyAsync(c->st_hp.p, hp, col_bytes, kind, c->stream));
+    rg = (const int32_t*)c->st_rg.p; tg = (const int32_t*)c->st_tg.p; hp = (const int32_t*)c->st_hp.p;
+    if (cell) {
+      CKR(ensure(c, c->st_cell, col_bytes));
+      CK(cudaMemcpyAsync(c->st_cell.p, cell, col_bytes, kind, c->stream));
+      cell = (const int32_t*)c->st_cell.p;
+    }
+    if (!on_device) c->stats.h2d_bytes += (int64_t)col_bytes * (cell ? 4 : 3);
+  }
+
+  // capacity: keep the EC table at most half full before the push starts
+  while ((u64)c->n_ec * 2 > c->table_slots) CKR(grow_table(c, c->table_slots * 2));
+  if (c->with_cells) {
+    // the triple table must be able to absorb one new entry per alignment without filling up
+    u64 need = ((u64)c->n_triples + (u64)n) * 2;
+    if (need > c->ttable_slots) CKR(rebuild_triple_table(c, pow2_ceil(need), nullptr));
+  }
+  const size_t ov_words = ((size_t)n + 31) / 32;
+  CKR(ensure(c, c->overflow_bits, ov_words * 4));
+  CK(cudaMemsetAsync(c->overflow_bits.p, 0, ov_words * 4, c->stream));
+
+  const u32 e_before = c->n_ec;
+  GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
+  const int max_ctas = c->opt_grid > 0 ? (int)c->opt_grid : group_resident_ctas(c);
+  const int64_t tiles = (n + ECB_TILE - 1) / ECB_TILE;
+  const int grid = (int)std::min<int64_t>(tiles, max_ctas);
+  const int64_t tiles_per_cta = (tiles + grid - 1) / grid;
+  P.chunk_len = (int)(tiles_per_cta * ECB_TILE);
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_TILE_THREADS, 0, c->stream>>>(P);
+  else ecb_group_insert_kernel<false><<<grid, ECB_TILE_THREADS, 0, c->stream>>>(P);
+  LAUNCH_CHECK("group_insert");
+  CK(cudaEventRecord(c->ev[2], c->stream));
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
+  while (c->h_ctr->n_overflow) {  // table too full for some reads: grow, then replay just those
+    c->stats.overflow_reads += c->h_ctr->n_overflow;
+    if (c->table_slots >= (1u << 31)) return fail(c, ECB_ERR_LIMIT, "EC table cannot grow beyond 2^31 slots");
+    CKR(grow_table(c, c->table_slots * 4u > c->table_slots ? c->table_slots * 4u : (1u << 31)));
+    CK(cudaMemsetAsync(&c->d_ctr->n_overflow, 0, sizeof(u32), c->stream));
+    P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
+    const int rg_grid = grid_for(ov_words, 256, c->sm_count * 8);
+    if (c->with_cells) ecb_replay_kernel<true><<<rg_grid, 256, 0, c->stream>>>(P);
+    else ecb_replay_kernel<false><<<rg_grid, 256, 0, c->stream>>>(P);
+    LAUNCH_CHECK("replay");
+    CKR(sync_counters(c));
+    CKR(check_device_error(c));
+  }
+  if (c->h_ctr->n_triple_overflow) return fail(c, ECB_ERR_LIMIT, "(file, EC, cell) table ran out of probes");
+  c->n_ec = c->h_ctr->n_ec;
+  c->n_triples = c->h_ctr->n_triples;
+  CK(cudaEventRecord(c->ev[3], c->stream));
+  CKR(harvest_new_rows(c, rg, tg, hp, n, e_before, c->n_ec));
+  CK(cudaEventRecord(c->ev[4], c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.group_ms = ms;
+  CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats.harvest_ms = ms;
+  CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[4])); c->stats.push_ms = ms;
+
+  c->min_base = std::min<u64>(c->min_base, (u64)order_base);
+  c->max_end = std::max<u64>(c->max_end, (u64)order_base + (u64)n);
+  c->n_alignments += n;
+  c->stats.table_slots = c->table_slots;
+  c->stats.table_used = c->n_ec;
+  return ECB_OK;
+}
+
+int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
+  if (!c || !out) return ECB_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots || c->n_ec == 0) return fail(c, ECB_ERR_EMPTY, "no equivalence classes (nothing pushed)");
+  CK(cudaEventRecord(c->ev[0], c->stream));
+  CKR(sync_counters(c));
+  const u32 n_prov = c->n_ec;
+  const u64 span = c->max_end - c->min_base;
+  if (span > (1ull << 34)) return fail(c, ECB_ERR_LIMIT, "order_base range spans more than 2^34 positions");
+  const size_t words = (size_t)((span + 31) / 32) + 1;
+
+  CKR(ensure(c, c->bitmap, words * 4));
+  CKR(ensure(c, c->word_rank, words * 4));
+  CKR(ensure(c, c->first_rel, (size_t)n_prov * 8));
+  CKR(ensure(c, c->ecid_of, (size_t)n_prov * 4));
+  CK(cudaMemsetAsync(c->bitmap.p, 0, words * 4, c->stream));
+
+  FinalizeParams F{};
+  F.table = (const EcbEntry*)c->table.p;
+  F.ec_slot = (const u32*)c->ec_slot.p;
+  F.row_len = (const u32*)c->row_len.p;
+  F.row_off = (const u32*)c->row_off.p;
+  F.arena = (const uint2*)c->arena.p;
+  F.n_ec = n_prov;
+  F.min_base = c->min_base;
+  F.bitmap = (u32*)c->bitmap.p;
+  F.word_rank = (const u32*)c->word_rank.p;
+  F.first_rel = (u64*)c->first_rel.p;
+  F.ecid_of = (u32*)c->ecid_of.p;
+
+  CellResult cr{};
+  if (c->with_cells) {
+    CKR(cells_prepare(c, min_cell_count, &cr));   // cell order, kept cells, ec_keep flags
+    F.ec_keep = (const u32*)c->ec_keep.p;
+  }
+
+  const int g_ec = grid_for(n_prov, 256, c->sm_count * 8);
+  ecb_fin_mark_kernel<<<g_ec, 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_mark");
+  u64 n_kept = 0;
+  CKR(device_scan<true>(c, F.bitmap, (u32*)c->word_rank.p, words, 0, &n_kept));
+  if (n_kept == 0) return fail(c, ECB_ERR_EMPTY, "no equivalence class survives the cell filter");
+  if (!c->with_cells && n_kept != n_prov)
+    return fail(c, ECB_ERR_INVALID, "order_base ranges of different pushes overlap (%llu first positions for %u ECs)",
+                (unsigned long long)n_kept, n_prov);
+  const u64 E = n_kept;
+  if (E + 1 > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "more than 2^31 equivalence classes");
+
+  CKR(ensure(c, c->r_a_indptr, (E + 1) * 4));
+  F.a_indptr = (int32_t*)c->r_a_indptr.p;
+  if (!c->with_cells) {
+    CKR(ensure(c, c->r_n_indptr, 2 * 4));
+    CKR(ensure(c, c->r_n_indices, E * 4));
+    CKR(ensure(c, c->r_n_data, E * 4));
+    F.n_indices = (int32_t*)c->r_n_indices.p;
+    F.n_data = (int32_t*)c->r_n_data.p;
+  }
+  CK(cudaMemsetAsync((int32_t*)c->r_a_indptr.p + E, 0, 4, c->stream));
+  if (c->with_cells) ecb_fin_rank_kernel<false><<<g_ec, 256, 0, c->stream>>>(F);
+  else ecb_fin_rank_kernel<true><<<g_ec, 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_rank");
+  u64 Z = 0;
+  CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, E + 1, 0, &Z));
+  if (Z > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix has more than 2^31-1 non-zeros");
+  CKR(ensure(c, c->r_a_indices, std::max<u64>(Z, 1) * 4));
+  CKR(ensure(c, c->r_a_data, std::max<u64>(Z, 1) * 4));
+  F.a_indices = (int32_t*)c->r_a_indices.p;
+  F.a_data = (int32_t*)c->r_a_data.p;
+  ecb_fin_rows_kernel<<<grid_for((u64)n_prov * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_rows");
+
+  int64_t n_samples = 1, nnz_n = (int64_t)E;
+  if (c->with_cells) {
+    CKR(cells_emit(c, &cr, (const u32*)c->ecid_of.p, E));   // N matrix as CSC
+    n_samples = cr.n_kept_cells;
+    nnz_n = cr.nnz_n;
+  } else {
+    ecb_set_pair_kernel<<<1, 1, 0, c->stream>>>((int32_t*)c->r_n_indptr.p, 0, (int32_t)E);
+    LAUNCH_CHECK("set_pair");
+  }
+
+  out->n_ec = (int64_t)E;
+  out->nnz_a = (int64_t)Z;
+  out->n_samples = n_samples;
+  out->nnz_n = nnz_n;
+  out->n_reads = (int64_t)c->h_ctr->n_reads;
+  out->n_alignments = c->n_alignments;
+  if (c->result_on_device) {
+    out->a_indptr = (const int32_t*)c->r_a_indptr.p;
+    out->a_indices = (const int32_t*)c->r_a_indices.p;
+    out->a_data = (const int32_t*)c->r_a_data.p;
+    out->n_indptr = (const int32_t*)c->r_n_indptr.p;
+    out->n_indices = (const int32_t*)c->r_n_indices.p;
+    out->n_data = (const int32_t*)c->r_n_data.p;
+    out->cell_order = c->with_cells ? (const int32_t*)c->r_cell_order.p : nullptr;
+  } else {
+    const size_t sizes[7] = {(size_t)(E + 1) * 4, (size_t)Z * 4, (size_t)Z * 4, (size_t)(n_samples + 1) * 4,
+                             (size_t)nnz_n * 4, (size_t)nnz_n * 4, c->with_cells ? (size_t)n_samples * 4 : 0};
+    const void* src[7] = {c->r_a_indptr.p, c->r_a_indices.p, c->r_a_data.p, c->r_n_indptr.p,
+                          c->r_n_indices.p, c->r_n_data.p, c->r_cell_order.p};
+    size_t total = 0, offs[7];
+    for (int i = 0; i < 7; ++i) { offs[i] = total; total += (sizes[i] + 63) & ~(size_t)63; }
+    if (total > c->h_res_bytes) {
+      if (c->h_res) CK(cudaFreeHost(c->h_res));
+      c->h_res = nullptr;
+      c->h_res_bytes = 0;
+      CK(cudaMallocHost(&c->h_res, total + total / 4));
+      c->h_res_bytes = total + total / 4;
+    }
+    char* base = (char*)c->h_res;
+    for (int i = 0; i < 7; ++i)
+      if (sizes[i]) {
+        CK(cudaMemcpyAsync(base + offs[i], src[i], sizes[i], cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (int64_t)sizes[i];
+      }
+    out->a_indptr = (const int32_t*)(base + offs[0]);
+    out->a_indices = (const int32_t*)(base + offs[1]);
+    out->a_data = (const int32_t*)(base + offs[2]);
+    out->n_indptr = (const int32_t*)(base + offs[3]);
+    out->n_indices = (const int32_t*)(base + offs[4]);
+    out->n_data = (const int32_t*)(base + offs[5]);
+    out->cell_order = c->with_cells ? (const int32_t*)(base + offs[6]) : nullptr;
+  }
+  CK(cudaEventRecord(c->ev[1], c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->stats.finalize_ms = ms;
+  return ECB_OK;
+}
+
+int ecb_reset(ecb_ctx* c) {
+  if (!c) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (c->table_slots) {
+    CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
+    if (c->ttable_slots) CK(cudaMemsetAsync(c->ttable.p, 0xFF, (size_t)c->ttable_slots * sizeof(EcbEntry), c->stream));
+    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(EcbCounters), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  memset(c->h_ctr, 0, sizeof(EcbCounters));
+  c->n_ec = 0;
+  c->n_triples = 0;
+  c->arena_used = 0;
+  c->min_base = ~0ull;
+  c->max_end = 0;
+  c->n_alignments = 0;
+  c->push_count = 0;
+  const int64_t slots = c->stats.table_slots;
+  c->stats = ecb_stats{};
+  c->stats.table_slots = slots;
+  return ECB_OK;
+}
+
+int ecb_get_stats(const ecb_ctx* c, ecb_stats* out) {
+  if (!c || !out) return ECB_ERR_INVALID;
+  *out = c->stats;
+  out->table_slots = c->table_slots;
+  out->table_used = c->n_ec;
+  return ECB_OK;
+}
+
+int ecb_destroy(ecb_ctx* c) {
+  if (!c) return ECB_OK;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->row_len, &c->row_off, &c->arena, &c->long_list,
+                    &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->overflow_bits,
+                    &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
+                    &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,
+                    &c->r_n_data, &c->r_cell_order};
+  for (DevBuf* b : bufs) release(*b);
+  cells_release(c);
+  if (c->d_ctr) cudaFree(c->d_ctr);
+  if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  if (c->h_res) cudaFreeHost(c->h_res);
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return ECB_OK;
+}
+
+}  // extern "C"

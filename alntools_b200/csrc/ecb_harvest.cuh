@@ -1,0 +1,147 @@
+// ecb_harvest.cuh — turn the representative read of every NEW equivalence class into its canonical
+// row: distinct main targets ascending, data = OR of (1 << haplotype).
+//
+// Replaces alntools/bam_utils.py:788-825 (EC key -> per-haplotype (ec, target) COO lists) and the
+// canonicalisation scipy performs in alntools/bin_utils.py:208-211 (sum of 2^h * data[h], tocsr()
+// with sorted column indices).  Runs at the end of every push, while the caller's columns are still
+// valid, over the ECs claimed in that push only (E rows, not R reads).
+#pragma once
+#include "ecb_common.cuh"
+#include "ecb_scan.cuh"
+
+struct HarvestParams {
+  const int32_t* rg;
+  const int32_t* tg;
+  const int32_t* hp;
+  int n;
+  const u32* ec_rep;
+  u32 e0, e1;        // provisional ids claimed in this push
+  u32* row_len;      // [capacity] out: row length (upper bound for long reads after the count pass)
+  u32* row_off;      // [capacity] absolute offsets inside the arena
+  uint2* arena;      // (target, mask) pairs
+  u32* long_list;    // provisional ids whose representative read has more than 32 alignments
+  EcbCounters* ctr;
+};
+
+#define HARVEST_LONG_MAX 16384
+
+// Length of the read starting at s (warp-cooperative, all lanes get the result).
+__device__ __forceinline__ int warp_read_length(const int32_t* rg, int n, int s, int lane) {
+  const int my = rg[s];
+  int k = 0;
+  for (;;) {
+    const int j = s + k + lane;
+    const bool in = j < n && rg[j] == my;
+    const u32 b = __ballot_sync(ECB_FULL, in);
+    if (b == ECB_FULL) {
+      k += 32;
+    } else {
+      k += __ffs(~b) - 1;  // members form a prefix
+      break;
+    }
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(256) ecb_harvest_count_kernel(const HarvestParams P) {
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 e = P.e0 + warp_global; e < P.e1; e += n_warps) {
+    const int s = (int)P.ec_rep[e];
+    const int k = warp_read_length(P.rg, P.n, s, lane);
+    if (k <= 32) {
+      const int t = lane < k ? P.tg[s + lane] : -1 - lane;
+      const u32 grp = __match_any_sync(ECB_FULL, t);
+      const bool leader = lane < k && lane == __ffs(grp) - 1;
+      const u32 nd = __popc(__ballot_sync(ECB_FULL, leader));
+      if (lane == 0) P.row_len[e] = nd;
+    } else if (lane == 0) {
+      P.row_len[e] = (u32)k;
+      if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
+      const u32 idx = atomicAdd(&P.ctr->n_long, 1u);
+      P.long_list[idx] = e;
+    }
+  }
+}
+
+// Rows of reads with at most 32 alignments: one warp per EC, one alignment per lane.
+__global__ void __launch_bounds__(256) ecb_harvest_fill_kernel(const HarvestParams P) {
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 e = P.e0 + warp_global; e < P.e1; e += n_warps) {
+    const int s = (int)P.ec_rep[e];
+    const int k = warp_read_length(P.rg, P.n, s, lane);
+    if (k > 32) continue;
+    const int t = lane < k ? P.tg[s + lane] : -1 - lane;
+    const u32 hbit = lane < k ? (1u << P.hp[s + lane]) : 0u;
+    const u32 grp = __match_any_sync(ECB_FULL, t);
+    const u32 mask = __reduce_or_sync(grp, hbit);
+    const bool leader = lane < k && lane == __ffs(grp) - 1;
+    const u32 leaders = __ballot_sync(ECB_FULL, leader);
+    u32 rank = 0;
+    for (int j = 0; j < k; ++j) {
+      const int tj = __shfl_sync(ECB_FULL, t, j);
+      rank += ((leaders >> j) & 1u) && tj < t;
+    }
+    if (leader) P.arena[(size_t)P.row_off[e] + rank] = make_uint2((u32)t, mask);
+  }
+}
+
+// Rows of long reads (33 .. HARVEST_LONG_MAX alignments): one CTA per EC, bitonic sort of the element
+// codes in shared memory, then one entry per distinct target.
+__global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestParams P, u32 n_long) {
+  extern __shared__ u32 sm_codes[];
+  __shared__ u32 s_scan[9];
+  __shared__ u32 s_run;
+  for (u32 li = blockIdx.x; li < n_long; li += gridDim.x) {
+    const u32 e = P.long_list[li];
+    const int s = (int)P.ec_rep[e];
+    const u32 k = min(P.row_len[e], (u32)HARVEST_LONG_MAX);
+    u32 np2 = 64;
+    while (np2 < k) np2 <<= 1;
+    for (u32 i = threadIdx.x; i < np2; i += blockDim.x)
+      sm_codes[i] = i < k ? ecb_code(P.tg[s + i], P.hp[s + i]) : 0xFFFFFFFFu;
+    __syncthreads();
+    for (u32 size = 2; size <= np2; size <<= 1) {
+      for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+        for (u32 i = threadIdx.x; i < (np2 >> 1); i += blockDim.x) {
+          const u32 lo = 2 * i - (i & (stride - 1));
+          const u32 hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const u32 a = sm_codes[lo], b = sm_codes[hi];
+          if ((a > b) == up) {
+            sm_codes[lo] = b;
+            sm_codes[hi] = a;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const size_t out0 = (size_t)P.row_off[e];
+    for (u32 base = 0; base < k; base += blockDim.x) {
+      const u32 i = base + threadIdx.x;
+      bool start = false;
+      u32 code = 0xFFFFFFFFu;
+      if (i < k) {
+        code = sm_codes[i];
+        start = (i == 0) || ((sm_codes[i - 1] >> 5) != (code >> 5));
+      }
+      u32 total;
+      const u32 excl = block_excl_scan_u32(start ? 1u : 0u, s_scan, total);
+      if (start) {
+        u32 mask = 0;
+        for (u32 j = i; j < k && (sm_codes[j] >> 5) == (code >> 5); ++j) mask |= 1u << (sm_codes[j] & 31u);
+        P.arena[out0 + s_run + excl] = make_uint2(code >> 5, mask);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) s_run += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) P.row_len[e] = s_run;
+    __syncthreads();
+  }
+}

@@ -1,0 +1,56 @@
+"""Host-side helpers that mirror alntools/utils.py (logging, partition, parse_targets)."""
+from collections import OrderedDict
+import logging
+
+LOG = None
+
+
+def get_logger():
+    """Same logger name as the reference (utils.py:21-30) so log capture keeps working."""
+    global LOG
+    if LOG is None:
+        LOG = logging.getLogger("alntools.utils")
+        LOG.addHandler(logging.NullHandler())
+    return LOG
+
+
+def configure_logging(level):
+    """utils.py:33-48: 0 -> WARNING, 1 -> INFO, >=2 -> DEBUG."""
+    log = get_logger()
+    if not any(isinstance(h, logging.StreamHandler) and not isinstance(h, logging.NullHandler)
+               for h in log.handlers):
+        handler = logging.StreamHandler()
+        handler.setFormatter(logging.Formatter("[alntools] %(message)s"))
+        log.addHandler(handler)
+    log.setLevel(logging.WARNING if level <= 0 else logging.INFO if level == 1 else logging.DEBUG)
+
+
+def format_time(start, end):
+    """utils.py:51-64."""
+    hours, rem = divmod(end - start, 3600)
+    minutes, seconds = divmod(rem, 60)
+    return "{:0>2}:{:0>2}:{:05.2f}".format(int(hours), int(minutes), seconds)
+
+
+def partition(lst, n):
+    """utils.py:67-87: contiguous runs, never an empty trailing partition."""
+    q, r = divmod(len(lst), n)
+    bounds = [q * i + min(i, r) for i in range(n + 1)]
+    parts = []
+    for i in range(n):
+        piece = lst[bounds[i]:bounds[i + 1]]
+        if len(piece) == 0:
+            break
+        parts.append(piece)
+    return parts
+
+
+def parse_targets(target_file):
+    """utils.py:161-178: first whitespace token of every non-'#' line, in file order."""
+    targets = OrderedDict()
+    with open(target_file, "r") as fh:
+        for line in fh:
+            if line and line[0] == "#":
+                continue
+            targets[line.strip().split()[0]] = len(targets)
+    return targets

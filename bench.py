@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — bam2ec EC-build throughput (alignments/s) on B200, per the driver contract.
+
+One "step" = one pass of the hot path over one batch of synthetic, name-grouped alignment columns:
+ecb_reset -> ecb_push (grouping + hash insert + row harvest) -> ecb_finalize (EC ids, CSR A, CSC N).
+
+  value : whole-job alignments/s with the columns already resident in HBM and results left in HBM
+  e2e   : the same through the public C-ABI call with HOST (pinned) columns and host results;
+          H2D and D2H copies are inside the timed region
+  roofline     : the grouping kernel against the measured HBM copy bandwidth
+  cpu_baseline : the oracle's Python port of the reference's per-alignment loop on the host cores,
+                 on a bounded sample of the same workload (rank 0, N=1 only)
+
+`--impl reference` times that CPU port as its own arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: diploid F1 mouse, 2 haplotypes x ~100k transcripts, 30M reads, 1 B200
+    "cfg2_diploid_30M": dict(n_reads=30_000_000, n_targets=100_000, n_haps=2, mode="diploid", seed=2),
+    "cfg1_small_1M": dict(n_reads=1_000_000, n_targets=2_000, n_haps=2, mode="light", seed=1),
+    "cfg3_do8_heavy": dict(n_reads=3_000_000, n_targets=140_000, n_haps=8, mode="heavy", seed=3),
+}
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's port of the reference's own multiprocessing bam2ec path
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(bam_path):
+    from alntools_b200 import bam_io
+    from oracle import ec_oracle
+    raw = bam_io.inflate_file(bam_path)
+    header = bam_io.parse_header(raw)
+    res = ec_oracle.group_chunk_single(bam_io.iter_records(raw, header.records_offset))
+    return res.ec, res.valid_alignments
+
+
+def make_cpu_sample(workdir, wl, sample_reads, n_procs):
+    """A bounded sample of the workload as `n_procs` read-aligned chunk BAMs (the reference also
+    materialises one temporary BAM per chunk, bam_utils.py:247-250)."""
+    import numpy as np
+    from alntools_b200 import bam_io, synth
+    cols = synth.make_columns(sample_reads, wl["n_targets"], wl["n_haps"], wl["seed"] + 1000, mode=wl["mode"])
+    rg = cols["read_group"]
+    tids = cols["target_idx"].astype(np.int64) * wl["n_haps"] + cols["hap_idx"]
+    refs = synth.reference_names(wl["n_targets"], wl["n_haps"])
+    cuts = [0]
+    for k in range(1, n_procs):
+        c = len(rg) * k // n_procs
+        while c < len(rg) and rg[c] == rg[c - 1]:
+            c += 1
+        cuts.append(c)
+    cuts.append(len(rg))
+    paths = []
+    for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        p = os.path.join(workdir, "chunk%03d.bam" % i)
+        bam_io.write_bam_columns(p, refs, rg[a:b], np.zeros(b - a, dtype=np.uint16), tids[a:b], level=1)
+        paths.append(p)
+    return paths, refs, len(rg)
+
+
+def cpu_step(paths, refs, pool):
+    """One pass of the reference algorithm: per-chunk grouping in a process pool, ordered merge,
+    EC -> matrix, EC-file bytes.  Returns (alignments, seconds)."""
+    from oracle import ec_oracle
+    t0 = time.perf_counter()
+    results = pool.map(_cpu_worker, paths) if pool is not None else [_cpu_worker(p) for p in paths]
+    ec = {}
+    valid = 0
+    for part, v in results:
+        valid += v
+        for k, c in part.items():
+            ec[k] = ec.get(k, 0) + c
+    tables = ec_oracle.HeaderTables([r[0] for r in refs], [r[1] for r in refs])
+    a_csr = ec_oracle.a_matrix_from_keys(list(ec.keys()), tables)
+    n_csc = ec_oracle.n_matrix_single(list(ec.values()))
+    blob = ec_oracle.ecsave2_bytes(tables.haplotypes, list(tables.main_targets.keys()), tables.lengths,
+                                   ["sample"], a_csr, n_csc)
+    assert len(blob) > 0
+    return valid, time.perf_counter() - t0
+
+
+def run_cpu_arm(wl_name, steps, warmup, sample_reads, max_seconds=240.0):
+    import multiprocessing
+    wl = WORKLOADS[wl_name]
+    n_procs = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory(prefix="ecb_cpu_") as tmp:
+        paths, refs, n_aln = make_cpu_sample(tmp, wl, sample_reads, n_procs)
+        ctx = multiprocessing.get_context("fork")
+        with ctx.Pool(n_procs) as pool:
+            for _ in range(warmup):
+                cpu_step(paths, refs, pool)
+            total_aln, total_s = 0, 0.0
+            done = 0
+            for _ in range(steps):
+                a, s = cpu_step(paths, refs, pool)
+                total_aln += a
+                total_s += s
+                done += 1
+                if total_s > max_seconds:
+                    break
+    return {"value": total_aln / total_s, "unit": "alignments/s", "cores": n_procs, "kind": "port",
+            "sample": "%d reads / %d alignments of %s as %d chunk BAMs; decode + group + merge + matrix + EC bytes, "
+                      "oracle Python port of bam_utils.convert, %d timed passes" % (sample_reads, n_aln, wl_name,
+                                                                                    n_procs, done),
+            "ms_per_step": 1e3 * total_s / max(done, 1), "steps_done": done}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2_diploid_30M", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table-slots", type=int, default=0)
+    ap.add_argument("--grid-ctas", type=int, default=0)
+    ap.add_argument("--warp-aggregate", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    config = {"workload": args.workload, "reads_per_gpu": wl["n_reads"], "n_targets": wl["n_targets"],
+              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU",
+              "l2": "inputs (>= 700 MB per GPU) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cpu = run_cpu_arm(args.workload, max(args.steps, 1), min(args.warmup, 1), args.cpu_sample_reads)
+        line = {"impl": "reference", "metric": "bam2ec alignments/sec (EC build)", "value": cpu["value"],
+                "unit": "alignments/s", "n_gpus": args.gpus, "steps": cpu["steps_done"], "warmup": min(args.warmup, 1),
+                "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": config, "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "alignments/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from alntools_b200 import synth
+    from alntools_b200._native import EcBuilder
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path for the EC build")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- synthetic shard of this rank (weak scaling: fixed reads per GPU) --------------------------
+    cols = synth.make_columns(wl["n_reads"], wl["n_targets"], wl["n_haps"], wl["seed"] + 7919 * rank, mode=wl["mode"])
+    n_aln = int(len(cols["read_group"]))
+    names = ("read_group", "target_idx", "hap_idx")
+    host = {k: torch.from_numpy(cols[k]).pin_memory() for k in names}
+    dev = {k: host[k].cuda(non_blocking=True) for k in names}
+    torch.cuda.synchronize()
+    order_base = 0
+    if world > 1:
+        counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        counts[rank] = n_aln
+        dist.all_reduce(counts)
+        order_base = int(counts[:rank].sum().item())
+        total_aln = int(counts.sum().item())
+    else:
+        total_aln = n_aln
+
+    opts = {}
+    if args.table_slots:
+        opts["table_slots"] = args.table_slots
+    if args.grid_ctas:
+        opts["grid_ctas"] = args.grid_ctas
+    opts["warp_aggregate"] = args.warp_aggregate
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(builder, columns, steps, finalize):
+        """K steps bracketed by barrier + synchronize, CUDA events on the library's stream."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        group_ms = []
+        e0.record(stream)
+        for _ in range(steps):
+            builder.reset()
+            builder.push(columns["read_group"], columns["target_idx"], columns["hap_idx"], order_base=order_base)
+            res = finalize(builder)
+            group_ms.append(builder.stats()["group_ms"])
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, res, group_ms
+
+    # ---- device-resident arm ("value") --------------------------------------------------------------
+    b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
+                      result_on_device=1, **opts)
+    b_dev.set_stream(stream.cuda_stream)
+    timed(b_dev, dev, args.warmup, lambda b: b.finalize_raw())
+    launches0 = b_dev.stats()["kernel_launches"]
+    with ClockSampler(local_rank) as clocks:
+        ms_dev, res_dev, group_ms = timed(b_dev, dev, args.steps, lambda b: b.finalize_raw())
+    stats_dev = b_dev.stats()
+    launches_per_step = stats_dev["kernel_launches"]  # stats are zeroed by reset(): this is the last step
+    n_ec, nnz_a = int(res_dev.n_ec), int(res_dev.nnz_a)
+    b_dev.close()
+    del launches0
+
+    # ---- end-to-end arm: host columns in, host matrices out ----------------------------------------
+    b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank, **opts)
+    b_e2e.set_stream(stream.cuda_stream)
+    timed(b_e2e, host, 1, lambda b: b.finalize_raw())
+    ms_e2e, res_e2e, _ = timed(b_e2e, host, args.steps, lambda b: b.finalize_raw())
+    stats_e2e = b_e2e.stats()
+    assert int(res_e2e.n_ec) == n_ec
+    b_e2e.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_kind = measured_peak_gbs()
+    gms = sorted(group_ms)[len(group_ms) // 2]
+    algo_bytes = 12.0 * n_aln  # three int32 columns read once by the grouping kernel
+    achieved = algo_bytes / (gms * 1e-3) / 1e9
+    line = {
+        "metric": "bam2ec alignments/sec (EC build)",
+        "value": total_aln * args.steps / (ms_dev * 1e-3),
+        "unit": "alignments/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "int32",
+        "data": "synthetic",
+        "config": dict(config, alignments_per_gpu=n_aln, n_ec=n_ec, nnz_a=nnz_a,
+                       table_slots=stats_dev["table_slots"], table_grows=stats_dev["table_grows"]),
+        "e2e": {"value": total_aln * args.steps / (ms_e2e * 1e-3), "unit": "alignments/s",
+                "h2d_bytes_per_step": stats_e2e["h2d_bytes"], "d2h_bytes_per_step": stats_e2e["d2h_bytes"],
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "ecb_group_insert_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": gms,
+                     "kernel_share_of_step": gms / (ms_dev / args.steps)},
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = run_cpu_arm(args.workload, 2, 0, args.cpu_sample_reads, max_seconds=60.0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,149 @@
+/*
+ * ecb200.h — C ABI of libecb200.so: B200 (sm_100a) equivalence-class builder for alntools bam2ec.
+ *
+ * The reference (churchill-lab/alntools) is pure Python and has no FFI; the seam this library
+ * replaces is the body of its per-alignment grouping loop, the chunk merge, the EC -> COO loop and
+ * the scipy canonicalisation, fed with int32 columns instead of pysam objects:
+ *
+ *   ecb_push      replaces  alntools/bam_utils.py:258-344  (process_convert_bam hot loop: group by
+ *                           read, set of tids per read, ec[key] += 1) and the chunk-ordered merge
+ *                           alntools/bam_utils.py:680-698 (EC id = rank of first occurrence);
+ *                           with cells: alntools/bam_utils_multisample.py:209-300 and :503-560.
+ *   ecb_finalize  replaces  alntools/bam_utils.py:788-847 (EC -> per-haplotype COO -> APM) plus the
+ *                           matrix part of alntools/bin_utils.py:208-232,246-275 (sum 2^h*data[h],
+ *                           tocsr, N as CSC); with cells: bam_utils_multisample.py:595-636,702-791.
+ *
+ * Host code (alntools_b200/*.py) keeps the reference's convert()/methods/CLI signatures, decodes
+ * the BAM, applies the filters (bam_utils.py:264-270) and the read-name comparison (:301-306), and
+ * hands over columns.  No torch types cross this boundary: plain pointers and sizes only.
+ *
+ * All functions return 0 on success and a negative ecb_status on failure; the message is available
+ * through ecb_last_error().  Nothing here ever falls back to a CPU implementation.
+ *
+ * Threading: a context is bound to one CUDA device and one stream and is not thread-safe; use one
+ * context per GPU.  Calls block the calling thread until the work they describe is finished unless
+ * stated otherwise (ctypes releases the GIL around them).
+ */
+#ifndef ECB200_H
+#define ECB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ecb_ctx ecb_ctx;
+
+enum ecb_status {
+  ECB_OK = 0,
+  ECB_ERR_INVALID = -1,     /* bad argument / contract violation */
+  ECB_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string) */
+  ECB_ERR_NO_DEVICE = -3,   /* no usable sm_100 device */
+  ECB_ERR_LIMIT = -4,       /* a format limit was exceeded (int32 file fields, read too long, ...) */
+  ECB_ERR_EMPTY = -5,       /* finalize with zero equivalence classes (the reference raises too:
+                               alntools/matrix/Sparse3DMatrix.py:45-46) */
+  ECB_ERR_STATE = -6        /* call sequence error */
+};
+
+/* Longest read (alignments sharing one name) whose canonical row can be built. */
+#define ECB_MAX_READ_ALIGNMENTS 16384
+/* target_idx < 2^26 and hap_idx < 31 (the EC file stores the haplotype mask in an int32,
+ * alntools/bin_utils.py:232). */
+#define ECB_MAX_TARGETS (1 << 26)
+#define ECB_MAX_HAPS 31
+
+enum ecb_option {
+  ECB_OPT_RESULT_ON_DEVICE = 1, /* 1: ecb_result pointers are DEVICE pointers (no D2H copy) */
+  ECB_OPT_TABLE_SLOTS = 2,      /* initial EC hash-table capacity (rounded up to a power of two) */
+  ECB_OPT_PAIR_SLOTS = 3,       /* initial (file, EC, cell) table capacity */
+  ECB_OPT_GRID_CTAS = 4,        /* CTAs of the grouping kernel (0 = resident CTAs x SMs) */
+  ECB_OPT_WARP_AGGREGATE = 5,   /* 1 (default): combine equal keys inside a warp before the atomics */
+  ECB_OPT_VERIFY_KEYS = 6       /* 1: finalize re-derives every read's row and compares it with its
+                                   EC's row, turning a 128-bit hash collision into an error */
+};
+
+typedef struct ecb_result {
+  int64_t n_ec;              /* E: number of equivalence classes (after the cell filter)          */
+  int64_t nnz_a;             /* Z                                                                 */
+  const int32_t* a_indptr;   /* [E+1]  CSR row offsets of the A matrix (E x T)                    */
+  const int32_t* a_indices;  /* [Z]    main-target index, ascending inside a row                  */
+  const int32_t* a_data;     /* [Z]    haplotype bitmask, bit h = sorted-haplotype index h        */
+  int64_t n_samples;         /* S: 1 without cells; number of kept cells with cells               */
+  int64_t nnz_n;
+  const int32_t* n_indptr;   /* [S+1]  CSC column offsets of the N matrix (E x S)                 */
+  const int32_t* n_indices;  /* [nnz_n] EC ids, ascending inside a column                         */
+  const int32_t* n_data;     /* [nnz_n] read counts                                               */
+  const int32_t* cell_order; /* [S] original cell_idx of every output column; NULL without cells  */
+  int64_t n_reads;           /* reads counted over all pushes (after drop_last_group)             */
+  int64_t n_alignments;      /* alignments pushed                                                 */
+} ecb_result;
+
+typedef struct ecb_stats {
+  double group_ms;        /* device time of the grouping/insert kernel(s) of the last push        */
+  double harvest_ms;      /* device time of the row-harvest kernels of the last push              */
+  double push_ms;         /* device time of the whole last push (incl. H2D when host pointers)    */
+  double finalize_ms;     /* device time of the last finalize (incl. D2H unless result on device) */
+  int64_t kernel_launches;/* kernels launched by this library since create/reset                  */
+  int64_t table_slots;    /* current EC table capacity                                            */
+  int64_t table_used;     /* ECs in the table                                                     */
+  int64_t table_grows;    /* rehash events                                                        */
+  int64_t overflow_reads; /* reads that had to be replayed after a table growth                   */
+  int64_t h2d_bytes;      /* bytes copied host->device since create/reset                         */
+  int64_t d2h_bytes;      /* bytes copied device->host since create/reset                         */
+} ecb_stats;
+
+/* Library/ABI version (major*1000 + minor). */
+int ecb_version(void);
+
+/* Create a context on CUDA device `device`.  n_targets/n_haps bound the column values;
+ * with_cells selects the per-cell (multisample) path; alignments_hint sizes tables and staging. */
+int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_cells,
+               int64_t alignments_hint);
+
+int ecb_set_option(ecb_ctx* ctx, int option, int64_t value);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*),
+ * e.g. torch.cuda.current_stream().cuda_stream.  NULL restores the context's own stream. */
+int ecb_set_stream(ecb_ctx* ctx, void* cuda_stream);
+
+/*
+ * Push one contiguous run of VALID alignments (already filtered, name-grouped).
+ *   read_group[n]  consecutive equal values form one read; values only need to change between reads
+ *   target_idx[n]  main-target index of the alignment's reference   (0 <= v < n_targets)
+ *   hap_idx[n]     index into the SORTED haplotype list             (0 <= v < n_haps)
+ *   cell_idx[n]    cell id of the alignment's read (value on the read's first alignment is used);
+ *                  NULL unless the context was created with_cells
+ *   order_base     global index of this push's first alignment in reference read order: EC ids are
+ *                  ranked by order_base + offset of the EC's first read, so pushes/shards may arrive
+ *                  in any order as long as their [order_base, order_base+n) ranges do not overlap
+ *   drop_last_group 1 reproduces alntools/bam_utils_multisample.py:306-308 (the last read of a file
+ *                  is never flushed); one push = one file in that case
+ *   on_device      0: host pointers (pinned preferred, copied with cudaMemcpyAsync);
+ *                  1: device pointers on this context's device
+ * Reads must not span pushes.  Buffers are caller-owned and may be reused after return.
+ */
+int ecb_push(ecb_ctx* ctx, const int32_t* read_group, const int32_t* target_idx,
+             const int32_t* hap_idx, const int32_t* cell_idx, int64_t n, int64_t order_base,
+             int drop_last_group, int on_device);
+
+/* Build the A (CSR) and N (CSC) matrices.  min_cell_count follows
+ * alntools/bam_utils_multisample.py:596-608 (<=0 means 1; ignored without cells).
+ * Result buffers are library-owned (pinned host memory, or device memory with
+ * ECB_OPT_RESULT_ON_DEVICE) and stay valid until the next finalize/reset/destroy. */
+int ecb_finalize(ecb_ctx* ctx, int64_t min_cell_count, ecb_result* out);
+
+/* Forget all pushed data but keep allocations (tables, staging) for the next job. */
+int ecb_reset(ecb_ctx* ctx);
+
+int ecb_get_stats(const ecb_ctx* ctx, ecb_stats* out);
+
+int ecb_destroy(ecb_ctx* ctx);
+
+/* Message of the last failing call on this context (or of ecb_create when ctx is NULL). */
+const char* ecb_last_error(const ecb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECB200_H */

@@ -1,0 +1,274 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libecb200.so), against the
+oracle on the same seeded inputs, against the reference's golden EC files, and - at BASELINE.json's
+full sizes - through size-independent properties plus the C oracle.  Bit-exact everywhere (integer work)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native(built):
+    import torch
+    assert torch.cuda.is_available(), "these tests need a B200"
+    from alntools_b200 import _native
+    _native.load_library()
+    return _native
+
+
+def _oracle(cols, drop_last=False):
+    from oracle import c_oracle
+    return c_oracle.ec_from_columns(cols["read_group"], cols["target_idx"], cols["hap_idx"], drop_last)
+
+
+def _assert_same(got, want):
+    indptr, indices, data, counts, n_reads = want
+    assert got["n_reads"] == n_reads
+    assert got["n_ec"] == len(counts)
+    assert np.array_equal(got["a_indptr"], indptr)
+    assert np.array_equal(got["a_indices"], indices)
+    assert np.array_equal(got["a_data"], data)
+    assert np.array_equal(got["n_data"], counts)
+    assert got["n_indptr"].tolist() == [0, len(counts)]
+    assert np.array_equal(got["n_indices"], np.arange(len(counts), dtype=np.int32))
+
+
+def _run(native, cols, n_targets, n_haps, **options):
+    with native.EcBuilder(n_targets, n_haps, alignments_hint=len(cols["read_group"]), **options) as b:
+        b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"])
+        return b.finalize(), b.stats()
+
+
+# ---------------------------------------------------------------- golden files (reference outputs)
+@pytest.mark.parametrize("case", golden_cases("single"), ids=lambda c: c["name"])
+def test_convert_reproduces_reference_file_single(native, case, tmp_path):
+    from alntools_b200 import bam_utils
+    out = str(tmp_path / "out.bin")
+    tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+    bam_utils.convert(os.path.join(GOLDEN, case["bam"]), out, None, num_chunks=1, number_processes=1,
+                      target_filename=tfile)
+    with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+        assert a.read() == b.read()
+
+
+@pytest.mark.parametrize("case", golden_cases("multisample"), ids=lambda c: c["name"])
+def test_convert_reproduces_reference_file_multisample(native, case, tmp_path):
+    from alntools_b200 import bam_utils_multisample
+    out = str(tmp_path / "out.bin")
+    files = [os.path.join(GOLDEN, case["dir"], fn) for fn in case["file_order"]]
+    bam_utils_multisample.convert_files(files, out, None, case["mincount"])
+    with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+        assert a.read() == b.read()
+
+
+# ---------------------------------------------------------------- seeded columns vs the oracle
+@pytest.mark.parametrize("n_reads,n_targets,n_haps,mode,dup", [
+    (1, 5, 2, "light", 0.0),
+    (7, 5, 2, "light", 0.5),
+    (1000, 50, 2, "light", 0.05),          # tiny target space: few, very hot ECs
+    (1023, 300, 2, "diploid", 0.0),
+    (50000, 2000, 2, "light", 0.02),       # cfg1 shape, scaled down
+    (200000, 2000, 2, "diploid", 0.02),
+    (30000, 1500, 8, "heavy", 0.01),       # reads longer than a warp and than a tile
+    (4000, 1000, 8, 64, 0.0),              # fixed 64 transcripts per read (cfg5)
+    (300000, 100000, 2, "diploid", 0.0),   # cfg2 shape, scaled down
+])
+def test_columns_match_oracle(native, n_reads, n_targets, n_haps, mode, dup):
+    from alntools_b200 import synth
+    cols = synth.make_columns(n_reads, n_targets, n_haps, seed=n_reads % 97 + 1, mode=mode, dup_rate=dup)
+    got, _ = _run(native, cols, n_targets, n_haps)
+    _assert_same(got, _oracle(cols))
+
+
+def test_tile_and_chunk_boundaries(native):
+    """Sizes around the 1024-alignment tile and reads that straddle tile / CTA-chunk boundaries."""
+    from alntools_b200 import synth
+    for n_reads in (340, 341, 342, 512, 1024, 1025, 2047, 2048, 2049, 4096):
+        cols = synth.make_columns(n_reads, 40, 3, seed=n_reads, mode="diploid", dup_rate=0.1)
+        for grid in (0, 1, 3):
+            got, _ = _run(native, cols, 40, 3, grid_ctas=grid)
+            _assert_same(got, _oracle(cols))
+    # exactly one tile, exactly two tiles, one alignment per read
+    for n in (1024, 2048, 3072):
+        rg = np.arange(n, dtype=np.int32)
+        cols = {"read_group": rg, "target_idx": (rg % 7).astype(np.int32), "hap_idx": (rg % 2).astype(np.int32)}
+        got, _ = _run(native, cols, 7, 2, grid_ctas=2)
+        _assert_same(got, _oracle(cols))
+
+
+def test_giant_read_spanning_many_tiles(native):
+    """One read of 5000 alignments (> 4 tiles) between ordinary reads; 5000 <= ECB_MAX_READ_ALIGNMENTS."""
+    rng = np.random.default_rng(3)
+    rg = np.concatenate([np.repeat(np.arange(300), 3), np.full(5000, 300), np.repeat(np.arange(301, 700), 2)])
+    tg = rng.integers(0, 900, len(rg))
+    hp = rng.integers(0, 4, len(rg))
+    cols = {"read_group": rg.astype(np.int32), "target_idx": tg.astype(np.int32), "hap_idx": hp.astype(np.int32)}
+    for grid in (0, 2, 5):
+        got, _ = _run(native, cols, 900, 4, grid_ctas=grid)
+        _assert_same(got, _oracle(cols))
+
+
+def test_read_longer_than_the_limit_is_an_error(native):
+    n = 16384 + 40
+    cols = {"read_group": np.zeros(n, np.int32), "target_idx": (np.arange(n) % 30000).astype(np.int32),
+            "hap_idx": np.zeros(n, np.int32)}
+    with native.EcBuilder(30000, 1) as b:
+        with pytest.raises(native.EcbError) as info:
+            b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"])
+            b.finalize()
+    assert info.value.code == -4
+
+
+def test_out_of_range_values_are_an_error(native):
+    with native.EcBuilder(10, 2) as b:
+        with pytest.raises(native.EcbError) as info:
+            b.push(np.array([0, 1], np.int32), np.array([3, 10], np.int32), np.array([0, 1], np.int32))
+    assert info.value.code == -1
+
+
+def test_empty_input_raises_like_the_reference(native):
+    with native.EcBuilder(10, 2) as b:
+        e = np.zeros(0, np.int32)
+        b.push(e, e, e)
+        with pytest.raises(native.EcbError) as info:
+            b.finalize()
+    assert info.value.code == native.ECB_ERR_EMPTY
+
+
+def test_table_growth_and_overflow_replay(native):
+    """A deliberately tiny table forces probe exhaustion, growth (rehash) and the replay kernel."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(60000, 20000, 2, seed=21, mode="diploid")
+    got, stats = _run(native, cols, 20000, 2, table_slots=1024)
+    _assert_same(got, _oracle(cols))
+    assert stats["table_grows"] >= 1 and stats["overflow_reads"] > 0
+
+
+def test_warp_aggregation_off_gives_the_same_result(native):
+    from alntools_b200 import synth
+    cols = synth.make_columns(40000, 300, 2, seed=22, mode="light", dup_rate=0.02)
+    a, _ = _run(native, cols, 300, 2, warp_aggregate=1)
+    b, _ = _run(native, cols, 300, 2, warp_aggregate=0)
+    for k in ("a_indptr", "a_indices", "a_data", "n_data"):
+        assert np.array_equal(a[k], b[k])
+    _assert_same(a, _oracle(cols))
+
+
+def test_multiple_pushes_equal_one_push(native):
+    """Chunk independence (bam_utils.py:680-698): pushing read-aligned pieces with their order_base
+    gives the same matrices as one push, in any arrival order."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(50000, 3000, 2, seed=23, mode="diploid", dup_rate=0.02)
+    rg = cols["read_group"]
+    want = _oracle(cols)
+    cuts = [0]
+    for k in range(1, 5):
+        c = len(rg) * k // 5
+        while rg[c] == rg[c - 1]:
+            c += 1
+        cuts.append(c)
+    cuts.append(len(rg))
+    pieces = list(zip(cuts[:-1], cuts[1:]))
+    for order in (pieces, pieces[::-1], [pieces[2], pieces[0], pieces[4], pieces[1], pieces[3]]):
+        with native.EcBuilder(3000, 2, alignments_hint=len(rg)) as b:
+            for a, e in order:
+                b.push(np.ascontiguousarray(rg[a:e]), np.ascontiguousarray(cols["target_idx"][a:e]),
+                       np.ascontiguousarray(cols["hap_idx"][a:e]), order_base=a)
+            _assert_same(b.finalize(), want)
+
+
+def test_overlapping_order_bases_are_detected(native):
+    from alntools_b200 import synth
+    cols = synth.make_columns(2000, 3000, 2, seed=24, mode="light")
+    with native.EcBuilder(3000, 2) as b:
+        b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"], order_base=0)
+        b.push(cols["read_group"], (cols["target_idx"] + 1) % 3000, cols["hap_idx"], order_base=0)
+        with pytest.raises(native.EcbError):
+            b.finalize()
+
+
+def test_device_resident_columns_and_results(native):
+    """on_device=1 pushes (torch only hands over device pointers), incl. a 4-byte-misaligned view."""
+    import torch
+    from alntools_b200 import synth
+    cols = synth.make_columns(80000, 5000, 2, seed=25, mode="diploid", dup_rate=0.01)
+    want = _oracle(cols)
+    dev = {k: torch.from_numpy(cols[k]).cuda() for k in ("read_group", "target_idx", "hap_idx")}
+    with native.EcBuilder(5000, 2, alignments_hint=len(cols["read_group"])) as b:
+        b.push(dev["read_group"], dev["target_idx"], dev["hap_idx"])
+        _assert_same(b.finalize(), want)
+        b.reset()
+        pad = {k: torch.cat([torch.zeros(1, dtype=torch.int32, device="cuda"), v])[1:] for k, v in dev.items()}
+        assert pad["read_group"].data_ptr() % 16 != 0
+        b.push(pad["read_group"], pad["target_idx"], pad["hap_idx"])
+        _assert_same(b.finalize(), want)
+    with native.EcBuilder(5000, 2, alignments_hint=len(cols["read_group"]), result_on_device=1) as b:
+        b.push(dev["read_group"], dev["target_idx"], dev["hap_idx"])
+        res = b.finalize_raw()
+        assert res.n_ec == len(want[3]) and res.nnz_a == len(want[1])
+
+
+def test_reset_reuses_the_context(native):
+    from alntools_b200 import synth
+    with native.EcBuilder(500, 2) as b:
+        for seed in (31, 32, 33):
+            cols = synth.make_columns(20000, 500, 2, seed=seed, mode="light", dup_rate=0.02)
+            b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"])
+            _assert_same(b.finalize(), _oracle(cols))
+            b.reset()
+
+
+def test_drop_last_group(native):
+    from alntools_b200 import synth
+    cols = synth.make_columns(5000, 200, 2, seed=34, mode="diploid")
+    with native.EcBuilder(200, 2) as b:
+        b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"], drop_last_group=True)
+        _assert_same(b.finalize(), _oracle(cols, drop_last=True))
+
+
+# ---------------------------------------------------------------- per-cell path vs the oracle
+@pytest.mark.parametrize("n_files,reads,n_cells,mincount", [(1, 3000, 10, 1), (3, 5000, 40, 1), (4, 20000, 300, 120),
+                                                            (2, 60000, 2000, 25)])
+def test_cells_match_oracle(native, n_files, reads, n_cells, mincount):
+    from alntools_b200 import synth
+    from oracle import ec_oracle
+    pushes = []
+    for f in range(n_files):
+        c = synth.make_columns(reads, 800, 2, seed=100 + f, mode="light", n_cells=n_cells, dup_rate=0.02)
+        pushes.append((c["read_group"], c["target_idx"], c["hap_idx"], c["cell_idx"], True))
+    want = ec_oracle.ec_from_columns_cells(pushes, mincount)
+    total = sum(len(p[0]) for p in pushes)
+    with native.EcBuilder(800, 2, with_cells=True, alignments_hint=total) as b:
+        base = 0
+        for rg, tg, hp, cell, drop in pushes:
+            b.push(rg, tg, hp, cell, order_base=base, drop_last_group=drop)
+            base += len(rg)
+        got = b.finalize(mincount)
+    for k in ("a_indptr", "a_indices", "a_data", "n_indptr", "n_indices", "n_data", "cell_order"):
+        assert np.array_equal(got[k], want[k]), k
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE configs)
+def test_full_size_cfg2_properties_and_oracle(native):
+    """cfg2 shape at full size (30 M reads, 2 haplotypes x 100 k transcripts): size-independent
+    properties on the GPU result, then the C oracle on the same columns."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(30_000_000, 100_000, 2, seed=2, mode="diploid")
+    got, stats = _run(native, cols, 100_000, 2)
+    n_aln = len(cols["read_group"])
+    assert got["n_reads"] == cols["n_reads"] and got["n_alignments"] == n_aln
+    assert int(got["n_data"].astype(np.int64).sum()) == cols["n_reads"]       # every read counted once
+    assert np.all(np.diff(got["a_indptr"]) >= 1)                              # no empty EC
+    rows = np.repeat(np.arange(got["n_ec"]), np.diff(got["a_indptr"]))
+    same_row = rows[1:] == rows[:-1]
+    assert np.all(got["a_indices"][1:][same_row] > got["a_indices"][:-1][same_row])  # sorted, unique targets
+    assert got["a_data"].min() >= 1 and got["a_data"].max() <= 3
+    # idempotence: a second context gives identical bytes
+    again, _ = _run(native, cols, 100_000, 2)
+    for k in ("a_indptr", "a_indices", "a_data", "n_data"):
+        assert np.array_equal(got[k], again[k])
+    _assert_same(got, _oracle(cols))

@@ -1,0 +1,97 @@
+"""Host logic without a GPU: header tables, the column emitter and the EC writer.  The emitter's
+columns are pushed through the ORACLE's column-level EC build (the contract the CUDA kernels
+implement) and the bytes must equal what the reference wrote."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_records
+from alntools_b200 import bin_utils, emitter, utils
+from alntools_b200.header import TargetTables
+from oracle import ec_oracle
+
+
+@pytest.mark.parametrize("case", golden_cases("single"), ids=lambda c: c["name"])
+def test_emitter_columns_reproduce_reference_single(case, tmp_path):
+    header, recs = load_records(os.path.join(GOLDEN, case["bam"]))
+    tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+    tables = TargetTables(header.references, header.lengths, tfile)
+    cols = emitter.emit_single(recs, tables)
+    indptr, indices, data, counts = ec_oracle.ec_from_columns(cols.read_group, cols.target_idx, cols.hap_idx)
+    out = str(tmp_path / "out.bin")
+    bin_utils.ecsave2_arrays(out, tables.haplotypes, list(tables.main_targets), tables.lengths, [case["bam"]],
+                             (indptr, indices, data), ec_oracle.n_matrix_single(counts))
+    with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+        assert a.read() == b.read()
+
+
+@pytest.mark.parametrize("case", golden_cases("multisample"), ids=lambda c: c["name"])
+def test_emitter_columns_reproduce_reference_multisample(case, tmp_path):
+    tables = None
+    cell_ids = {}
+    pushes = []
+    for fn in case["file_order"]:
+        header, recs = load_records(os.path.join(GOLDEN, case["dir"], fn))
+        if tables is None:
+            tables = TargetTables(header.references, header.lengths, None)
+        cols = emitter.emit_multisample(recs, tables, cell_ids)
+        pushes.append((cols.read_group, cols.target_idx, cols.hap_idx, cols.cell_idx, True))
+    res = ec_oracle.ec_from_columns_cells(pushes, case["mincount"])
+    names = {v: k for k, v in cell_ids.items()}
+    out = str(tmp_path / "out.bin")
+    bin_utils.ecsave2_arrays(out, tables.haplotypes, list(tables.main_targets), tables.lengths,
+                             [names[c] for c in res["cell_order"].tolist()],
+                             (res["a_indptr"], res["a_indices"], res["a_data"]),
+                             (res["n_indptr"], res["n_indices"], res["n_data"]))
+    with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+        assert a.read() == b.read()
+
+
+def test_header_tables_quirks():
+    refs = ["G1_A", "G1_B", "G2", "_G3", "G5_x_A"]
+    t = TargetTables(refs, [1, 2, 3, 4, 5])
+    assert t.haplotypes == ["", "A", "B"]                      # '' sorts first (bam_utils.py:602)
+    assert list(t.main_targets) == ["G1", "G2", "_G3", "G5_x"]  # split at the LAST '_', not at index 0
+    assert t.tid_target.tolist() == [0, 0, 1, 2, 3]
+    assert t.tid_hap.tolist() == [1, 2, 0, 0, 1]
+    assert t.lengths[0].tolist() == [0, 1, 2]
+
+
+def test_header_tables_reject_ambiguous_names():
+    with pytest.raises(ValueError):
+        TargetTables(["a", "a_"], [1, 1])
+
+
+def test_emitter_filters_and_trimming():
+    t = TargetTables(["T_A", "T_B"], [1, 1])
+    P, PP, R2, UN = 1, 2, 0x80, 4
+    recs = [("r1 x", 0, 0, 0, -1, -1), ("r1", 0, 1, 0, -1, -1), ("r2", UN, -1, 0, -1, -1),
+            ("r2", P | PP, 0, 0, 0, 5), ("r2", P | PP | R2, 0, 0, 0, 5), ("r2", P, 1, 0, 1, 5),
+            ("r2", P | PP, 1, 0, 0, 5), ("r2", P | PP, 1, 0, 1, -1), (" r3", 0, 1, 0, -1, -1)]
+    cols = emitter.emit_single(recs, t)
+    assert cols.all_alignments == 9 and cols.valid_alignments == 4
+    assert cols.read_group.tolist() == [0, 0, 1, 2]
+    assert cols.hap_idx.tolist() == [0, 1, 0, 1]
+
+
+def test_multisample_emitter_needs_15_fields():
+    t = TargetTables(["T_A"], [1])
+    with pytest.raises(IndexError):
+        emitter.emit_multisample([("plainname", 0, 0, 0, -1, -1)], t, {})
+
+
+def test_ec_file_round_trip(tmp_path):
+    out = str(tmp_path / "x.bin")
+    a = (np.array([0, 1, 3], np.int32), np.array([0, 0, 2], np.int32), np.array([3, 1, 2], np.int32))
+    n = (np.array([0, 2], np.int32), np.array([0, 1], np.int32), np.array([7, 9], np.int32))
+    bin_utils.ecsave2_arrays(out, ["A", "B"], ["t0", "t1", "t2"], np.arange(6).reshape(3, 2), ["s"], a, n)
+    back = bin_utils.ecload_arrays(out)
+    assert back["haplotypes"] == ["A", "B"] and back["targets"] == ["t0", "t1", "t2"] and back["samples"] == ["s"]
+    for x, y in zip(back["a"] + back["n"], a + n):
+        assert np.array_equal(x, y)
+
+
+def test_partition_matches_reference_semantics():
+    assert utils.partition(list(range(7)), 3) == [[0, 1, 2], [3, 4], [5, 6]]
+    assert utils.partition(list(range(2)), 4) == [[0], [1]]

@@ -1,0 +1,114 @@
+"""Pin the oracle: it must reproduce, byte for byte, the EC files written by the UNMODIFIED reference
+(tests/golden/, minted by oracle/make_golden.py) and agree with itself across its three forms
+(record-level Python, column-level numpy, column-level C)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_records
+from oracle import ec_oracle
+
+
+def _sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.mark.parametrize("case", golden_cases("single"), ids=lambda c: c["name"])
+def test_record_oracle_matches_reference_single(case):
+    header, recs = load_records(os.path.join(GOLDEN, case["bam"]))
+    tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+    got = ec_oracle.convert_single(header.references, header.lengths, [recs], case["bam"], tfile)
+    with open(os.path.join(GOLDEN, case["ec"]), "rb") as fh:
+        want = fh.read()
+    assert _sha(want) == case["sha256"]
+    assert got == want
+
+
+@pytest.mark.parametrize("case", golden_cases("single"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("n_chunks", [2, 5])
+def test_record_oracle_chunk_independent(case, n_chunks):
+    """bam_utils.py:680-698: merging chunk results in order gives the same file as one chunk, as long
+    as reads do not span chunks."""
+    header, recs = load_records(os.path.join(GOLDEN, case["bam"]))
+    names = [ec_oracle.trim_name(r[0]) for r in recs]
+    cuts = [0]
+    for k in range(1, n_chunks):
+        c = len(recs) * k // n_chunks
+        while 0 < c < len(recs) and names[c] == names[c - 1]:
+            c += 1
+        cuts.append(max(c, cuts[-1]))
+    cuts.append(len(recs))
+    chunks = [recs[a:b] for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    chunks = [c for c in chunks if any(ec_oracle.alignment_is_valid(r[1], r[2], r[4], r[5]) for r in c)]
+    tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+    got = ec_oracle.convert_single(header.references, header.lengths, chunks, case["bam"], tfile)
+    with open(os.path.join(GOLDEN, case["ec"]), "rb") as fh:
+        assert got == fh.read()
+
+
+@pytest.mark.parametrize("case", golden_cases("multisample"), ids=lambda c: c["name"])
+def test_record_oracle_matches_reference_multisample(case):
+    files = []
+    header0 = None
+    for fn in case["file_order"]:
+        header, recs = load_records(os.path.join(GOLDEN, case["dir"], fn))
+        header0 = header0 or header
+        files.append(recs)
+    got = ec_oracle.convert_multisample(header0.references, header0.lengths, files, case["mincount"])
+    with open(os.path.join(GOLDEN, case["ec"]), "rb") as fh:
+        want = fh.read()
+    assert _sha(want) == case["sha256"]
+    assert got == want
+
+
+def test_worked_example_from_survey():
+    """reads {T0_A,T0_B}x2, {T1_A}x2, {T1_A,T10_B}x1."""
+    rg = [0, 0, 1, 2, 2, 3, 3, 4]
+    tg = [0, 0, 1, 1, 2, 0, 0, 1]
+    hp = [0, 1, 0, 0, 1, 1, 0, 0]
+    indptr, indices, data, counts = ec_oracle.ec_from_columns(rg, tg, hp)
+    assert indptr.tolist() == [0, 1, 2, 4]
+    assert indices.tolist() == [0, 1, 1, 2]
+    assert data.tolist() == [3, 1, 1, 2]
+    assert counts.tolist() == [2, 2, 1]
+
+
+@pytest.mark.parametrize("seed,mode,haps", [(11, "light", 2), (12, "diploid", 2), (13, "heavy", 8), (14, 64, 8)])
+def test_c_oracle_matches_numpy_oracle(built, seed, mode, haps):
+    from alntools_b200 import synth
+    from oracle import c_oracle
+    cols = synth.make_columns(3000 if mode != 64 else 300, 400, haps, seed, mode=mode, dup_rate=0.03)
+    want = ec_oracle.ec_from_columns(cols["read_group"], cols["target_idx"], cols["hap_idx"])
+    got = c_oracle.ec_from_columns(cols["read_group"], cols["target_idx"], cols["hap_idx"])
+    for a, b in zip(got[:4], want):
+        assert np.array_equal(a, b)
+    assert got[4] == cols["n_reads"]
+    assert int(got[3].sum()) == cols["n_reads"]
+
+
+def test_c_oracle_edge_cases(built):
+    from oracle import c_oracle
+    e = np.zeros(0, dtype=np.int32)
+    indptr, indices, data, counts, n_reads = c_oracle.ec_from_columns(e, e, e)
+    assert indptr.tolist() == [0] and n_reads == 0 and len(counts) == 0
+    one = np.array([5], dtype=np.int32)
+    indptr, indices, data, counts, n_reads = c_oracle.ec_from_columns(one, one, np.array([3], dtype=np.int32))
+    assert (indptr.tolist(), indices.tolist(), data.tolist(), counts.tolist()) == ([0, 1], [5], [8], [1])
+    indptr, *_rest, n_reads = c_oracle.ec_from_columns(one, one, one, drop_last=True)
+    assert indptr.tolist() == [0] and n_reads == 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/alntools"), reason="reference only exists in the build container")
+def test_goldens_regenerate_identically(tmp_path):
+    """Re-run the unmodified reference on one golden input and compare with the committed file."""
+    from oracle import run_reference
+    case = golden_cases("single")[0]
+    out = str(tmp_path / "out.bin")
+    bam = str(tmp_path / case["bam"])
+    with open(os.path.join(GOLDEN, case["bam"]), "rb") as src, open(bam, "wb") as dst:
+        dst.write(src.read())
+    run_reference.bam2ec(bam, out, 1, 1, None, temp_dir=str(tmp_path))
+    with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+        assert a.read() == b.read()
