@@ -16,7 +16,7 @@ ECB_OPT_RESULT_ON_DEVICE = 1
 ECB_OPT_TABLE_SLOTS = 2
 ECB_OPT_PAIR_SLOTS = 3
 ECB_OPT_GRID_CTAS = 4
-ECB_OPT_WARP_AGGREGATE = 5
+ECB_OPT_HOT_CACHE = 5
 ECB_OPT_VERIFY_KEYS = 6
 
 ECB_ERR_EMPTY = -5
@@ -32,6 +32,15 @@ class EcbResult(ctypes.Structure):
         ("n_indptr", _i32p), ("n_indices", _i32p), ("n_data", _i32p),
         ("cell_order", _i32p),
         ("n_reads", ctypes.c_int64), ("n_alignments", ctypes.c_int64),
+    ]
+
+
+class EcbExport(ctypes.Structure):
+    _fields_ = [
+        ("n_ec", ctypes.c_int64), ("n_rows", ctypes.c_int64),
+        ("meta", ctypes.POINTER(ctypes.c_int64)), ("rows", _i32p),
+        ("part_ec_counts", ctypes.POINTER(ctypes.c_int64)), ("part_row_counts", ctypes.POINTER(ctypes.c_int64)),
+        ("min_base", ctypes.c_int64), ("max_end", ctypes.c_int64),
     ]
 
 
@@ -63,6 +72,17 @@ SIGNATURES = {
     "ecb_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(EcbStats)]),
     "ecb_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "ecb_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "ecb_export_partition": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(EcbExport)]),
+    "ecb_import_entries": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                          ctypes.c_int]),
+    "ecb_global_mark": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]),
+    "ecb_global_count": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.POINTER(ctypes.c_int64)]),
+    "ecb_global_lens": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "ecb_global_indptr": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.POINTER(ctypes.c_int64)]),
+    "ecb_global_rows": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
 }
 
 _lib = None
@@ -111,6 +131,20 @@ def _ptr(x):
     raise TypeError("unsupported column type %r" % type(x))
 
 
+class _CudaArray(object):
+    """Zero-copy hand-off of library-owned device memory to torch (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _device_view(ptr, shape, typestr, dtype, device):
+    import torch
+    if shape[0] == 0 or not ptr:
+        return torch.empty(shape, dtype=dtype, device=device)
+    return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=device)
+
+
 def _on_device(x):
     return bool(getattr(x, "is_cuda", False))
 
@@ -132,7 +166,7 @@ class EcBuilder(object):
 
     _OPTIONS = {"result_on_device": ECB_OPT_RESULT_ON_DEVICE, "table_slots": ECB_OPT_TABLE_SLOTS,
                 "pair_slots": ECB_OPT_PAIR_SLOTS, "grid_ctas": ECB_OPT_GRID_CTAS,
-                "warp_aggregate": ECB_OPT_WARP_AGGREGATE, "verify_keys": ECB_OPT_VERIFY_KEYS}
+                "hot_cache": ECB_OPT_HOT_CACHE, "verify_keys": ECB_OPT_VERIFY_KEYS}
 
     def _check(self, rc):
         if rc != 0:
@@ -188,6 +222,45 @@ class EcBuilder(object):
 
     def reset(self):
         self._check(self._lib.ecb_reset(self._ctx))
+
+    # ---- multi-GPU exchange primitives (see alntools_b200/multi_gpu.py) -------------------------
+    def export_partition(self, world):
+        """-> (meta int64[n_ec, 5], rows int32[n_rows, 2]) torch device tensors (copies), per-owner
+        EC / row counts (lists) and the pushed order-key range."""
+        import torch
+        exp = EcbExport()
+        self._check(self._lib.ecb_export_partition(self._ctx, int(world), ctypes.byref(exp)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        meta = _device_view(ctypes.cast(exp.meta, ctypes.c_void_p).value, (exp.n_ec, 5), "<i8", torch.int64, dev)
+        rows = _device_view(ctypes.cast(exp.rows, ctypes.c_void_p).value, (exp.n_rows, 2), "<i4", torch.int32, dev)
+        ec_counts = [int(exp.part_ec_counts[i]) for i in range(world)]
+        row_counts = [int(exp.part_row_counts[i]) for i in range(world)]
+        return meta, rows, ec_counts, row_counts, int(exp.min_base), int(exp.max_end)
+
+    def import_entries(self, meta, rows, ec_counts, row_counts):
+        n = len(ec_counts)
+        a = (ctypes.c_int64 * n)(*ec_counts)
+        b = (ctypes.c_int64 * n)(*row_counts)
+        self._check(self._lib.ecb_import_entries(self._ctx, meta.data_ptr(), rows.data_ptr(), a, b, n))
+
+    def global_mark(self, min_base, bitmap):
+        self._check(self._lib.ecb_global_mark(self._ctx, int(min_base), bitmap.data_ptr(), bitmap.numel()))
+
+    def global_count(self, bitmap):
+        total = ctypes.c_int64()
+        self._check(self._lib.ecb_global_count(self._ctx, bitmap.data_ptr(), bitmap.numel(), ctypes.byref(total)))
+        return int(total.value)
+
+    def global_lens(self, lens, counts):
+        self._check(self._lib.ecb_global_lens(self._ctx, lens.data_ptr(), counts.data_ptr()))
+
+    def global_indptr(self, lens):
+        nnz = ctypes.c_int64()
+        self._check(self._lib.ecb_global_indptr(self._ctx, lens.data_ptr(), lens.numel(), ctypes.byref(nnz)))
+        return int(nnz.value)
+
+    def global_rows(self, indptr, indices, data):
+        self._check(self._lib.ecb_global_rows(self._ctx, indptr.data_ptr(), indices.data_ptr(), data.data_ptr()))
 
     def stats(self):
         st = EcbStats()

@@ -14,6 +14,7 @@
 #include "ecb_finalize.cuh"
 #include "ecb_sort.cuh"
 #include "ecb_cells.cuh"
+#include "ecb_exchange.cuh"
 
 namespace {
 
@@ -35,12 +36,14 @@ struct ecb_ctx {
   // options
   int result_on_device = 0;
   int64_t opt_table_slots = 0, opt_pair_slots = 0, opt_grid = 0;
-  int warp_aggregate = 1;
+  int use_cache = 1;
   int verify_keys = 0;
   // EC table
   DevBuf table;
   u32 table_slots = 0;
-  DevBuf ec_slot, ec_rep, row_len, row_off;  // [table_slots] u32 each
+  DevBuf ec_slot, ec_rep, ec_len, row_len, row_off;  // [table_slots] u32 each
+  DevBuf spill;
+  bool group_attr_set = false;
   DevBuf arena;                              // uint2 pairs
   u64 arena_used = 0;
   DevBuf long_list;
@@ -72,6 +75,11 @@ struct ecb_ctx {
   ecb_stats stats{};
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool long_attr_set = false;
+  // multi-GPU exchange
+  DevBuf x_meta, x_rows, x_counts, x_base;
+  int64_t x_part_ec[ECB_MAX_WORLD], x_part_rows[ECB_MAX_WORLD];
+  u64 g_min_base = 0;
+  u64 g_n_ec_total = 0;
   std::string err;
 };
 
@@ -187,6 +195,7 @@ int device_scan(ecb_ctx* c, const u32* in, u32* out, u64 n, u32 base_offset, u64
 int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
   CKR(ensure(c, c->ec_slot, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->ec_rep, (size_t)slots * 4, preserve));
+  CKR(ensure(c, c->ec_len, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->row_len, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->row_off, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->long_list, (size_t)slots * 4, false));
@@ -194,7 +203,7 @@ int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
 }
 
 int init_table(ecb_ctx* c) {
-  u64 want = c->opt_table_slots > 0 ? (u64)c->opt_table_slots : std::max<u64>(1u << 16, (u64)c->hint / 16);
+  u64 want = c->opt_table_slots > 0 ? (u64)c->opt_table_slots : std::max<u64>(1u << 16, (u64)c->hint / 8);
   c->table_slots = std::max<u32>(1u << 10, pow2_ceil(want));
   CKR(ensure(c, c->table, (size_t)c->table_slots * sizeof(EcbEntry)));
   CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
@@ -258,14 +267,16 @@ GroupParams make_group_params(ecb_ctx* c, const int32_t* rg, const int32_t* tg, 
   P.n = (int)n;
   P.order_base = (u64)order_base;
   P.drop_last = drop_last;
-  P.warp_aggregate = c->warp_aggregate;
+  P.use_cache = c->use_cache;
   P.n_targets = c->n_targets;
   P.n_haps = c->n_haps;
   P.table = (EcbEntry*)c->table.p;
   P.mask = c->table_slots - 1;
   P.ec_slot = (u32*)c->ec_slot.p;
   P.ec_rep = (u32*)c->ec_rep.p;
+  P.ec_len = (u32*)c->ec_len.p;
   P.ctr = c->d_ctr;
+  P.spill = (EcbSpill*)c->spill.p;
   P.overflow_bits = (u32*)c->overflow_bits.p;
   P.ttable = (EcbEntry*)c->ttable.p;
   P.tmask = c->ttable_slots ? c->ttable_slots - 1 : 0;
@@ -273,11 +284,22 @@ GroupParams make_group_params(ecb_ctx* c, const int32_t* rg, const int32_t* tg, 
   return P;
 }
 
+int group_prepare_launch(ecb_ctx* c) {
+  if (!c->group_attr_set) {
+    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    c->group_attr_set = true;
+  }
+  return ECB_OK;
+}
+
 int group_resident_ctas(ecb_ctx* c) {
   int per_sm = 0;
   cudaError_t e = c->with_cells
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<true>, ECB_TILE_THREADS, 0)
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<false>, ECB_TILE_THREADS, 0);
+      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<true>, ECB_TILE_THREADS, sizeof(GroupSmem))
+      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<false>, ECB_TILE_THREADS, sizeof(GroupSmem));
   if (e != cudaSuccess || per_sm < 1) per_sm = 2;
   return per_sm * c->sm_count;
 }
@@ -288,25 +310,29 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   HarvestParams H{};
   H.rg = rg; H.tg = tg; H.hp = hp; H.n = (int)n;
   H.ec_rep = (const u32*)c->ec_rep.p;
+  H.ec_len = (const u32*)c->ec_len.p;
   H.e0 = e0; H.e1 = e1;
   H.row_len = (u32*)c->row_len.p;
-  H.row_off = (u32*)c->row_off.p;
+  H.row_off = (const u32*)c->row_off.p;
   H.long_list = (u32*)c->long_list.p;
   H.ctr = c->d_ctr;
   const u32 n_new = e1 - e0;
-  const int g = grid_for((u64)n_new * 32, 256, c->sm_count * 8);
-  ecb_harvest_count_kernel<<<g, 256, 0, c->stream>>>(H);
-  LAUNCH_CHECK("harvest_count");
   u64 total = 0;
   if (c->arena_used > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
-  CKR(device_scan<false>(c, H.row_len + e0, H.row_off + e0, n_new, (u32)c->arena_used, &total));
-  CKR(sync_counters(c));
-  CKR(check_device_error(c));
+  // row offsets from the read lengths (upper bound of the row length); rows never overlap
+  CKR(device_scan<false>(c, H.ec_len + e0, (u32*)c->row_off.p + e0, n_new, (u32)c->arena_used, &total));
   if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
   CKR(ensure(c, c->arena, (size_t)(c->arena_used + total) * sizeof(uint2), true));
   H.arena = (uint2*)c->arena.p;
-  ecb_harvest_fill_kernel<<<g, 256, 0, c->stream>>>(H);
-  LAUNCH_CHECK("harvest_fill");
+  ecb_harvest_short_kernel<<<grid_for(n_new, 256, c->sm_count * 16), 256, 0, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_short");
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
+  if (c->h_ctr->scratch[1]) {
+    ecb_harvest_warp_kernel<<<grid_for((u64)n_new * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(H);
+    LAUNCH_CHECK("harvest_warp");
+    CK(cudaMemsetAsync(&c->d_ctr->scratch[1], 0, sizeof(u32), c->stream));
+  }
   const u32 n_long = c->h_ctr->n_long;
   if (n_long) {
     if (!c->long_attr_set) {
@@ -321,7 +347,6 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   c->arena_used += total;
   return ECB_OK;
 }
-
 
 // Stable LSD radix sort of n (key, value) pairs on the low `bits` key bits.  Input in sort_k[0]/
 // sort_v[0]; returns which ping-pong buffer holds the result.
@@ -536,7 +561,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
       if (c->ttable_slots) return fail(c, ECB_ERR_STATE, "table already allocated");
       c->opt_pair_slots = value; break;
     case ECB_OPT_GRID_CTAS: c->opt_grid = value; break;
-    case ECB_OPT_WARP_AGGREGATE: c->warp_aggregate = value ? 1 : 0; break;
+    case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     default: return fail(c, ECB_ERR_INVALID, "unknown option %d", option);
   }
@@ -598,32 +623,47 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
   CK(cudaMemsetAsync(c->overflow_bits.p, 0, ov_words * 4, c->stream));
 
   const u32 e_before = c->n_ec;
-  GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
+  CKR(group_prepare_launch(c));
   const int max_ctas = c->opt_grid > 0 ? (int)c->opt_grid : group_resident_ctas(c);
   const int64_t tiles = (n + ECB_TILE - 1) / ECB_TILE;
   const int grid = (int)std::min<int64_t>(tiles, max_ctas);
   const int64_t tiles_per_cta = (tiles + grid - 1) / grid;
+  CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
+  GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = (int)(tiles_per_cta * ECB_TILE);
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_TILE_THREADS, 0, c->stream>>>(P);
-  else ecb_group_insert_kernel<false><<<grid, ECB_TILE_THREADS, 0, c->stream>>>(P);
+  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_TILE_THREADS, sizeof(GroupSmem), c->stream>>>(P);
+  else ecb_group_insert_kernel<false><<<grid, ECB_TILE_THREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
   CK(cudaEventRecord(c->ev[2], c->stream));
   CKR(sync_counters(c));
   CKR(check_device_error(c));
-  while (c->h_ctr->n_overflow) {  // table too full for some reads: grow, then replay just those
+  DevBuf spill_in;
+  while (c->h_ctr->n_overflow || c->h_ctr->n_spill) {  // table too full: grow, then replay just what did not fit
     c->stats.overflow_reads += c->h_ctr->n_overflow;
+    const u32 n_spill = c->h_ctr->n_spill;
     if (c->table_slots >= (1u << 31)) return fail(c, ECB_ERR_LIMIT, "EC table cannot grow beyond 2^31 slots");
+    if (n_spill) {
+      CKR(ensure(c, spill_in, (size_t)n_spill * sizeof(EcbSpill)));
+      CK(cudaMemcpyAsync(spill_in.p, c->spill.p, (size_t)n_spill * sizeof(EcbSpill), cudaMemcpyDeviceToDevice, c->stream));
+    }
     CKR(grow_table(c, c->table_slots * 4u > c->table_slots ? c->table_slots * 4u : (1u << 31)));
     CK(cudaMemsetAsync(&c->d_ctr->n_overflow, 0, sizeof(u32), c->stream));
+    CK(cudaMemsetAsync(&c->d_ctr->n_spill, 0, sizeof(u32), c->stream));
     P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
     const int rg_grid = grid_for(ov_words, 256, c->sm_count * 8);
     if (c->with_cells) ecb_replay_kernel<true><<<rg_grid, 256, 0, c->stream>>>(P);
     else ecb_replay_kernel<false><<<rg_grid, 256, 0, c->stream>>>(P);
     LAUNCH_CHECK("replay");
+    if (n_spill) {
+      ecb_spill_replay_kernel<<<grid_for(n_spill, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+          P, (const EcbSpill*)spill_in.p, n_spill);
+      LAUNCH_CHECK("spill_replay");
+    }
     CKR(sync_counters(c));
     CKR(check_device_error(c));
   }
+  release(spill_in);
   if (c->h_ctr->n_triple_overflow) return fail(c, ECB_ERR_LIMIT, "(file, EC, cell) table ran out of probes");
   c->n_ec = c->h_ctr->n_ec;
   c->n_triples = c->h_ctr->n_triples;
@@ -674,6 +714,8 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   F.word_rank = (const u32*)c->word_rank.p;
   F.first_rel = (u64*)c->first_rel.p;
   F.ecid_of = (u32*)c->ecid_of.p;
+  F.long_rows_flag = &c->d_ctr->scratch[2];
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[2], 0, sizeof(u32), c->stream));
 
   CellResult cr{};
   if (c->with_cells) {
@@ -713,8 +755,13 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   CKR(ensure(c, c->r_a_data, std::max<u64>(Z, 1) * 4));
   F.a_indices = (int32_t*)c->r_a_indices.p;
   F.a_data = (int32_t*)c->r_a_data.p;
-  ecb_fin_rows_kernel<<<grid_for((u64)n_prov * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  ecb_fin_rows_kernel<<<grid_for(n_prov, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rows");
+  CKR(sync_counters(c));
+  if (c->h_ctr->scratch[2]) {
+    ecb_fin_rows_long_kernel<<<grid_for((u64)n_prov * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+    LAUNCH_CHECK("fin_rows_long");
+  }
 
   int64_t n_samples = 1, nnz_n = (int64_t)E;
   if (c->with_cells) {
@@ -807,15 +854,215 @@ int ecb_get_stats(const ecb_ctx* c, ecb_stats* out) {
   return ECB_OK;
 }
 
+int ecb_export_partition(ecb_ctx* c, int world, ecb_export* out) {
+  if (!c || !out) return ECB_ERR_INVALID;
+  if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
+  if (c->with_cells) return fail(c, ECB_ERR_INVALID, "the multi-GPU exchange covers the single-sample path only");
+  memset(out, 0, sizeof *out);
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots) CKR(init_table(c));
+  const u32 n_ec = c->n_ec;
+  CKR(ensure(c, c->x_counts, (size_t)2 * world * 4));
+  CKR(ensure(c, c->x_base, (size_t)2 * world * 8));
+  CK(cudaMemsetAsync(c->x_counts.p, 0, (size_t)2 * world * 4, c->stream));
+  ExportParams P{};
+  P.table = (const EcbEntry*)c->table.p;
+  P.ec_slot = (const u32*)c->ec_slot.p;
+  P.row_len = (const u32*)c->row_len.p;
+  P.row_off = (const u32*)c->row_off.p;
+  P.arena = (const uint2*)c->arena.p;
+  P.n_ec = n_ec;
+  P.world = (u32)world;
+  P.counts = (u32*)c->x_counts.p;
+  P.base = (const u64*)c->x_base.p;
+  std::vector<u32> h_counts(2 * world, 0);
+  const int g = grid_for(std::max<u32>(n_ec, 1), 256, c->sm_count * 8);
+  if (n_ec) {
+    ecb_export_count_kernel<<<g, 256, 0, c->stream>>>(P);
+    LAUNCH_CHECK("export_count");
+    CK(cudaMemcpyAsync(h_counts.data(), c->x_counts.p, (size_t)2 * world * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  std::vector<u64> h_base(2 * world, 0);
+  u64 ec_run = 0, row_run = 0;
+  for (int w = 0; w < world; ++w) {
+    h_base[w] = ec_run;
+    h_base[world + w] = row_run;
+    c->x_part_ec[w] = h_counts[w];
+    c->x_part_rows[w] = h_counts[world + w];
+    ec_run += h_counts[w];
+    row_run += h_counts[world + w];
+  }
+  CKR(ensure(c, c->x_meta, std::max<u64>(ec_run, 1) * ECB_META_WORDS * 8));
+  CKR(ensure(c, c->x_rows, std::max<u64>(row_run, 1) * 8));
+  if (n_ec) {
+    CK(cudaMemcpyAsync(c->x_base.p, h_base.data(), (size_t)2 * world * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->x_counts.p, 0, (size_t)2 * world * 4, c->stream));
+    P.meta = (long long*)c->x_meta.p;
+    P.rows = (int2*)c->x_rows.p;
+    ecb_export_fill_kernel<<<g, 256, 0, c->stream>>>(P);
+    LAUNCH_CHECK("export_fill");
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  out->n_ec = (int64_t)ec_run;
+  out->n_rows = (int64_t)row_run;
+  out->meta = (const int64_t*)c->x_meta.p;
+  out->rows = (const int32_t*)c->x_rows.p;
+  out->part_ec_counts = c->x_part_ec;
+  out->part_row_counts = c->x_part_rows;
+  out->min_base = n_ec ? (int64_t)c->min_base : 0;
+  out->max_end = n_ec ? (int64_t)c->max_end : 0;
+  return ECB_OK;
+}
+
+int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* rows_device,
+                       const int64_t* part_ec_counts, const int64_t* part_row_counts, int n_parts) {
+  if (!c) return ECB_ERR_INVALID;
+  if (n_parts < 1 || n_parts > ECB_MAX_WORLD || !part_ec_counts || !part_row_counts)
+    return fail(c, ECB_ERR_INVALID, "bad partition description");
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots) CKR(init_table(c));
+  PartTable parts{};
+  parts.n = (u32)n_parts;
+  u64 n_rec = 0, n_rows = 0;
+  for (int p = 0; p < n_parts; ++p) {
+    if (part_ec_counts[p] < 0 || part_row_counts[p] < 0) return fail(c, ECB_ERR_INVALID, "negative partition size");
+    parts.row_base[p] = (long long)n_rows;
+    n_rec += (u64)part_ec_counts[p];
+    n_rows += (u64)part_row_counts[p];
+    parts.ec_end[p] = (long long)n_rec;
+  }
+  if (n_rec == 0) return ECB_OK;
+  if (!meta_device || (n_rows && !rows_device)) return fail(c, ECB_ERR_INVALID, "NULL exchange buffer");
+  if (n_rec > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "too many records in one import");
+  // the owner table must be able to take every incoming record as a new EC without filling up
+  const u64 need = ((u64)c->n_ec + n_rec) * 2;
+  if (need > c->table_slots) CKR(grow_table(c, pow2_ceil(need)));
+  const u32 e0 = c->n_ec;
+  ImportParams P{};
+  P.meta = (const long long*)meta_device;
+  P.n_rec = (u32)n_rec;
+  P.table = (EcbEntry*)c->table.p;
+  P.mask = c->table_slots - 1;
+  P.ec_slot = (u32*)c->ec_slot.p;
+  P.ec_rep = (u32*)c->ec_rep.p;
+  P.row_len = (u32*)c->row_len.p;
+  P.ctr = c->d_ctr;
+  ecb_import_insert_kernel<<<grid_for(n_rec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P);
+  LAUNCH_CHECK("import_insert");
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
+  c->n_ec = c->h_ctr->n_ec;
+  const u32 e1 = c->n_ec;
+  if (e1 > e0) {
+    u64 total = 0;
+    CKR(device_scan<false>(c, (const u32*)c->row_len.p + e0, (u32*)c->row_off.p + e0, e1 - e0, (u32)c->arena_used, &total));
+    if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
+    CKR(ensure(c, c->arena, std::max<u64>(c->arena_used + total, 1) * sizeof(uint2), true));
+    ecb_import_rows_kernel<<<grid_for((u64)(e1 - e0) * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+        (const long long*)meta_device, (const int2*)rows_device, parts, (const u32*)c->ec_rep.p,
+        (const u32*)c->row_len.p, (const u32*)c->row_off.p, (uint2*)c->arena.p, e0, e1);
+    LAUNCH_CHECK("import_rows");
+    c->arena_used += total;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return ECB_OK;
+}
+
+static FinalizeParams global_params(ecb_ctx* c) {
+  FinalizeParams F{};
+  F.table = (const EcbEntry*)c->table.p;
+  F.ec_slot = (const u32*)c->ec_slot.p;
+  F.row_len = (const u32*)c->row_len.p;
+  F.row_off = (const u32*)c->row_off.p;
+  F.arena = (const uint2*)c->arena.p;
+  F.n_ec = c->n_ec;
+  F.min_base = c->g_min_base;
+  F.first_rel = (u64*)c->first_rel.p;
+  F.ecid_of = (u32*)c->ecid_of.p;
+  return F;
+}
+
+int ecb_global_mark(ecb_ctx* c, int64_t min_base, uint32_t* bitmap_device, int64_t n_words) {
+  if (!c || !bitmap_device || n_words <= 0 || min_base < 0) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  c->g_min_base = (u64)min_base;
+  if (c->n_ec == 0) return ECB_OK;
+  CKR(ensure(c, c->first_rel, (size_t)c->n_ec * 8));
+  CKR(ensure(c, c->ecid_of, (size_t)c->n_ec * 4));
+  FinalizeParams F = global_params(c);
+  F.bitmap = bitmap_device;
+  ecb_fin_mark_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_mark");
+  CK(cudaStreamSynchronize(c->stream));
+  return ECB_OK;
+}
+
+int ecb_global_count(ecb_ctx* c, const uint32_t* bitmap_device, int64_t n_words, int64_t* n_ec_total) {
+  if (!c || !bitmap_device || n_words <= 0 || !n_ec_total) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CKR(ensure(c, c->word_rank, (size_t)n_words * 4));
+  CKR(ensure(c, c->bitmap, (size_t)n_words * 4));
+  CK(cudaMemcpyAsync(c->bitmap.p, bitmap_device, (size_t)n_words * 4, cudaMemcpyDeviceToDevice, c->stream));
+  u64 total = 0;
+  CKR(device_scan<true>(c, (const u32*)c->bitmap.p, (u32*)c->word_rank.p, (u64)n_words, 0, &total));
+  c->g_n_ec_total = total;
+  *n_ec_total = (int64_t)total;
+  return ECB_OK;
+}
+
+int ecb_global_lens(ecb_ctx* c, int32_t* lens_device, int32_t* counts_device) {
+  if (!c || !lens_device || !counts_device) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (c->n_ec == 0) return ECB_OK;
+  FinalizeParams F = global_params(c);
+  F.bitmap = (u32*)c->bitmap.p;
+  F.word_rank = (const u32*)c->word_rank.p;
+  F.a_indptr = lens_device;
+  F.n_data = counts_device;
+  CKR(ensure(c, c->r_n_indices, (size_t)c->g_n_ec_total * 4));
+  F.n_indices = (int32_t*)c->r_n_indices.p;
+  ecb_fin_rank_kernel<true><<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_rank");
+  CK(cudaStreamSynchronize(c->stream));
+  return ECB_OK;
+}
+
+int ecb_global_indptr(ecb_ctx* c, int32_t* lens_device, int64_t n, int64_t* nnz) {
+  if (!c || !lens_device || n < 1 || !nnz) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  u64 total = 0;
+  CKR(device_scan<false>(c, (const u32*)lens_device, (u32*)lens_device, (u64)n, 0, &total));
+  if (total > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix has more than 2^31-1 non-zeros");
+  *nnz = (int64_t)total;
+  return ECB_OK;
+}
+
+int ecb_global_rows(ecb_ctx* c, const int32_t* indptr_device, int32_t* indices_device, int32_t* data_device) {
+  if (!c || !indptr_device || !indices_device || !data_device) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  if (c->n_ec == 0) return ECB_OK;
+  FinalizeParams F = global_params(c);
+  F.a_indptr = const_cast<int32_t*>(indptr_device);
+  F.a_indices = indices_device;
+  F.a_data = data_device;
+  ecb_fin_rows_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_rows");
+  ecb_fin_rows_long_kernel<<<grid_for((u64)c->n_ec * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  LAUNCH_CHECK("fin_rows_long");
+  CK(cudaStreamSynchronize(c->stream));
+  return ECB_OK;
+}
+
 int ecb_destroy(ecb_ctx* c) {
   if (!c) return ECB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->row_len, &c->row_off, &c->arena, &c->long_list,
+  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list,
                     &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,
-                    &c->r_n_data, &c->r_cell_order};
+                    &c->r_n_data, &c->r_cell_order, &c->x_meta, &c->x_rows, &c->x_counts, &c->x_base};
   for (DevBuf* b : bufs) release(*b);
   cells_release(c);
   if (c->d_ctr) cudaFree(c->d_ctr);

@@ -90,17 +90,22 @@ __device__ __forceinline__ u32 ecb_code(int target, int hap) { return ((u32)targ
 
 // 128-bit contribution of one DISTINCT (target, haplotype) element.  A read's key is the lane-wise
 // sum (mod 2^32) of the contributions of its distinct elements: a commutative set hash, so no
-// per-read sort is needed on the streaming path.  Each lane is a bijection of the 31-bit code, so
-// single-element sets never collide.
+// per-read sort is needed on the streaming path.  Every lane is an independent two-round
+// multiply-fold of the 31-bit code (5 instructions per lane).
 struct Mix4 {
   u32 a, b, c, d;
 };
+// multiply-fold: low ^ high half of a 32x32 -> 64 bit product (one IMAD.WIDE + one LOP3)
+__device__ __forceinline__ u32 mum32(u32 x, u32 k) {
+  const u64 p = (u64)x * k;
+  return (u32)p ^ (u32)(p >> 32);
+}
 __device__ __forceinline__ Mix4 ecb_mix(u32 code) {
   Mix4 m;
-  m.a = fmix32(code ^ 0x9e3779b9u);
-  m.b = fmix32(code ^ 0x7f4a7c15u);
-  m.c = fmix32((code + 0x632be5abu) * 0x2545f491u);
-  m.d = fmix32((code ^ 0x1b873593u) * 0x9e3779b1u + 0x52dce729u);
+  m.a = mum32(mum32(code ^ 0x9e3779b9u, 0x85ebca6bu) ^ 0x27d4eb2fu, 0xc2b2ae35u);
+  m.b = mum32(mum32(code ^ 0x7f4a7c15u, 0x2545f491u) ^ 0x165667b1u, 0x9e3779b1u);
+  m.c = mum32(mum32(code ^ 0x632be5abu, 0xd6e8feb9u) ^ 0x52dce729u, 0xa0761d65u);
+  m.d = mum32(mum32(code ^ 0x1b873593u, 0xe7037ed1u) ^ 0x8ebc6af1u, 0x589965cdu);
   return m;
 }
 __device__ __forceinline__ void mix_add(Mix4& x, const Mix4& y) {
@@ -131,6 +136,8 @@ struct EcbCounters {
   u64 n_reads;        // reads counted
   u32 n_triples;      // entries in the (file, EC, cell) table
   u32 n_triple_overflow;
+  u32 n_spill;        // hot-cache entries parked because the table was too full
+  u32 pad0;
   u64 arena_used;     // (target, mask) pairs in the row arena
   u32 scratch[8];
 };

@@ -1,0 +1,126 @@
+// ecb_exchange.cuh — kernels of the multi-GPU exchange.
+//
+// Reads shard across GPUs by contiguous chunk (the reference's utils.partition + ordered imap,
+// alntools/bam_utils.py:647-680); every GPU builds a local EC table.  Global dedup = the chunk merge
+// of alntools/bam_utils.py:680-698 (sum the counts of equal keys, EC id = rank of the GLOBAL first
+// occurrence): local ECs are hash-partitioned to an owner GPU (all-to-all), the owner merges them,
+// and the global ids come from the same first-occurrence bitmap as on one GPU, OR-ed across ranks.
+//
+// Record layout of an exported EC ("meta", 5 x int64): key_lo, key_hi, first,
+// count << 32 | row_len, row offset inside the partition (in (target, mask) pairs).
+#pragma once
+#include "ecb_common.cuh"
+#include "ecb_group.cuh"
+
+#define ECB_META_WORDS 5
+#define ECB_MAX_WORLD 64
+
+__device__ __forceinline__ u32 ecb_owner_of(const Key128& k, u32 world) {
+  return fmix32((u32)(k.hi >> 32) ^ 0x5bd1e995u) % world;
+}
+
+struct ExportParams {
+  const EcbEntry* table;
+  const u32* ec_slot;
+  const u32* row_len;
+  const u32* row_off;
+  const uint2* arena;
+  u32 n_ec;
+  u32 world;
+  u32* counts;       // [2*world] ECs, rows per owner (count pass) / running cursors (fill pass)
+  const u64* base;   // [2*world] partition bases (fill pass)
+  long long* meta;
+  int2* rows;
+};
+
+__global__ void __launch_bounds__(256) ecb_export_count_kernel(const ExportParams P) {
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
+    const EcbEntry* en = P.table + P.ec_slot[e];
+    const u32 owner = ecb_owner_of(Key128{en->key_lo, en->key_hi}, P.world);
+    atomicAdd(&P.counts[owner], 1u);
+    atomicAdd(&P.counts[P.world + owner], P.row_len[e]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ecb_export_fill_kernel(const ExportParams P) {
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
+    const EcbEntry en = P.table[P.ec_slot[e]];
+    const u32 owner = ecb_owner_of(Key128{en.key_lo, en.key_hi}, P.world);
+    const u32 len = P.row_len[e];
+    const u32 idx = atomicAdd(&P.counts[owner], 1u);
+    const u32 roff = atomicAdd(&P.counts[P.world + owner], len);
+    long long* m = P.meta + (P.base[owner] + idx) * ECB_META_WORDS;
+    m[0] = (long long)en.key_lo;
+    m[1] = (long long)en.key_hi;
+    m[2] = (long long)en.first;
+    m[3] = (long long)(((u64)(en.countm1 + 1u) << 32) | len);
+    m[4] = (long long)roff;
+    const uint2* src = P.arena + P.row_off[e];
+    int2* dst = P.rows + P.base[P.world + owner] + roff;
+    for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+  }
+}
+
+struct ImportParams {
+  const long long* meta;
+  u32 n_rec;
+  EcbEntry* table;
+  u32 mask;
+  u32* ec_slot;
+  u32* ec_rep;     // provisional id -> record index of the import that created it
+  u32* row_len;
+  EcbCounters* ctr;
+};
+
+// Merge received records into the owner table: sum counts, min first (bam_utils.py:693-698).
+__global__ void __launch_bounds__(256) ecb_import_insert_kernel(const ImportParams P) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rec; i += gridDim.x * blockDim.x) {
+    const long long* m = P.meta + (size_t)i * ECB_META_WORDS;
+    const Key128 key{(u64)m[0], (u64)m[1]};
+    const u64 first = (u64)m[2];
+    const u32 count = (u32)((u64)m[3] >> 32);
+    bool claimed;
+    u64 seen;
+    const u32 slot = table_find_or_claim(P.table, P.mask, key, claimed, seen);
+    if (slot == ECB_NONE) {
+      atomicOr(&P.ctr->error, ECB_DEVERR_EC_CAPACITY);
+      continue;
+    }
+    EcbEntry* e = P.table + slot;
+    atomicAdd(&e->countm1, count);
+    if (first < seen) atomicMin(&e->first, first);
+    if (claimed) {
+      const u32 ecl = atomicAdd(&P.ctr->n_ec, 1u);
+      e->aux = ecl;
+      P.ec_slot[ecl] = slot;
+      P.ec_rep[ecl] = i;
+      P.row_len[ecl] = (u32)((u64)m[3] & 0xFFFFFFFFull);
+    }
+  }
+}
+
+struct PartTable {
+  long long row_base[ECB_MAX_WORLD];  // first row of each source partition in the receive buffer
+  long long ec_end[ECB_MAX_WORLD];    // cumulative record count after each source partition
+  u32 n;
+};
+
+// Copy the rows of the ECs created by this import from the receive buffer into the arena.
+__global__ void __launch_bounds__(256) ecb_import_rows_kernel(const long long* __restrict__ meta,
+                                                              const int2* __restrict__ rows, const PartTable parts,
+                                                              const u32* __restrict__ ec_rep,
+                                                              const u32* __restrict__ row_len,
+                                                              const u32* __restrict__ row_off, uint2* arena, u32 e0,
+                                                              u32 e1) {
+  const int lane = threadIdx.x & 31;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (u32 e = e0 + warp_global; e < e1; e += n_warps) {
+    const u32 rec = ec_rep[e];
+    u32 part = 0;
+    while (part + 1 < parts.n && (long long)rec >= parts.ec_end[part]) ++part;
+    const int2* src = rows + parts.row_base[part] + meta[(size_t)rec * ECB_META_WORDS + 4];
+    uint2* dst = arena + row_off[e];
+    for (u32 j = lane; j < row_len[e]; j += 32) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
+  }
+}

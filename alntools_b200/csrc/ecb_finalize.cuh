@@ -26,6 +26,7 @@ struct FinalizeParams {
   int32_t* a_data;
   int32_t* n_indices;   // single-sample N matrix
   int32_t* n_data;
+  u32* long_rows_flag;  // set when some row has more than 8 entries
 };
 
 __global__ void __launch_bounds__(256) ecb_fin_mark_kernel(const FinalizeParams P) {
@@ -47,7 +48,9 @@ __global__ void __launch_bounds__(256) ecb_fin_rank_kernel(const FinalizeParams 
     const u32 w = (u32)(rel >> 5), b = (u32)(rel & 31);
     const u32 id = P.word_rank[w] + __popc(P.bitmap[w] & ((1u << b) - 1u));
     P.ecid_of[e] = id;
-    P.a_indptr[id] = (int32_t)P.row_len[e];
+    const u32 len = P.row_len[e];
+    P.a_indptr[id] = (int32_t)len;
+    if (len > 8 && P.long_rows_flag && *P.long_rows_flag == 0u) *P.long_rows_flag = 1u;
     if (SINGLE_SAMPLE) {
       P.n_indices[id] = (int32_t)id;
       P.n_data[id] = (int32_t)(P.table[P.ec_slot[e]].countm1 + 1u);
@@ -55,15 +58,33 @@ __global__ void __launch_bounds__(256) ecb_fin_rank_kernel(const FinalizeParams 
   }
 }
 
-// One warp per EC: copy its row from the arena to its CSR position.
+// Copy rows from the arena to their CSR position.  Rows of up to 8 entries (the bulk): one thread per
+// EC; longer rows: one warp per EC (second launch, only when such rows exist).
 __global__ void __launch_bounds__(256) ecb_fin_rows_kernel(const FinalizeParams P) {
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
+    const u32 id = P.ecid_of[e];
+    if (id == ECB_NONE) continue;
+    const u32 len = P.row_len[e];
+    if (len > 8) continue;
+    const uint2* src = P.arena + P.row_off[e];
+    const size_t dst = (size_t)P.a_indptr[id];
+    for (u32 j = 0; j < len; ++j) {
+      const uint2 v = src[j];
+      P.a_indices[dst + j] = (int32_t)v.x;
+      P.a_data[dst + j] = (int32_t)v.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ecb_fin_rows_long_kernel(const FinalizeParams P) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 e = warp_global; e < P.n_ec; e += n_warps) {
+    const u32 len = P.row_len[e];
+    if (len <= 8) continue;
     const u32 id = P.ecid_of[e];
     if (id == ECB_NONE) continue;
-    const u32 len = P.row_len[e];
     const size_t src = P.row_off[e];
     const size_t dst = (size_t)P.a_indptr[id];
     for (u32 j = lane; j < len; j += 32) {

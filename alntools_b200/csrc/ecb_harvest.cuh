@@ -1,10 +1,15 @@
-// ecb_harvest.cuh — turn the representative read of every NEW equivalence class into its canonical
-// row: distinct main targets ascending, data = OR of (1 << haplotype).
+// ecb_harvest.cuh — turn one read of every NEW equivalence class into its canonical row: distinct main
+// targets ascending, data = OR of (1 << haplotype).
 //
 // Replaces alntools/bam_utils.py:788-825 (EC key -> per-haplotype (ec, target) COO lists) and the
 // canonicalisation scipy performs in alntools/bin_utils.py:208-211 (sum of 2^h * data[h], tocsr()
 // with sorted column indices).  Runs at the end of every push, while the caller's columns are still
-// valid, over the ECs claimed in that push only (E rows, not R reads).
+// valid, over the ECs claimed in that push only (E rows, not R reads).  The grouping kernel recorded
+// for every new EC the offset and the length of one read with that key; row offsets come from an
+// exclusive scan of those lengths (an upper bound of the row length).
+//   k <= 8        one thread per EC: 8-element sorting network in registers
+//   8 < k <= 32   one warp per EC: __match_any_sync / __reduce_or_sync, rank by counting
+//   k > 32        one CTA per EC: bitonic sort in shared memory (up to ECB_MAX_READ_ALIGNMENTS)
 #pragma once
 #include "ecb_common.cuh"
 #include "ecb_scan.cuh"
@@ -15,65 +20,80 @@ struct HarvestParams {
   const int32_t* hp;
   int n;
   const u32* ec_rep;
+  const u32* ec_len;
   u32 e0, e1;        // provisional ids claimed in this push
-  u32* row_len;      // [capacity] out: row length (upper bound for long reads after the count pass)
-  u32* row_off;      // [capacity] absolute offsets inside the arena
+  u32* row_len;      // [capacity] out: row length
+  const u32* row_off;  // [capacity] absolute offsets inside the arena
   uint2* arena;      // (target, mask) pairs
-  u32* long_list;    // provisional ids whose representative read has more than 32 alignments
-  EcbCounters* ctr;
+  u32* long_list;    // provisional ids whose read has more than 32 alignments
+  EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, n_long = #ECs with k > 32
 };
 
 #define HARVEST_LONG_MAX 16384
 
-// Length of the read starting at s (warp-cooperative, all lanes get the result).
-__device__ __forceinline__ int warp_read_length(const int32_t* rg, int n, int s, int lane) {
-  const int my = rg[s];
-  int k = 0;
-  for (;;) {
-    const int j = s + k + lane;
-    const bool in = j < n && rg[j] == my;
-    const u32 b = __ballot_sync(ECB_FULL, in);
-    if (b == ECB_FULL) {
-      k += 32;
-    } else {
-      k += __ffs(~b) - 1;  // members form a prefix
-      break;
-    }
+#define ECB_CSWAP(a, b)            \
+  {                                \
+    const u32 lo_ = min(a, b);     \
+    const u32 hi_ = max(a, b);     \
+    a = lo_;                       \
+    b = hi_;                       \
   }
-  return k;
+
+__global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestParams P) {
+  u32 n_mid = 0;
+  for (u32 e = P.e0 + blockIdx.x * blockDim.x + threadIdx.x; e < P.e1; e += gridDim.x * blockDim.x) {
+    const u32 k = P.ec_len[e];
+    if (k > 8) {
+      if (k <= 32) {
+        ++n_mid;
+      } else {
+        if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
+        P.long_list[atomicAdd(&P.ctr->n_long, 1u)] = e;
+      }
+      continue;
+    }
+    const int s = (int)P.ec_rep[e];
+    u32 c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = (u32)j < k ? ecb_code(P.tg[s + j], P.hp[s + j]) : 0xFFFFFFFFu;
+    // Batcher odd-even merge sort network for 8 keys (19 comparators)
+    ECB_CSWAP(c[0], c[1]) ECB_CSWAP(c[2], c[3]) ECB_CSWAP(c[4], c[5]) ECB_CSWAP(c[6], c[7])
+    ECB_CSWAP(c[0], c[2]) ECB_CSWAP(c[1], c[3]) ECB_CSWAP(c[4], c[6]) ECB_CSWAP(c[5], c[7])
+    ECB_CSWAP(c[1], c[2]) ECB_CSWAP(c[5], c[6])
+    ECB_CSWAP(c[0], c[4]) ECB_CSWAP(c[1], c[5]) ECB_CSWAP(c[2], c[6]) ECB_CSWAP(c[3], c[7])
+    ECB_CSWAP(c[2], c[4]) ECB_CSWAP(c[3], c[5])
+    ECB_CSWAP(c[1], c[2]) ECB_CSWAP(c[3], c[4]) ECB_CSWAP(c[5], c[6])
+    uint2* out = P.arena + P.row_off[e];
+    u32 cnt = 0, prev_t = 0xFFFFFFFFu, mask = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (c[j] != 0xFFFFFFFFu) {
+        const u32 t = c[j] >> 5;
+        if (t != prev_t) {
+          if (cnt) out[cnt - 1] = make_uint2(prev_t, mask);
+          ++cnt;
+          prev_t = t;
+          mask = 0;
+        }
+        mask |= 1u << (c[j] & 31u);
+      }
+    }
+    if (cnt) out[cnt - 1] = make_uint2(prev_t, mask);
+    P.row_len[e] = cnt;
+  }
+  n_mid = __reduce_add_sync(ECB_FULL, n_mid);
+  if ((threadIdx.x & 31) == 0 && n_mid) atomicAdd(&P.ctr->scratch[1], n_mid);
 }
 
-__global__ void __launch_bounds__(256) ecb_harvest_count_kernel(const HarvestParams P) {
+// Rows of reads with 9..32 alignments: one warp per EC, one alignment per lane.
+__global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
   for (u32 e = P.e0 + warp_global; e < P.e1; e += n_warps) {
+    const int k = (int)P.ec_len[e];
+    if (k <= 8 || k > 32) continue;
     const int s = (int)P.ec_rep[e];
-    const int k = warp_read_length(P.rg, P.n, s, lane);
-    if (k <= 32) {
-      const int t = lane < k ? P.tg[s + lane] : -1 - lane;
-      const u32 grp = __match_any_sync(ECB_FULL, t);
-      const bool leader = lane < k && lane == __ffs(grp) - 1;
-      const u32 nd = __popc(__ballot_sync(ECB_FULL, leader));
-      if (lane == 0) P.row_len[e] = nd;
-    } else if (lane == 0) {
-      P.row_len[e] = (u32)k;
-      if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
-      const u32 idx = atomicAdd(&P.ctr->n_long, 1u);
-      P.long_list[idx] = e;
-    }
-  }
-}
-
-// Rows of reads with at most 32 alignments: one warp per EC, one alignment per lane.
-__global__ void __launch_bounds__(256) ecb_harvest_fill_kernel(const HarvestParams P) {
-  const int lane = threadIdx.x & 31;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 e = P.e0 + warp_global; e < P.e1; e += n_warps) {
-    const int s = (int)P.ec_rep[e];
-    const int k = warp_read_length(P.rg, P.n, s, lane);
-    if (k > 32) continue;
     const int t = lane < k ? P.tg[s + lane] : -1 - lane;
     const u32 hbit = lane < k ? (1u << P.hp[s + lane]) : 0u;
     const u32 grp = __match_any_sync(ECB_FULL, t);
@@ -86,6 +106,7 @@ __global__ void __launch_bounds__(256) ecb_harvest_fill_kernel(const HarvestPara
       rank += ((leaders >> j) & 1u) && tj < t;
     }
     if (leader) P.arena[(size_t)P.row_off[e] + rank] = make_uint2((u32)t, mask);
+    if (lane == 0) P.row_len[e] = (u32)__popc(leaders);
   }
 }
 
@@ -98,7 +119,7 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
   for (u32 li = blockIdx.x; li < n_long; li += gridDim.x) {
     const u32 e = P.long_list[li];
     const int s = (int)P.ec_rep[e];
-    const u32 k = min(P.row_len[e], (u32)HARVEST_LONG_MAX);
+    const u32 k = min(P.ec_len[e], (u32)HARVEST_LONG_MAX);
     u32 np2 = 64;
     while (np2 < k) np2 <<= 1;
     for (u32 i = threadIdx.x; i < np2; i += blockDim.x)

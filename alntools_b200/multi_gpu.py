@@ -1,0 +1,85 @@
+"""Multi-GPU EC build: one process per GPU, shards of contiguous reads, one exchange step.
+
+The reference's only parallelism is a process pool over contiguous BAM chunks whose results are
+merged in chunk order (alntools/bam_utils.py:647-724).  Here every rank builds a local EC table from
+its shard (order_base = global offset of the shard) and the merge becomes:
+
+  all-to-all   local ECs, hash-partitioned by owner rank (key, first, count, row)       [NCCL]
+  owner merge  equal keys: counts summed, smallest first-occurrence kept                [kernel]
+  all-reduce   first-occurrence bitmap, OR as SUM of disjoint bits -> global EC ids     [NCCL]
+  all-reduce   row lengths / counts / rows scattered at their global ids (disjoint      [NCCL]
+               supports, so SUM assembles the final CSR on every rank)
+
+torch.distributed is the plumbing (process group, collectives on device tensors); every compute
+step is a libecb200 kernel behind the C ABI.  The same orchestration runs on gloo/CPU in the tests
+with a stand-in for the kernels.
+"""
+import torch
+import torch.distributed as dist
+
+
+def _all_to_all_counts(counts, device, group):
+    send = torch.tensor(counts, dtype=torch.int64, device=device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.tolist()
+
+
+def distributed_finalize(local, make_owner, device, group=None):
+    """local: builder holding this rank's shard; make_owner(): fresh builder for the owner role.
+    Returns dict(a_indptr, a_indices, a_data, n_data, n_ec, nnz_a) of int32 tensors on `device`,
+    identical on every rank."""
+    world = dist.get_world_size(group)
+    meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
+
+    # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
+    recv_ec = _all_to_all_counts(ec_counts, device, group)
+    recv_rows = _all_to_all_counts(row_counts, device, group)
+    meta_in = torch.empty((sum(recv_ec), 5), dtype=torch.int64, device=device)
+    rows_in = torch.empty((sum(recv_rows), 2), dtype=torch.int32, device=device)
+    dist.all_to_all_single(meta_in, meta, output_split_sizes=recv_ec, input_split_sizes=ec_counts, group=group)
+    dist.all_to_all_single(rows_in, rows, output_split_sizes=recv_rows, input_split_sizes=row_counts, group=group)
+
+    owner = make_owner()
+    owner.import_entries(meta_in, rows_in, recv_ec, recv_rows)
+
+    # ---- global EC ids from the OR-ed first-occurrence bitmap ------------------------------------
+    span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
+    dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)
+    g_min, g_max = -int(span[0].item()), int(span[1].item())
+    if g_max <= g_min:
+        raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
+    n_words = (g_max - g_min + 31) // 32 + 1
+    bitmap = torch.zeros(n_words, dtype=torch.int32, device=device)
+    owner.global_mark(g_min, bitmap)
+    dist.all_reduce(bitmap, op=dist.ReduceOp.SUM, group=group)   # disjoint bits: SUM == OR
+    n_ec = owner.global_count(bitmap)
+
+    lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=device)
+    counts = torch.zeros(n_ec, dtype=torch.int32, device=device)
+    owner.global_lens(lens, counts)
+    dist.all_reduce(lens, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    nnz = owner.global_indptr(lens)                              # lens becomes indptr in place
+    indices = torch.zeros(max(nnz, 1), dtype=torch.int32, device=device)
+    data = torch.zeros(max(nnz, 1), dtype=torch.int32, device=device)
+    owner.global_rows(lens, indices, data)
+    dist.all_reduce(indices, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(data, op=dist.ReduceOp.SUM, group=group)
+    return {"a_indptr": lens, "a_indices": indices[:nnz], "a_data": data[:nnz], "n_data": counts,
+            "n_ec": n_ec, "nnz_a": nnz}
+
+
+def shard_bounds(read_group, world):
+    """Split an alignment stream into `world` contiguous, read-aligned shards (the reference's
+    utils.partition gives each worker a contiguous run of chunks; chunk starts are moved to the next
+    read boundary, bam_utils.py:1236-1247).  Returns world+1 offsets."""
+    n = len(read_group)
+    cuts = [0]
+    for k in range(1, world):
+        c = max(cuts[-1], n * k // world)
+        while 0 < c < n and read_group[c] == read_group[c - 1]:
+            c += 1
+        cuts.append(c)
+    cuts.append(n)
+    return cuts

@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--grid-ctas", type=int, default=0)
-    ap.add_argument("--warp-aggregate", type=int, default=1)
+    ap.add_argument("--hot-cache", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -237,7 +237,7 @@ def main():
         opts["table_slots"] = args.table_slots
     if args.grid_ctas:
         opts["grid_ctas"] = args.grid_ctas
-    opts["warp_aggregate"] = args.warp_aggregate
+    opts["hot_cache"] = args.hot_cache
     stream = torch.cuda.current_stream()
 
     def barrier():

@@ -58,7 +58,7 @@ enum ecb_option {
   ECB_OPT_TABLE_SLOTS = 2,      /* initial EC hash-table capacity (rounded up to a power of two) */
   ECB_OPT_PAIR_SLOTS = 3,       /* initial (file, EC, cell) table capacity */
   ECB_OPT_GRID_CTAS = 4,        /* CTAs of the grouping kernel (0 = resident CTAs x SMs) */
-  ECB_OPT_WARP_AGGREGATE = 5,   /* 1 (default): combine equal keys inside a warp before the atomics */
+  ECB_OPT_HOT_CACHE = 5,        /* 1 (default): per-CTA shared-memory cache of hot ECs in front of the HBM table */
   ECB_OPT_VERIFY_KEYS = 6       /* 1: finalize re-derives every read's row and compares it with its
                                    EC's row, turning a 128-bit hash collision into an error */
 };
@@ -142,6 +142,59 @@ int ecb_destroy(ecb_ctx* ctx);
 
 /* Message of the last failing call on this context (or of ecb_create when ctx is NULL). */
 const char* ecb_last_error(const ecb_ctx* ctx);
+
+/* ---- multi-GPU exchange -------------------------------------------------------------------------
+ * Reads shard across GPUs by contiguous chunk (alntools/utils.py:67-87 + bam_utils.py:647-680: each
+ * worker gets a contiguous run of chunks and results are merged in chunk order).  Each rank pushes its
+ * shard into a LOCAL context with order_base = global offset of the shard.  The merge of
+ * alntools/bam_utils.py:680-698 then becomes:
+ *   1. ecb_export_partition on the local context: local ECs packed into `world` partitions by owner
+ *      rank (hash of the 128-bit key);
+ *   2. the host exchanges the partitions (NCCL all-to-all through torch.distributed);
+ *   3. ecb_import_entries on a fresh OWNER context: equal keys are merged (counts summed, smallest
+ *      first-occurrence kept), rows adopted;
+ *   4. ecb_global_mark / all-reduce(bitmap) / ecb_global_count: EC ids = rank of the first-occurrence
+ *      bit in the bitmap OR-ed over all ranks;
+ *   5. ecb_global_lens / all-reduce / ecb_global_indptr / ecb_global_rows / all-reduce: every rank
+ *      scatters its owned rows and counts into zero-initialised global arrays; supports are disjoint,
+ *      so a SUM all-reduce assembles the final CSR A matrix and the counts on every rank.
+ * All pointers marked "device" are device memory of the context's GPU owned by the caller.
+ */
+#define ECB_EXPORT_META_WORDS 5
+typedef struct ecb_export {
+  int64_t n_ec;                    /* local ECs exported                                           */
+  int64_t n_rows;                  /* (target, mask) pairs exported                                */
+  const int64_t* meta;             /* device [n_ec * 5]: key_lo, key_hi, first, count<<32|row_len,
+                                      row offset inside its partition                              */
+  const int32_t* rows;             /* device [n_rows * 2]: (target_idx, hap_mask), partition-major */
+  const int64_t* part_ec_counts;   /* host [world]                                                 */
+  const int64_t* part_row_counts;  /* host [world]                                                 */
+  int64_t min_base, max_end;       /* order-key range this rank has pushed                         */
+} ecb_export;
+
+int ecb_export_partition(ecb_ctx* ctx, int world, ecb_export* out);
+
+/* Merge n_parts received partitions (concatenated, in source-rank order) into this OWNER context. */
+int ecb_import_entries(ecb_ctx* ctx, const int64_t* meta_device, const int32_t* rows_device,
+                       const int64_t* part_ec_counts, const int64_t* part_row_counts, int n_parts);
+
+/* Set the first-occurrence bits of the ECs this context owns in bitmap[n_words] (bit i = order key
+ * min_base + i).  The caller zero-fills the bitmap and all-reduces it afterwards. */
+int ecb_global_mark(ecb_ctx* ctx, int64_t min_base, uint32_t* bitmap_device, int64_t n_words);
+
+/* Rank the bits of the (all-reduced) bitmap: *n_ec_total = number of set bits = global EC count. */
+int ecb_global_count(ecb_ctx* ctx, const uint32_t* bitmap_device, int64_t n_words, int64_t* n_ec_total);
+
+/* Scatter row lengths and read counts of the owned ECs into zero-filled lens[n_ec_total+1] and
+ * counts[n_ec_total] at their global ids. */
+int ecb_global_lens(ecb_ctx* ctx, int32_t* lens_device, int32_t* counts_device);
+
+/* In-place exclusive scan lens -> indptr (n = n_ec_total + 1); *nnz = indptr[n_ec_total]. */
+int ecb_global_indptr(ecb_ctx* ctx, int32_t* lens_device, int64_t n, int64_t* nnz);
+
+/* Scatter the owned rows into zero-filled indices[nnz] / data[nnz] at indptr[global id]. */
+int ecb_global_rows(ecb_ctx* ctx, const int32_t* indptr_device, int32_t* indices_device,
+                    int32_t* data_device);
 
 #ifdef __cplusplus
 }

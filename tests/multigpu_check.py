@@ -1,0 +1,61 @@
+"""Multi-GPU parity check, launched one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tests/multigpu_check.py [n_reads]
+
+Every rank builds its contiguous shard of a seeded synthetic workload on its own B200, the ranks
+exchange hash-partitioned ECs over NCCL (alntools_b200/multi_gpu.py) and every rank must end up with
+exactly the matrices the C oracle computes for the whole, unsharded input."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from alntools_b200 import multi_gpu, synth
+    from alntools_b200._native import EcBuilder
+    from oracle import c_oracle
+
+    for seed, mode, n_targets, n_haps in ((11, "diploid", 20000, 2), (12, "heavy", 3000, 8)):
+        reads = n_reads if mode == "diploid" else n_reads // 20
+        cols = synth.make_columns(reads, n_targets, n_haps, seed=seed, mode=mode, dup_rate=0.01)
+        rg, tg, hp = cols["read_group"], cols["target_idx"], cols["hap_idx"]
+        cuts = multi_gpu.shard_bounds(rg, world)
+        a, b = cuts[rank], cuts[rank + 1]
+        local_b = EcBuilder(n_targets, n_haps, alignments_hint=b - a, device=local)
+        local_b.push(np.ascontiguousarray(rg[a:b]), np.ascontiguousarray(tg[a:b]), np.ascontiguousarray(hp[a:b]),
+                     order_base=a)
+        res = multi_gpu.distributed_finalize(
+            local_b, lambda: EcBuilder(n_targets, n_haps, alignments_hint=b - a, device=local), dev)
+        indptr, indices, data, counts, n_reads_o = c_oracle.ec_from_columns(rg, tg, hp)
+        ok = (np.array_equal(res["a_indptr"].cpu().numpy(), indptr)
+              and np.array_equal(res["a_indices"].cpu().numpy(), indices)
+              and np.array_equal(res["a_data"].cpu().numpy(), data)
+              and np.array_equal(res["n_data"].cpu().numpy(), counts))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("multigpu_check world=%d mode=%s reads=%d alignments=%d ECs=%d: %s"
+                  % (world, mode, reads, len(rg), len(counts), "OK" if flag.item() else "MISMATCH"), flush=True)
+        if not flag.item():
+            dist.destroy_process_group()
+            sys.exit(1)
+        local_b.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,11 +148,11 @@ def test_table_growth_and_overflow_replay(native):
     assert stats["table_grows"] >= 1 and stats["overflow_reads"] > 0
 
 
-def test_warp_aggregation_off_gives_the_same_result(native):
+def test_hot_cache_off_gives_the_same_result(native):
     from alntools_b200 import synth
     cols = synth.make_columns(40000, 300, 2, seed=22, mode="light", dup_rate=0.02)
-    a, _ = _run(native, cols, 300, 2, warp_aggregate=1)
-    b, _ = _run(native, cols, 300, 2, warp_aggregate=0)
+    a, _ = _run(native, cols, 300, 2, hot_cache=1)
+    b, _ = _run(native, cols, 300, 2, hot_cache=0)
     for k in ("a_indptr", "a_indices", "a_data", "n_data"):
         assert np.array_equal(a[k], b[k])
     _assert_same(a, _oracle(cols))
@@ -272,3 +272,86 @@ def test_full_size_cfg2_properties_and_oracle(native):
     for k in ("a_indptr", "a_indices", "a_data", "n_data"):
         assert np.array_equal(got[k], again[k])
     _assert_same(got, _oracle(cols))
+
+
+# ---------------------------------------------------------------- multi-GPU exchange (needs >= 2 GPUs)
+def test_multigpu_exchange_matches_oracle(native):
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    world = 2 if n < 4 else 4
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(ROOT, "tests", "multigpu_check.py"), "300000"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("OK") == 2
+
+
+def test_exchange_primitives_single_gpu(native):
+    """The export -> import -> global id path with world = 1..3 emulated on ONE GPU: all partitions
+    are imported into owner contexts on the same device and the bitmap 'all-reduce' is a local sum."""
+    import torch
+    from alntools_b200 import synth
+    cols = synth.make_columns(120000, 4000, 2, seed=41, mode="diploid", dup_rate=0.02)
+    rg, tg, hp = cols["read_group"], cols["target_idx"], cols["hap_idx"]
+    want = _oracle(cols)
+    dev = torch.device("cuda", 0)
+    from alntools_b200 import multi_gpu
+    for world in (1, 2, 3):
+        cuts = multi_gpu.shard_bounds(rg, world)
+        exports = []
+        locals_ = []
+        for r in range(world):
+            a, b = cuts[r], cuts[r + 1]
+            lb = native.EcBuilder(4000, 2, alignments_hint=b - a)
+            lb.push(np.ascontiguousarray(rg[a:b]), np.ascontiguousarray(tg[a:b]), np.ascontiguousarray(hp[a:b]), order_base=a)
+            locals_.append(lb)
+            exports.append(lb.export_partition(world))
+        owners = []
+        for o in range(world):   # what all_to_all would deliver to owner o
+            metas, rows, ecn, rown = [], [], [], []
+            for src in range(world):
+                meta, row, ec_counts, row_counts, _, _ = exports[src]
+                e0, r0 = sum(ec_counts[:o]), sum(row_counts[:o])
+                metas.append(meta[e0:e0 + ec_counts[o]])
+                rows.append(row[r0:r0 + row_counts[o]])
+                ecn.append(ec_counts[o])
+                rown.append(row_counts[o])
+            ob = native.EcBuilder(4000, 2, alignments_hint=len(rg))
+            ob.import_entries(torch.cat(metas).contiguous(), torch.cat(rows).contiguous(), ecn, rown)
+            owners.append(ob)
+        n_words = (len(rg) + 31) // 32 + 1
+        bitmap = torch.zeros(n_words, dtype=torch.int32, device=dev)
+        for ob in owners:
+            part = torch.zeros_like(bitmap)
+            ob.global_mark(0, part)
+            bitmap += part
+        totals = [ob.global_count(bitmap) for ob in owners]
+        assert len(set(totals)) == 1 and totals[0] == len(want[3])
+        n_ec = totals[0]
+        lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=dev)
+        counts = torch.zeros(n_ec, dtype=torch.int32, device=dev)
+        for ob in owners:
+            l, c = torch.zeros_like(lens), torch.zeros_like(counts)
+            ob.global_lens(l, c)
+            lens += l
+            counts += c
+        nnz = owners[0].global_indptr(lens)
+        indices = torch.zeros(nnz, dtype=torch.int32, device=dev)
+        data = torch.zeros(nnz, dtype=torch.int32, device=dev)
+        for ob in owners:
+            i, d = torch.zeros_like(indices), torch.zeros_like(data)
+            ob.global_rows(lens, i, d)
+            indices += i
+            data += d
+        assert np.array_equal(lens.cpu().numpy(), want[0])
+        assert np.array_equal(indices.cpu().numpy(), want[1])
+        assert np.array_equal(data.cpu().numpy(), want[2])
+        assert np.array_equal(counts.cpu().numpy(), want[3])
+        for b in locals_ + owners:
+            b.close()
