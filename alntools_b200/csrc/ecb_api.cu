@@ -35,7 +35,7 @@ struct ecb_ctx {
   int64_t hint = 0;
   // options
   int result_on_device = 0;
-  int64_t opt_table_slots = 0, opt_pair_slots = 0, opt_grid = 0;
+  int64_t opt_table_slots = 0, opt_pair_slots = 0, opt_grid = 0, opt_chunk_len = 0;
   int use_cache = 1;
   int verify_keys = 0;
   // EC table
@@ -295,13 +295,16 @@ int group_prepare_launch(ecb_ctx* c) {
   return ECB_OK;
 }
 
-int group_resident_ctas(ecb_ctx* c) {
-  int per_sm = 0;
-  cudaError_t e = c->with_cells
-      ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<true>, ECB_TILE_THREADS, sizeof(GroupSmem))
-      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ecb_group_insert_kernel<false>, ECB_TILE_THREADS, sizeof(GroupSmem));
-  if (e != cudaSuccess || per_sm < 1) per_sm = 2;
-  return per_sm * c->sm_count;
+// Launch geometry of the grouping kernel: one persistent CTA per SM, every warp takes chunks of
+// `chunk_len` alignments from a shared counter.
+void group_geometry(ecb_ctx* c, int64_t n, int* grid, int* chunk_len) {
+  const int64_t warps = (int64_t)c->sm_count * ECB_GWARPS;
+  int64_t cl = c->opt_chunk_len > 0 ? c->opt_chunk_len : std::min<int64_t>(4096, std::max<int64_t>(256, n / (warps * 4)));
+  cl = (cl + 31) / 32 * 32;
+  const int64_t chunks = (n + cl - 1) / cl;
+  int64_t g = c->opt_grid > 0 ? c->opt_grid : std::min<int64_t>(c->sm_count, (chunks + ECB_GWARPS - 1) / ECB_GWARPS);
+  *grid = (int)std::max<int64_t>(1, g);
+  *chunk_len = (int)cl;
 }
 
 int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int32_t* hp, int64_t n, u32 e0,
@@ -563,6 +566,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_GRID_CTAS: c->opt_grid = value; break;
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
+    case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
     default: return fail(c, ECB_ERR_INVALID, "unknown option %d", option);
   }
   return ECB_OK;
@@ -580,7 +584,7 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
              const int32_t* cell_idx, int64_t n, int64_t order_base, int drop_last_group, int on_device) {
   if (!c) return ECB_ERR_INVALID;
   if (n < 0 || order_base < 0) return fail(c, ECB_ERR_INVALID, "negative n or order_base");
-  if (n > 0x7FFFFFFFll - 4 * ECB_TILE) return fail(c, ECB_ERR_LIMIT, "a push is limited to 2^31-4096 alignments; split it");
+  if (n > 0x7FFFFFFFll - 8192) return fail(c, ECB_ERR_LIMIT, "a push is limited to 2^31-8192 alignments; split it");
   if (n > 0 && (!read_group || !target_idx || !hap_idx)) return fail(c, ECB_ERR_INVALID, "NULL column");
   if (c->with_cells && n > 0 && !cell_idx) return fail(c, ECB_ERR_INVALID, "context has cells but cell_idx is NULL");
   if (!c->with_cells && cell_idx) return fail(c, ECB_ERR_INVALID, "cell_idx given but context was created without cells");
@@ -624,16 +628,15 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
 
   const u32 e_before = c->n_ec;
   CKR(group_prepare_launch(c));
-  const int max_ctas = c->opt_grid > 0 ? (int)c->opt_grid : group_resident_ctas(c);
-  const int64_t tiles = (n + ECB_TILE - 1) / ECB_TILE;
-  const int grid = (int)std::min<int64_t>(tiles, max_ctas);
-  const int64_t tiles_per_cta = (tiles + grid - 1) / grid;
+  int grid = 1, chunk_len = 32;
+  group_geometry(c, n, &grid, &chunk_len);
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
-  P.chunk_len = (int)(tiles_per_cta * ECB_TILE);
+  P.chunk_len = chunk_len;
+  CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_TILE_THREADS, sizeof(GroupSmem), c->stream>>>(P);
-  else ecb_group_insert_kernel<false><<<grid, ECB_TILE_THREADS, sizeof(GroupSmem), c->stream>>>(P);
+  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
   CK(cudaEventRecord(c->ev[2], c->stream));
   CKR(sync_counters(c));

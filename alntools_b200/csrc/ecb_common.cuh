@@ -137,7 +137,7 @@ struct EcbCounters {
   u32 n_triples;      // entries in the (file, EC, cell) table
   u32 n_triple_overflow;
   u32 n_spill;        // hot-cache entries parked because the table was too full
-  u32 pad0;
+  u32 chunk_next;     // next unclaimed chunk of the grouping kernel (reset before every launch)
   u64 arena_used;     // (target, mask) pairs in the row arena
   u32 scratch[8];
 };

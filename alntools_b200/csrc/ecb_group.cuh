@@ -5,31 +5,35 @@
 // by read, collapse duplicate tids, ec[key] += 1) and the ordering half of :680-698 (EC id = rank of
 // the key's first occurrence), on int32 columns.
 //
-// Shape of the kernel (HBM-bound integer work, no tensor cores):
-//   * one CTA per contiguous chunk of the alignment stream (grid = resident CTAs x 148 SMs).  The CTA
-//     walks its chunk in tiles of 1024 alignments; the three columns of the NEXT tile are fetched by
-//     the TMA engine (cp.async.bulk, 3 x 4 KB, mbarrier completion) into a two-stage shared-memory
-//     ring while the current tile is processed, so no thread spends registers or issue slots on the
-//     streaming loads;
-//   * a read is owned by the CTA in whose chunk it STARTS; the owner runs past its chunk end until
-//     the read closes, the next CTA skips the leading partial read;
-//   * inside a tile every warp owns 128 consecutive alignments as 4 rows of 32 (lane = consecutive
-//     alignment), so read boundaries, read starts, duplicate (target, haplotype) pairs and per-read
-//     sums are warp-wide bit tricks: one ballot gives every lane its read start, one 64-bit
-//     __match_any_sync on (read start, element code) finds duplicates inside a read, one on the read
-//     start groups the lanes of a read, and __reduce_add_sync adds the 128-bit element mixes of a
-//     read (commutative set hash -> no per-read sort);
-//   * closed reads are compacted into a shared-memory queue so the insert phase runs with full
-//     warps; a per-CTA shared-memory cache absorbs the hot ECs (a few hundred keys carry more than
-//     half of the reads), everything else goes to the HBM table: one 256-bit sector load per probe,
-//     a 128-bit atomicCAS only when the slot looks empty, RED.ADD on the count and atomicMin on the
-//     first-occurrence key only when it can lower it.  The cache is flushed at the end of the chunk.
+// Shape of the kernel (HBM-bound integer work, no tensor cores; the binding resource after the
+// column stream is instruction issue, so the design minimises warp instructions per alignment):
+//   * one persistent CTA per SM (grid = 148), 32 warps; every WARP owns one contiguous chunk of the
+//     alignment stream and walks it on its own — no CTA-wide barrier, no cross-warp carry;
+//   * a warp looks at a WINDOW of 32 consecutive alignments (lane = alignment) that always starts at
+//     a read start.  One ballot of the "last alignment of its read" flags gives every lane its read
+//     start, one __match_any_sync on the element code finds duplicate (target, haplotype) pairs
+//     inside a read, a segmented shuffle scan with only ceil(log2(longest read in the window))
+//     steps adds the 128-bit element mixes of a read (commutative set hash -> no per-read sort).
+//     The window then advances to the first alignment after its last COMPLETE read, so no read ever
+//     straddles two windows; the columns of the next window are requested before the current one
+//     is processed and the lines further ahead are pulled into L2 by prefetches, so the dependent
+//     window address never waits for HBM.  Reads longer than a window take a warp-cooperative path;
+//   * a read is owned by the warp in whose chunk it STARTS; the owner runs past its chunk end until
+//     the read closes, the next warp starts at the first read start inside its chunk;
+//   * closed reads first try the per-CTA shared-memory cache of hot ECs (4096 entries; the top few
+//     thousand ECs carry more than half of the reads).  Misses are parked in a per-warp
+//     shared-memory queue — with an L2 prefetch of their table sector — and inserted into the HBM
+//     table 32 at a time with a full warp: one 256-bit sector load per probe, a 128-bit atomicCAS
+//     only when the slot looks empty, RED.ADD on the count and atomicMin on the first-occurrence key
+//     only when it can lower it.  The cache is flushed when the CTA has finished its chunks.
 #pragma once
 #include "ecb_common.cuh"
 
-#define ECB_ROWS 4                     // rows of 32 alignments per warp and tile
-#define ECB_WARP_SPAN (32 * ECB_ROWS)  // 128
-#define ECB_CACHE 512                  // per-CTA hot-EC cache entries
+#define ECB_GWARPS 32                  // warps per CTA of the grouping kernel
+#define ECB_GTHREADS (32 * ECB_GWARPS)
+#define ECB_CACHE 4096                 // per-CTA hot-EC cache entries
+#define ECB_MQ 64                      // per-warp miss-queue ring (entries)
+#define ECB_PF_DIST 256                // L2 prefetch distance of the column stream (alignments)
 
 // A hot-cache entry that could not be flushed because the table was too full (replayed after growth).
 struct EcbSpill {
@@ -61,33 +65,6 @@ struct GroupParams {
   u32 tmask;
   u32 push_id;
 };
-
-// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) ----------------------------------------------------
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-  u32 done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
-}
 
 // Find `key` or claim an empty slot for it.  Returns the slot, or ECB_NONE when ECB_MAX_PROBE
 // slots were tried.  first_seen = the entry's `first` as loaded (+inf when unknown/new).
@@ -194,335 +171,292 @@ __device__ __forceinline__ u32 global_upsert(const GroupParams& P, const Key128&
   return slot;
 }
 
-__device__ __forceinline__ Mix4 shfl_up_mix(const Mix4& m, int d) {
-  Mix4 r;
-  r.a = __shfl_up_sync(ECB_FULL, m.a, d);
-  r.b = __shfl_up_sync(ECB_FULL, m.b, d);
-  r.c = __shfl_up_sync(ECB_FULL, m.c, d);
-  r.d = __shfl_up_sync(ECB_FULL, m.d, d);
-  return r;
-}
-
-__device__ __forceinline__ Mix4 shfl_mix(const Mix4& m, int src) {
-  Mix4 r;
-  r.a = __shfl_sync(ECB_FULL, m.a, src);
-  r.b = __shfl_sync(ECB_FULL, m.b, src);
-  r.c = __shfl_sync(ECB_FULL, m.c, src);
-  r.d = __shfl_sync(ECB_FULL, m.d, src);
-  return r;
-}
-
 struct GroupSmem {
-  // two-stage ring of the three columns of a tile (filled by TMA bulk copies)
-  alignas(128) int32_t col[2][3][ECB_TILE];
-  // queue of closed reads of the current tile
-  alignas(16) uint4 qkey[ECB_TILE];
-  u32 qpos[ECB_TILE];
-  u32 qlen[ECB_TILE];
-  // hot-EC cache of this CTA
-  alignas(8) u64 c_lo[ECB_CACHE];
-  u64 c_hi[ECB_CACHE];
-  u64 c_replen[ECB_CACHE];  // len << 32 | offset of one read with this key
-  u32 c_cnt[ECB_CACHE];
-  u32 c_first[ECB_CACHE];  // len << 32 | offset of one read with this key
-  // per-warp summaries
-  int w_last_head[ECB_WARPS];
-  u32 w_flag[ECB_WARPS];
-  Mix4 w_sum[ECB_WARPS];
-  alignas(8) u64 bar[2];
+  // hot-EC cache of this CTA (direct mapped, first come first installed, flushed at the end)
+  alignas(16) uint4 c_key[ECB_CACHE];
+  u32 c_tag[ECB_CACHE];    // 0 = empty, 1 = being installed, else the ready entry's tag
+  u32 c_cnt[ECB_CACHE];    // reads counted in this entry
+  u32 c_first[ECB_CACHE];  // smallest offset (in this push) of a read with this key
+  u32 c_rep[ECB_CACHE];    // offset and length of one read with this key (the installer's)
+  u32 c_len[ECB_CACHE];
+  // per-warp queues of reads that missed the cache
+  alignas(16) uint4 q_key[ECB_GWARPS][ECB_MQ];
+  u32 q_pos[ECB_GWARPS][ECB_MQ];
+  u32 q_len[ECB_GWARPS][ECB_MQ];
 };
 
+__device__ __forceinline__ Key128 key_of(const uint4& k) {
+  return Key128{((u64)k.y << 32) | k.x, ((u64)k.w << 32) | k.z};
+}
+__device__ __forceinline__ uint4 key_words(const Mix4& m) {
+  const Key128 k = mix_to_key(m);
+  return make_uint4((u32)k.lo, (u32)(k.lo >> 32), (u32)k.hi, (u32)(k.hi >> 32));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One read that missed the cache goes into the HBM table.
 template <bool WITH_CELLS>
-__global__ void __launch_bounds__(ECB_TILE_THREADS, 3) ecb_group_insert_kernel(const GroupParams P) {
+__device__ __forceinline__ void insert_miss(const GroupParams& P, const uint4& kq, u32 s, u32 len) {
+  const u32 slot = global_upsert(P, key_of(kq), 1u, s, s, len);
+  if (slot == ECB_NONE) {  // table too full: the host grows it and replays the flagged reads
+    atomicOr(&P.overflow_bits[s >> 5], 1u << (s & 31));
+    atomicAdd(&P.ctr->n_overflow, 1u);
+  } else if (WITH_CELLS) {
+    triple_upsert(P, slot, (u32)P.cell[s], P.order_base + s);
+  }
+}
+
+// Key and length of a read that starts at w and fills a whole window (>= 32 alignments).
+// Warp-cooperative: walks the read in blocks of 32; duplicates inside a block come from one
+// match, duplicates against the earlier blocks of the read from shuffled compares.
+__device__ __noinline__ int ecb_long_read(const GroupParams& P, int w, uint4* key_out) {
+  const int lane = threadIdx.x & 31;
+  const u32 lt_mask = (1u << lane) - 1u;
+  const int n = P.n;
+  const int rg0 = P.rg[w];
+  Mix4 sum = mix_zero();
+  int len = 0;
+  bool bad = false, too_long = false;
+  for (int b = 0;; ++b) {
+    const int pos = w + 32 * b + lane;
+    bool in = pos < n;
+    const int r = in ? P.rg[pos] : 0;
+    const int t = in ? P.tg[pos] : 0, h = in ? P.hp[pos] : 0;
+    in = in && r == rg0;
+    const u32 m = __ballot_sync(ECB_FULL, in);  // the read is contiguous: m is a run of low bits
+    const u32 code = in ? ecb_code(t, h) : (0x80000000u | (u32)lane);
+    bad |= in && ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps);
+    bool dup = (__match_any_sync(ECB_FULL, code) & lt_mask) != 0u;
+    if (!too_long) {
+      for (int e = 0; e < b; ++e) {
+        const int pe = w + 32 * e + lane;
+        const u32 ce = ecb_code(P.tg[pe], P.hp[pe]);
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) dup |= __shfl_sync(ECB_FULL, ce, j) == code;
+      }
+    }
+    if (in && !dup) mix_add(sum, ecb_mix(code));
+    len += __popc(m);
+    if (m != ECB_FULL) break;
+    if (len > ECB_MAX_READ_ALIGNMENTS) too_long = true;
+  }
+  if (bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+  if (too_long && lane == 0) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
+  sum.a = __reduce_add_sync(ECB_FULL, sum.a);
+  sum.b = __reduce_add_sync(ECB_FULL, sum.b);
+  sum.c = __reduce_add_sync(ECB_FULL, sum.c);
+  sum.d = __reduce_add_sync(ECB_FULL, sum.d);
+  *key_out = key_words(sum);
+  return len;
+}
+
+template <bool WITH_CELLS>
+__global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const GroupParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1u;
   const int n = P.n;
-  const long long cb64 = (long long)blockIdx.x * P.chunk_len;
-  if (cb64 >= n) return;
-  const int cb = (int)cb64;
-  const int ce = min(cb + P.chunk_len, n);
+  const bool use_cache = !WITH_CELLS && P.use_cache;
 
-  for (int i = tid; i < ECB_CACHE; i += ECB_TILE_THREADS) {
-    S.c_lo[i] = ~0ull;
-    S.c_hi[i] = ~0ull;
-    S.c_cnt[i] = 0u;
-    S.c_first[i] = 0xFFFFFFFFu;
-  }
-  if (tid == 0) {
-    mbar_init(&S.bar[0], 1);
-    mbar_init(&S.bar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (use_cache) {
+    for (int i = tid; i < ECB_CACHE; i += ECB_GTHREADS) {
+      S.c_tag[i] = 0u;
+      S.c_cnt[i] = 0u;
+      S.c_first[i] = 0xFFFFFFFFu;
+    }
   }
   __syncthreads();
-  if (tid == 0 && cb + ECB_TILE <= n) {
-    mbar_expect_tx(&S.bar[0], 3 * ECB_TILE * 4);
-    bulk_g2s(S.col[0][0], P.rg + cb, ECB_TILE * 4, &S.bar[0]);
-    bulk_g2s(S.col[0][1], P.tg + cb, ECB_TILE * 4, &S.bar[0]);
-    bulk_g2s(S.col[0][2], P.hp + cb, ECB_TILE * 4, &S.bar[0]);
-  }
 
-  int carry_head = -1;           // latest read start seen in [cb, current tile)
-  Mix4 carry_sum = mix_zero();   // key contributions of the read that is open at the tile boundary
-  u32 reads_counted = 0;
+  uint4* const qk = S.q_key[warp];
+  u32* const qp = S.q_pos[warp];
+  u32* const ql = S.q_len[warp];
+  u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
+  u32 reads_counted = 0;  // warp-uniform
 
-  for (int tile = 0;; ++tile) {
-    const int tile_base = cb + tile * ECB_TILE;
-    const int stg = tile & 1;
-    const int wbase = tile_base + warp * ECB_WARP_SPAN;
+  for (;;) {
+    // ---- next chunk of the stream (dynamic: whichever warp is free takes it) -------------------------
+    u32 ci = 0;
+    if (lane == 0) ci = atomicAdd(&P.ctr->chunk_next, 1u);
+    ci = __shfl_sync(ECB_FULL, ci, 0);
+    const long long cb64 = (long long)ci * P.chunk_len;
+    if (cb64 >= n) break;
+    const int cb = (int)cb64;
+    const int ce = (int)min(cb64 + P.chunk_len, (long long)n);
 
-    // ---- stage in: wait for the TMA copies of this tile (or fill a partial last tile by hand) ------
-    if (tile_base + ECB_TILE <= n) {
-      mbar_wait(&S.bar[stg], (u32)(tile >> 1) & 1u);
-    } else {
-      for (int i = tid; i < ECB_TILE; i += ECB_TILE_THREADS) {
-        const int pos = tile_base + i;
-        const bool in = pos < n;
-        S.col[stg][0][i] = in ? P.rg[pos] : 0;
-        S.col[stg][1][i] = in ? P.tg[pos] : 0;
-        S.col[stg][2][i] = in ? P.hp[pos] : 0;
-      }
-      __syncthreads();
-    }
-    // prefetch the next tile into the other stage (its last readers finished before barrier (3) of
-    // the previous iteration)
-    if (tid == 0 && (long long)tile_base + 2 * ECB_TILE <= (long long)n) {
-      const int nb = tile_base + ECB_TILE;
-      mbar_expect_tx(&S.bar[stg ^ 1], 3 * ECB_TILE * 4);
-      bulk_g2s(S.col[stg ^ 1][0], P.rg + nb, ECB_TILE * 4, &S.bar[stg ^ 1]);
-      bulk_g2s(S.col[stg ^ 1][1], P.tg + nb, ECB_TILE * 4, &S.bar[stg ^ 1]);
-      bulk_g2s(S.col[stg ^ 1][2], P.hp + nb, ECB_TILE * 4, &S.bar[stg ^ 1]);
-    }
-
-    const int32_t* s_rg = S.col[stg][0];
-    const int32_t* s_tg = S.col[stg][1];
-    const int32_t* s_hp = S.col[stg][2];
-
-    // ---- head flags: lane = consecutive alignment, 4 rows per warp ---------------------------------
-    int rgv[ECB_ROWS];
-    u32 code[ECB_ROWS];
-    u32 hb[ECB_ROWS];      // ballot of head flags per row
-    bool range_bad = false;
-    int before0 = 0;       // read_group of the alignment right before this warp's span
-    if (lane == 0 && wbase > 0 && wbase - 1 < n) before0 = (warp > 0) ? s_rg[warp * ECB_WARP_SPAN - 1] : P.rg[wbase - 1];
-#pragma unroll
-    for (int r = 0; r < ECB_ROWS; ++r) {
-      const int li = warp * ECB_WARP_SPAN + r * 32 + lane;
-      const int pos = tile_base + li;
-      rgv[r] = s_rg[li];
-      const int t = s_tg[li], h = s_hp[li];
-      const bool valid = pos < n;
-      code[r] = valid ? ecb_code(t, h) : 0xFFFFFFFFu;
-      range_bad |= valid && ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps);
-      int prev = __shfl_up_sync(ECB_FULL, rgv[r], 1);
-      const int prev_row_last = __shfl_sync(ECB_FULL, r > 0 ? rgv[r - 1] : 0, 31);
-      if (lane == 0) prev = (r == 0) ? before0 : prev_row_last;
-      const bool hd = (pos <= n) && (pos == n || pos == 0 || rgv[r] != prev);  // n = virtual closing head
-      hb[r] = __ballot_sync(ECB_FULL, hd);
-    }
-    if (range_bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
-    int lh = -1;  // latest head inside this warp's span (warp-uniform)
-#pragma unroll
-    for (int r = 0; r < ECB_ROWS; ++r)
-      if (hb[r]) lh = wbase + r * 32 + 31 - __clz(hb[r]);
-    if (lane == 0) S.w_last_head[warp] = lh;
-    // head flag of the position right after this warp's span (needed by lane 31 of the last row)
-    bool next_span_head = false;
-    if (lane == 31) {
-      const int pos = wbase + ECB_WARP_SPAN;
-      if (pos == n) next_span_head = true;
-      else if (pos < n)
-        next_span_head = ((warp < ECB_WARPS - 1) ? s_rg[(warp + 1) * ECB_WARP_SPAN] : P.rg[pos]) != rgv[ECB_ROWS - 1];
-    }
-    __syncthreads();  // (1) per-warp head summaries visible
-
-    int open_st = carry_head;  // start of the read that is open at the beginning of this warp's span
-    int tile_last_head = carry_head;
-#pragma unroll
-    for (int w = 0; w < ECB_WARPS; ++w) {
-      const int v = S.w_last_head[w];
-      if (w < warp) open_st = max(open_st, v);
-      tile_last_head = max(tile_last_head, v);
-    }
-
-    // ---- per row: read start, duplicates, per-read sums --------------------------------------------
-    Mix4 sum[ECB_ROWS];
-    int st[ECB_ROWS];
-    u32 pushb[ECB_ROWS];   // ballot: lane closes an owned read in this row
-#pragma unroll
-    for (int r = 0; r < ECB_ROWS; ++r) {
-      const int rowbase = wbase + r * 32;
-      const int pos = rowbase + lane;
-      const bool valid = pos < n;
-      const u32 m = hb[r] & (lt_mask | (1u << lane));
-      st[r] = m ? rowbase + 31 - __clz(m) : open_st;
-      const bool owned = st[r] >= 0 && st[r] < ce;
-      // duplicates of (read, element) inside the row
-      const u64 k64 = valid ? (((u64)(u32)st[r] << 32) | code[r]) : (0xFFFFFFFF00000000ull | (u32)lane);
-      const u32 dm = __match_any_sync(ECB_FULL, k64);
-      bool contrib = valid && owned && (lane == __ffs(dm) - 1);
-      if (contrib && st[r] < rowbase) {  // the read began before this row: look at its earlier part
-        for (int j = rowbase - 1; j >= st[r]; --j) {
-          const int rel = j - tile_base;
-          const u32 cj = rel >= 0 ? ecb_code(s_tg[rel], s_hp[rel]) : ecb_code(P.tg[j], P.hp[j]);
-          if (cj == code[r]) {
-            contrib = false;
-            break;
-          }
+    // first read start inside the chunk (a read belongs to the chunk it starts in)
+    int w = cb;
+    if (cb > 0) {
+      w = -1;
+      for (int b = cb; b < ce; b += 32) {
+        const int pos = b + lane;
+        const bool hd = pos < ce && P.rg[pos] != P.rg[pos - 1];
+        const u32 m = __ballot_sync(ECB_FULL, hd);
+        if (m) {
+          w = b + __ffs(m) - 1;
+          break;
         }
       }
-      Mix4 X = ecb_mix(code[r]);
-      if (!contrib) X = mix_zero();
-      // segmented inclusive scan over the lanes of each read (segments = reads; a read continuing
-      // from the previous row forms the segment that starts at lane 0).  Only as many doubling
-      // steps as the longest segment of the row needs (warp-uniform, from the head ballot).
-      const int seg0 = max(st[r] - rowbase, 0);
-      const u32 x1 = ~(hb[r] | 1u);
-      const u32 x2 = x1 & (x1 >> 1);
-      const u32 x4 = x2 & (x2 >> 2);
-      const u32 x8 = x4 & (x4 >> 4);
-      const u32 x16 = x8 & (x8 >> 8);
-#define ECB_SEG_STEP(D)                                   \
-  {                                                       \
-    const Mix4 v = shfl_up_mix(X, D);                     \
-    if (lane - D >= seg0) mix_add(X, v);                  \
+      if (w < 0) continue;  // one long read covers the whole chunk
+    }
+
+    int rgv = 0, tgv = 0, hpv = 0;
+    if (w + lane < n) {
+      rgv = P.rg[w + lane];
+      tgv = P.tg[w + lane];
+      hpv = P.hp[w + lane];
+    }
+
+    // ---- windows of 32 alignments, each starting at a read start -------------------------------------
+    while (w < ce) {
+      const int pos = w + lane;
+      const int prev = __shfl_up_sync(ECB_FULL, rgv, 1);
+      const bool hd = lane == 0 || pos == n || (pos < n && rgv != prev);  // n = virtual closing head
+      const u32 hb = __ballot_sync(ECB_FULL, hd);
+
+      bool ins;     // this lane holds the last alignment of a complete, owned read
+      uint4 key;    // ... its key
+      u32 s, len;   // ... its first alignment and its number of alignments
+      int wnext;
+      if (hb == 1u) {
+        // one read fills the window
+        const int l = ecb_long_read(P, w, &key);
+        ins = lane == 0 && !(P.drop_last && w + l == n);
+        s = (u32)w;
+        len = (u32)l;
+        wnext = w + l;
+      } else {
+        const int last_head = 31 - __clz(hb);  // >= 1; lanes below it form complete reads
+        wnext = w + last_head;
+        const int st = 31 - __clz(hb & ((2u << lane) - 1u));  // lane of this alignment's read start
+        const bool active = lane < last_head;
+        const u32 code = ecb_code(tgv, hpv);
+        if (active && ((u32)tgv >= (u32)P.n_targets || (u32)hpv >= (u32)P.n_haps))
+          atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+        // an element counts once per read: drop it if a lower lane of the same read has the same code
+        const u32 same = __match_any_sync(ECB_FULL, code);
+        const bool contrib = active && ((same & lt_mask) >> st) == 0u;
+        Mix4 X = ecb_mix(code);
+        if (!contrib) X = mix_zero();
+        // segmented inclusive scan over the lanes of each read, with only as many doubling steps as
+        // the longest complete read of the window needs (warp-uniform, from the head ballot)
+        const u32 x1 = ~hb & ((1u << last_head) - 1u);
+        const u32 x2 = x1 & (x1 >> 1);
+        const u32 x4 = x2 & (x2 >> 2);
+        const u32 x8 = x4 & (x4 >> 4);
+        const u32 x16 = x8 & (x8 >> 8);
+#define ECB_SEG_STEP(D)                                \
+  {                                                    \
+    const u32 va = __shfl_up_sync(ECB_FULL, X.a, D);   \
+    const u32 vb = __shfl_up_sync(ECB_FULL, X.b, D);   \
+    const u32 vc = __shfl_up_sync(ECB_FULL, X.c, D);   \
+    const u32 vd = __shfl_up_sync(ECB_FULL, X.d, D);   \
+    if (lane - D >= st) {                              \
+      X.a += va; X.b += vb; X.c += vc; X.d += vd;      \
+    }                                                  \
   }
-      if (x1) ECB_SEG_STEP(1)
-      if (x2) ECB_SEG_STEP(2)
-      if (x4) ECB_SEG_STEP(4)
-      if (x8) ECB_SEG_STEP(8)
-      if (x16) ECB_SEG_STEP(16)
+        if (x1) ECB_SEG_STEP(1)
+        if (x2) ECB_SEG_STEP(2)
+        if (x4) ECB_SEG_STEP(4)
+        if (x8) ECB_SEG_STEP(8)
+        if (x16) ECB_SEG_STEP(16)
 #undef ECB_SEG_STEP
-      if (r > 0 && !(hb[r] & 1u)) {  // the read of the previous row's last lane continues here
-        const Mix4 cs = shfl_mix(sum[r - 1], 31);
-        if (st[r] < rowbase) mix_add(X, cs);
+        const bool is_end = active && ((hb >> 1) >> lane) & 1u;  // lane + 1 is a head
+        s = (u32)(w + st);
+        len = (u32)(lane - st + 1);
+        ins = is_end && (int)s < ce && !(P.drop_last && pos == n - 1);
+        key = key_words(X);
       }
-      sum[r] = X;
-      // does this lane hold the last alignment of its read?
-      bool nh = ((hb[r] >> 1) >> lane) & 1u;  // head flag of lane + 1
-      if (lane == 31) nh = (r < ECB_ROWS - 1) ? ((hb[r + 1] & 1u) != 0) : next_span_head;
-      const bool push = valid && nh && owned && !(P.drop_last && pos == n - 1);
-      pushb[r] = __ballot_sync(ECB_FULL, push);
-      if (hb[r]) open_st = rowbase + 31 - __clz(hb[r]);
-    }
-    // tail of the span: partial sum of the read that is still open at its end (without carry-in)
-    {
-      const Mix4 tail = shfl_mix(sum[ECB_ROWS - 1], 31);
-      if (lane == 0) {
-        S.w_sum[warp] = tail;
-        S.w_flag[warp] = lh >= 0 ? 1u : 0u;
-      }
-    }
-    __syncthreads();  // (2) per-warp tails visible
 
-    Mix4 Xc = carry_sum;  // contributions of the open read before this warp's span
-    Mix4 Xt = carry_sum;  // ... before the next tile
-#pragma unroll
-    for (int w = 0; w < ECB_WARPS; ++w) {
-      const Mix4 ws = S.w_sum[w];
-      const bool wf = S.w_flag[w] != 0;
-      if (w < warp) {
-        if (wf) Xc = ws; else mix_add(Xc, ws);
+      // ---- request the next window's columns now; they arrive while this window is inserted ---------
+      int nrg = 0, ntg = 0, nhp = 0;
+      if (wnext < ce) {
+        const int np = wnext + lane;
+        if (np < n) {
+          nrg = P.rg[np];
+          ntg = P.tg[np];
+          nhp = P.hp[np];
+        }
+        if (lane < 3) {  // pull the lines further ahead into L2 (one line per column per window)
+          const int pp = wnext + ECB_PF_DIST;
+          const int32_t* col = lane == 0 ? P.rg : (lane == 1 ? P.tg : P.hp);
+          if (pp < n) prefetch_l2(col + pp);
+        }
       }
-      if (wf) Xt = ws; else mix_add(Xt, ws);
-    }
-    // closed reads go to this warp's private queue region (no CTA-wide compaction needed)
-    u32 nq_w = 0;
-#pragma unroll
-    for (int r = 0; r < ECB_ROWS; ++r) {
-      if ((pushb[r] >> lane) & 1u) {
-        Mix4 y = sum[r];
-        if (st[r] < wbase) mix_add(y, Xc);  // read started before this warp's span: add what earlier warps / tiles saw
-        const Key128 k = mix_to_key(y);
-        const u32 q = warp * ECB_WARP_SPAN + nq_w + __popc(pushb[r] & lt_mask);
-        S.qkey[q] = make_uint4((u32)k.lo, (u32)(k.lo >> 32), (u32)k.hi, (u32)(k.hi >> 32));
-        S.qpos[q] = (u32)st[r];
-        S.qlen[q] = (u32)(wbase + r * 32 + lane - st[r] + 1);
-      }
-      nq_w += __popc(pushb[r]);
-    }
-    carry_sum = Xt;
-    carry_head = tile_last_head;
-    if (lane == 0) reads_counted += nq_w;
-    __syncwarp();
 
-    // ---- insert phase: every warp drains its own queue region with full warps -----------------------
-    for (u32 q0 = 0; q0 < nq_w; q0 += 32) {
-      const u32 qi = q0 + lane;
-      if (qi < nq_w) {
-        const u32 q = warp * ECB_WARP_SPAN + qi;
-        const uint4 kq = S.qkey[q];
-        const u32 s = S.qpos[q];
-        const u32 len = S.qlen[q];
-        Key128 key;
-        key.lo = ((u64)kq.y << 32) | kq.x;
-        key.hi = ((u64)kq.w << 32) | kq.z;
-        bool cached = false;
-        u32 cs = 0;
-        if (!WITH_CELLS && P.use_cache && key.lo != ~0ull) {
-          cs = (kq.x ^ (kq.z >> 7)) & (ECB_CACHE - 1);
-          const u64 lo = *reinterpret_cast<volatile u64*>(&S.c_lo[cs]);
-          bool lo_ok = lo == key.lo;
-          if (!lo_ok && lo == ~0ull) {
-            const u64 plo = atomicCAS(&S.c_lo[cs], ~0ull, key.lo);
-            lo_ok = (plo == ~0ull || plo == key.lo);
-          }
-          if (lo_ok) {
-            const u64 hi = *reinterpret_cast<volatile u64*>(&S.c_hi[cs]);
-            cached = hi == key.hi;
-            if (!cached && hi == ~0ull) {
-              const u64 phi = atomicCAS(&S.c_hi[cs], ~0ull, key.hi);
-              cached = (phi == ~0ull || phi == key.hi);
-              // exactly one thread installs the high half: its read becomes the key's representative
-              if (phi == ~0ull) S.c_replen[cs] = ((u64)len << 32) | s;
-            }
+      // ---- closed reads: hot-EC cache first --------------------------------------------------------
+      reads_counted += __popc(__ballot_sync(ECB_FULL, ins));
+      bool miss = ins;
+      if (use_cache && ins) {
+        const u32 cidx = (key.y >> 7) & (ECB_CACHE - 1);
+        const u32 tag = key.w | 2u;
+        u32 t = *reinterpret_cast<volatile u32*>(&S.c_tag[cidx]);
+        if (t == 0u) {
+          t = atomicCAS(&S.c_tag[cidx], 0u, 1u);
+          if (t == 0u) {  // this lane installs the entry; its read becomes the key's representative
+            S.c_key[cidx] = key;
+            S.c_rep[cidx] = s;
+            S.c_len[cidx] = len;
+            __threadfence_block();
+            *reinterpret_cast<volatile u32*>(&S.c_tag[cidx]) = tag;
+            t = tag;
           }
         }
-        if (cached) {
-          atomicAdd(&S.c_cnt[cs], 1u);
-          if (s < *reinterpret_cast<volatile u32*>(&S.c_first[cs])) atomicMin(&S.c_first[cs], s);
-        } else {
-          const u32 slot = global_upsert(P, key, 1u, s, s, len);
-          if (slot == ECB_NONE) {
-            atomicOr(&P.overflow_bits[s >> 5], 1u << (s & 31));
-            atomicAdd(&P.ctr->n_overflow, 1u);
-          } else if (WITH_CELLS) {
-            triple_upsert(P, slot, (u32)P.cell[s], P.order_base + s);
+        if (t == tag) {
+          const uint4 ck = S.c_key[cidx];
+          if (ck.x == key.x && ck.y == key.y && ck.z == key.z && ck.w == key.w) {
+            atomicAdd(&S.c_cnt[cidx], 1u);
+            if (s < *reinterpret_cast<volatile u32*>(&S.c_first[cidx])) atomicMin(&S.c_first[cidx], s);
+            miss = false;
           }
         }
       }
-    }
+      // ---- misses: park in the warp's queue, insert into the HBM table 32 at a time -----------------
+      const u32 mm = __ballot_sync(ECB_FULL, miss);
+      if (mm) {
+        if (miss) {
+          const u32 q = qn + __popc(mm & lt_mask);
+          qk[q] = key;
+          qp[q] = s;
+          ql[q] = len;
+          prefetch_l2(P.table + (key_slot_hash(key_of(key)) & P.mask));
+        }
+        qn += __popc(mm);
+        __syncwarp();
+        if (qn >= 32u) {
+          qn -= 32u;
+          insert_miss<WITH_CELLS>(P, qk[qn + lane], qp[qn + lane], ql[qn + lane]);
+          __syncwarp();
+        }
+      }
 
-    // ---- continue? ----------------------------------------------------------------------------------
-    const long long tile_end = (long long)tile_base + ECB_TILE;
-    bool stop = tile_end > n;                                  // the virtual head at n was in this tile
-    stop = stop || (tile_end >= ce && (carry_head < 0 || carry_head >= ce));  // no owned read is still open
-    if (stop) {
-      // a TMA prefetch of the next tile may still be in flight: it must land before the CTA retires
-      if ((long long)tile_base + 2 * ECB_TILE <= (long long)n) mbar_wait(&S.bar[stg ^ 1], (u32)((tile + 1) >> 1) & 1u);
-      break;
+      w = wnext;
+      rgv = nrg;
+      tgv = ntg;
+      hpv = nhp;
     }
   }
 
-  // ---- flush the hot-EC cache into the HBM table -------------------------------------------------------
+  // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
+  if ((u32)lane < qn) insert_miss<WITH_CELLS>(P, qk[lane], qp[lane], ql[lane]);
+  if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
   __syncthreads();
-  if (!WITH_CELLS && P.use_cache) {
-    for (int i = tid; i < ECB_CACHE; i += ECB_TILE_THREADS) {
+  if (use_cache) {
+    for (int i = tid; i < ECB_CACHE; i += ECB_GTHREADS) {
       const u32 cnt = S.c_cnt[i];
       if (cnt) {
-        const Key128 key{S.c_lo[i], S.c_hi[i]};
-        const u64 rl = S.c_replen[i];
-        const u32 slot = global_upsert(P, key, cnt, S.c_first[i], (u32)rl, (u32)(rl >> 32));
+        const uint4 k = S.c_key[i];
+        const Key128 key = key_of(k);
+        const u32 first = S.c_first[i], rep = S.c_rep[i], rlen = S.c_len[i];
+        const u32 slot = global_upsert(P, key, cnt, first, rep, rlen);
         if (slot == ECB_NONE) {  // table too full: park the entry, the host grows the table and replays it
           const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
-          P.spill[si] = EcbSpill{key.lo, key.hi, cnt, S.c_first[i], (u32)rl, (u32)(rl >> 32)};
+          P.spill[si] = EcbSpill{key.lo, key.hi, cnt, first, rep, rlen};
         }
       }
     }
   }
-  if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
 }
 
 // Key of the read that starts at offset s, computed serially (replay / verification path).

@@ -57,10 +57,11 @@ enum ecb_option {
   ECB_OPT_RESULT_ON_DEVICE = 1, /* 1: ecb_result pointers are DEVICE pointers (no D2H copy) */
   ECB_OPT_TABLE_SLOTS = 2,      /* initial EC hash-table capacity (rounded up to a power of two) */
   ECB_OPT_PAIR_SLOTS = 3,       /* initial (file, EC, cell) table capacity */
-  ECB_OPT_GRID_CTAS = 4,        /* CTAs of the grouping kernel (0 = resident CTAs x SMs) */
+  ECB_OPT_GRID_CTAS = 4,        /* CTAs of the grouping kernel (0 = one persistent CTA per SM) */
   ECB_OPT_HOT_CACHE = 5,        /* 1 (default): per-CTA shared-memory cache of hot ECs in front of the HBM table */
-  ECB_OPT_VERIFY_KEYS = 6       /* 1: finalize re-derives every read's row and compares it with its
+  ECB_OPT_VERIFY_KEYS = 6,      /* 1: finalize re-derives every read's row and compares it with its
                                    EC's row, turning a 128-bit hash collision into an error */
+  ECB_OPT_CHUNK_LEN = 7         /* alignments per work chunk of the grouping kernel (0 = automatic) */
 };
 
 typedef struct ecb_result {

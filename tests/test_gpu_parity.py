@@ -85,13 +85,14 @@ def test_columns_match_oracle(native, n_reads, n_targets, n_haps, mode, dup):
 
 
 def test_tile_and_chunk_boundaries(native):
-    """Sizes around the 1024-alignment tile and reads that straddle tile / CTA-chunk boundaries."""
+    """Sizes around the 32-alignment window and reads that straddle window / work-chunk boundaries."""
     from alntools_b200 import synth
-    for n_reads in (340, 341, 342, 512, 1024, 1025, 2047, 2048, 2049, 4096):
+    for n_reads in (15, 16, 17, 31, 32, 33, 340, 341, 342, 512, 1024, 1025, 2047, 2048, 2049, 4096):
         cols = synth.make_columns(n_reads, 40, 3, seed=n_reads, mode="diploid", dup_rate=0.1)
-        for grid in (0, 1, 3):
-            got, _ = _run(native, cols, 40, 3, grid_ctas=grid)
-            _assert_same(got, _oracle(cols))
+        want = _oracle(cols)
+        for grid, chunk in ((0, 0), (1, 32), (3, 64), (2, 96), (148, 32)):
+            got, _ = _run(native, cols, 40, 3, grid_ctas=grid, chunk_len=chunk)
+            _assert_same(got, want)
     # exactly one tile, exactly two tiles, one alignment per read
     for n in (1024, 2048, 3072):
         rg = np.arange(n, dtype=np.int32)
@@ -107,9 +108,10 @@ def test_giant_read_spanning_many_tiles(native):
     tg = rng.integers(0, 900, len(rg))
     hp = rng.integers(0, 4, len(rg))
     cols = {"read_group": rg.astype(np.int32), "target_idx": tg.astype(np.int32), "hap_idx": hp.astype(np.int32)}
-    for grid in (0, 2, 5):
-        got, _ = _run(native, cols, 900, 4, grid_ctas=grid)
-        _assert_same(got, _oracle(cols))
+    want = _oracle(cols)
+    for grid, chunk in ((0, 0), (2, 256), (5, 32), (1, 4096)):
+        got, _ = _run(native, cols, 900, 4, grid_ctas=grid, chunk_len=chunk)
+        _assert_same(got, want)
 
 
 def test_read_longer_than_the_limit_is_an_error(native):
