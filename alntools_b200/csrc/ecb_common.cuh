@@ -127,6 +127,9 @@ __device__ __forceinline__ u32 key_slot_hash(const Key128& k) {
   return fmix32(h);
 }
 
+// Slot hash of the EC table: EC keys are sums of well-mixed words, two of them are enough.
+__device__ __forceinline__ u32 ec_slot_hash(const Key128& k) { return (u32)k.lo ^ (u32)(k.hi >> 32); }
+
 // Counters shared between kernels and the host (one small device struct per context).
 struct EcbCounters {
   u32 n_ec;           // provisional EC ids handed out so far (== ECs in the table)

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) ecb_import_insert_kernel(const ImportPara
     const u32 count = (u32)((u64)m[3] >> 32);
     bool claimed;
     u64 seen;
-    const u32 slot = table_find_or_claim(P.table, P.mask, key, claimed, seen);
+    const u32 slot = table_find_or_claim<true>(P.table, P.mask, key, claimed, seen);
     if (slot == ECB_NONE) {
       atomicOr(&P.ctr->error, ECB_DEVERR_EC_CAPACITY);
       continue;

@@ -68,9 +68,10 @@ struct GroupParams {
 
 // Find `key` or claim an empty slot for it.  Returns the slot, or ECB_NONE when ECB_MAX_PROBE
 // slots were tried.  first_seen = the entry's `first` as loaded (+inf when unknown/new).
+template <bool EC = false>
 __device__ __forceinline__ u32 table_find_or_claim(EcbEntry* table, u32 mask, const Key128& key,
                                                    bool& claimed, u64& first_seen) {
-  u32 slot = key_slot_hash(key) & mask;
+  u32 slot = (EC ? ec_slot_hash(key) : key_slot_hash(key)) & mask;
   claimed = false;
   first_seen = ~0ull;
   for (int p = 0; p < ECB_MAX_PROBE; ++p) {
@@ -154,7 +155,7 @@ __device__ __forceinline__ u32 global_upsert(const GroupParams& P, const Key128&
                                              u32 s, u32 len) {
   bool claimed;
   u64 first_seen;
-  const u32 slot = table_find_or_claim(P.table, P.mask, key, claimed, first_seen);
+  const u32 slot = table_find_or_claim<true>(P.table, P.mask, key, claimed, first_seen);
   if (slot != ECB_NONE) {
     EcbEntry* e = P.table + slot;
     atomicAdd(&e->countm1, count);
@@ -177,20 +178,21 @@ struct GroupSmem {
   u32 c_tag[ECB_CACHE];    // 0 = empty, 1 = being installed, else the ready entry's tag
   u32 c_cnt[ECB_CACHE];    // reads counted in this entry
   u32 c_first[ECB_CACHE];  // smallest offset (in this push) of a read with this key
-  u32 c_rep[ECB_CACHE];    // offset and length of one read with this key (the installer's)
-  u32 c_len[ECB_CACHE];
+  alignas(8) uint2 c_rep[ECB_CACHE];  // offset and length of one read with this key (the installer's)
   // per-warp queues of reads that missed the cache
   alignas(16) uint4 q_key[ECB_GWARPS][ECB_MQ];
-  u32 q_pos[ECB_GWARPS][ECB_MQ];
-  u32 q_len[ECB_GWARPS][ECB_MQ];
+  alignas(8) uint2 q_rep[ECB_GWARPS][ECB_MQ];  // offset, length
 };
+
+#define ECB_RG_SENTINEL ((int)0x80000000)  // stands for read_group beyond the end of the push
 
 __device__ __forceinline__ Key128 key_of(const uint4& k) {
   return Key128{((u64)k.y << 32) | k.x, ((u64)k.w << 32) | k.z};
 }
 __device__ __forceinline__ uint4 key_words(const Mix4& m) {
-  const Key128 k = mix_to_key(m);
-  return make_uint4((u32)k.lo, (u32)(k.lo >> 32), (u32)k.hi, (u32)(k.hi >> 32));
+  uint4 k = make_uint4(m.a, m.b, m.c, m.d);
+  if ((k.x & k.y & k.z & k.w) == 0xFFFFFFFFu) k.x = k.y = 0u;  // all-ones is the empty marker (as mix_to_key)
+  return k;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -206,31 +208,37 @@ __device__ __forceinline__ void insert_miss(const GroupParams& P, const uint4& k
   }
 }
 
+struct LongRead {
+  uint4 key;
+  int len;
+};
+
 // Key and length of a read that starts at w and fills a whole window (>= 32 alignments).
 // Warp-cooperative: walks the read in blocks of 32; duplicates inside a block come from one
 // match, duplicates against the earlier blocks of the read from shuffled compares.
-__device__ __noinline__ int ecb_long_read(const GroupParams& P, int w, uint4* key_out) {
+__device__ __noinline__ LongRead ecb_long_read(const int32_t* __restrict__ rg, const int32_t* __restrict__ tg,
+                                               const int32_t* __restrict__ hp, int n, int w, int n_targets,
+                                               int n_haps, EcbCounters* ctr) {
   const int lane = threadIdx.x & 31;
   const u32 lt_mask = (1u << lane) - 1u;
-  const int n = P.n;
-  const int rg0 = P.rg[w];
+  const int rg0 = rg[w];
   Mix4 sum = mix_zero();
   int len = 0;
   bool bad = false, too_long = false;
   for (int b = 0;; ++b) {
     const int pos = w + 32 * b + lane;
     bool in = pos < n;
-    const int r = in ? P.rg[pos] : 0;
-    const int t = in ? P.tg[pos] : 0, h = in ? P.hp[pos] : 0;
+    const int r = in ? rg[pos] : 0;
+    const int t = in ? tg[pos] : 0, h = in ? hp[pos] : 0;
     in = in && r == rg0;
     const u32 m = __ballot_sync(ECB_FULL, in);  // the read is contiguous: m is a run of low bits
     const u32 code = in ? ecb_code(t, h) : (0x80000000u | (u32)lane);
-    bad |= in && ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps);
+    bad |= in && ((u32)t >= (u32)n_targets || (u32)h >= (u32)n_haps);
     bool dup = (__match_any_sync(ECB_FULL, code) & lt_mask) != 0u;
     if (!too_long) {
       for (int e = 0; e < b; ++e) {
         const int pe = w + 32 * e + lane;
-        const u32 ce = ecb_code(P.tg[pe], P.hp[pe]);
+        const u32 ce = ecb_code(tg[pe], hp[pe]);
 #pragma unroll 8
         for (int j = 0; j < 32; ++j) dup |= __shfl_sync(ECB_FULL, ce, j) == code;
       }
@@ -240,14 +248,16 @@ __device__ __noinline__ int ecb_long_read(const GroupParams& P, int w, uint4* ke
     if (m != ECB_FULL) break;
     if (len > ECB_MAX_READ_ALIGNMENTS) too_long = true;
   }
-  if (bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
-  if (too_long && lane == 0) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
+  if (bad) atomicOr(&ctr->error, ECB_DEVERR_VALUE_RANGE);
+  if (too_long && lane == 0) atomicOr(&ctr->error, ECB_DEVERR_READ_TOO_LONG);
   sum.a = __reduce_add_sync(ECB_FULL, sum.a);
   sum.b = __reduce_add_sync(ECB_FULL, sum.b);
   sum.c = __reduce_add_sync(ECB_FULL, sum.c);
   sum.d = __reduce_add_sync(ECB_FULL, sum.d);
-  *key_out = key_words(sum);
-  return len;
+  LongRead r;
+  r.key = key_words(sum);
+  r.len = len;
+  return r;
 }
 
 template <bool WITH_CELLS>
@@ -257,8 +267,16 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 lt_mask = (1u << lane) - 1u;
+  const u32 le_mask = (2u << lane) - 1u;
   const int n = P.n;
   const bool use_cache = !WITH_CELLS && P.use_cache;
+  const int32_t* __restrict__ const c_rg = P.rg;
+  const int32_t* __restrict__ const c_tg = P.tg;
+  const int32_t* __restrict__ const c_hp = P.hp;
+  // lanes 0..2 pull one column each into L2 ahead of the window
+  const int32_t* const pf_col = (lane == 0 ? c_rg : (lane == 1 ? c_tg : c_hp)) + ECB_PF_DIST;
+  const int pf_end = lane < 3 ? n - ECB_PF_DIST : 0;
+  const int drop_pos = P.drop_last ? n - 1 : -1;  // the read that ends here is not counted
 
   if (use_cache) {
     for (int i = tid; i < ECB_CACHE; i += ECB_GTHREADS) {
@@ -270,10 +288,9 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   __syncthreads();
 
   uint4* const qk = S.q_key[warp];
-  u32* const qp = S.q_pos[warp];
-  u32* const ql = S.q_len[warp];
+  uint2* const qr = S.q_rep[warp];
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
-  u32 reads_counted = 0;  // warp-uniform
+  u32 reads_counted = 0;  // per lane
 
   for (;;) {
     // ---- next chunk of the stream (dynamic: whichever warp is free takes it) -------------------------
@@ -291,7 +308,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       w = -1;
       for (int b = cb; b < ce; b += 32) {
         const int pos = b + lane;
-        const bool hd = pos < ce && P.rg[pos] != P.rg[pos - 1];
+        const bool hd = pos < ce && c_rg[pos] != c_rg[pos - 1];
         const u32 m = __ballot_sync(ECB_FULL, hd);
         if (m) {
           w = b + __ffs(m) - 1;
@@ -301,35 +318,34 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       if (w < 0) continue;  // one long read covers the whole chunk
     }
 
-    int rgv = 0, tgv = 0, hpv = 0;
+    int rgv = ECB_RG_SENTINEL, tgv = 0, hpv = 0;
     if (w + lane < n) {
-      rgv = P.rg[w + lane];
-      tgv = P.tg[w + lane];
-      hpv = P.hp[w + lane];
+      rgv = c_rg[w + lane];
+      tgv = c_tg[w + lane];
+      hpv = c_hp[w + lane];
     }
 
     // ---- windows of 32 alignments, each starting at a read start -------------------------------------
-    while (w < ce) {
-      const int pos = w + lane;
+    do {
+      // read starts: positions beyond the end hold the sentinel, so the first of them closes the last read
       const int prev = __shfl_up_sync(ECB_FULL, rgv, 1);
-      const bool hd = lane == 0 || pos == n || (pos < n && rgv != prev);  // n = virtual closing head
-      const u32 hb = __ballot_sync(ECB_FULL, hd);
+      const u32 hb = __ballot_sync(ECB_FULL, rgv != prev) | 1u;
 
-      bool ins;     // this lane holds the last alignment of a complete, owned read
-      uint4 key;    // ... its key
-      u32 s, len;   // ... its first alignment and its number of alignments
+      bool ins;    // this lane holds the last alignment of a complete, owned read
+      uint4 key;   // ... its key
+      u32 s, len;  // ... its first alignment and its number of alignments
       int wnext;
       if (hb == 1u) {
         // one read fills the window
-        const int l = ecb_long_read(P, w, &key);
-        ins = lane == 0 && !(P.drop_last && w + l == n);
+        const LongRead lr = ecb_long_read(c_rg, c_tg, c_hp, n, w, P.n_targets, P.n_haps, P.ctr);
+        key = lr.key;
         s = (u32)w;
-        len = (u32)l;
-        wnext = w + l;
+        len = (u32)lr.len;
+        wnext = w + lr.len;
+        ins = lane == 0 && wnext - 1 != drop_pos;
       } else {
-        const int last_head = 31 - __clz(hb);  // >= 1; lanes below it form complete reads
-        wnext = w + last_head;
-        const int st = 31 - __clz(hb & ((2u << lane) - 1u));  // lane of this alignment's read start
+        const int last_head = 31 - __clz(hb);          // >= 1; lanes below it form complete reads
+        const int st = 31 - __clz(hb & le_mask);       // lane of this alignment's read start
         const bool active = lane < last_head;
         const u32 code = ecb_code(tgv, hpv);
         if (active && ((u32)tgv >= (u32)P.n_targets || (u32)hpv >= (u32)P.n_haps))
@@ -341,11 +357,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         if (!contrib) X = mix_zero();
         // segmented inclusive scan over the lanes of each read, with only as many doubling steps as
         // the longest complete read of the window needs (warp-uniform, from the head ballot)
-        const u32 x1 = ~hb & ((1u << last_head) - 1u);
-        const u32 x2 = x1 & (x1 >> 1);
-        const u32 x4 = x2 & (x2 >> 2);
-        const u32 x8 = x4 & (x4 >> 4);
-        const u32 x16 = x8 & (x8 >> 8);
+        u32 run = ~hb & ((1u << last_head) - 1u);  // lanes that continue a read
 #define ECB_SEG_STEP(D)                                \
   {                                                    \
     const u32 va = __shfl_up_sync(ECB_FULL, X.a, D);   \
@@ -356,38 +368,48 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       X.a += va; X.b += vb; X.c += vc; X.d += vd;      \
     }                                                  \
   }
-        if (x1) ECB_SEG_STEP(1)
-        if (x2) ECB_SEG_STEP(2)
-        if (x4) ECB_SEG_STEP(4)
-        if (x8) ECB_SEG_STEP(8)
-        if (x16) ECB_SEG_STEP(16)
+        if (run) {
+          ECB_SEG_STEP(1)
+          run &= run >> 1;
+          if (run) {
+            ECB_SEG_STEP(2)
+            run &= run >> 2;
+            if (run) {
+              ECB_SEG_STEP(4)
+              run &= run >> 4;
+              if (run) {
+                ECB_SEG_STEP(8)
+                run &= run >> 8;
+                if (run) ECB_SEG_STEP(16)
+              }
+            }
+          }
+        }
 #undef ECB_SEG_STEP
-        const bool is_end = active && ((hb >> 1) >> lane) & 1u;  // lane + 1 is a head
+        wnext = w + last_head;
         s = (u32)(w + st);
         len = (u32)(lane - st + 1);
-        ins = is_end && (int)s < ce && !(P.drop_last && pos == n - 1);
+        // lane + 1 is a head, the read is complete, starts in this chunk and is not the dropped one
+        ins = (((hb >> 1) >> lane) & 1u) && active && (int)s < ce && w + lane != drop_pos;
         key = key_words(X);
       }
 
       // ---- request the next window's columns now; they arrive while this window is inserted ---------
-      int nrg = 0, ntg = 0, nhp = 0;
-      if (wnext < ce) {
+      {
         const int np = wnext + lane;
+        rgv = ECB_RG_SENTINEL;
         if (np < n) {
-          nrg = P.rg[np];
-          ntg = P.tg[np];
-          nhp = P.hp[np];
+          rgv = c_rg[np];
+          tgv = c_tg[np];
+          hpv = c_hp[np];
         }
-        if (lane < 3) {  // pull the lines further ahead into L2 (one line per column per window)
-          const int pp = wnext + ECB_PF_DIST;
-          const int32_t* col = lane == 0 ? P.rg : (lane == 1 ? P.tg : P.hp);
-          if (pp < n) prefetch_l2(col + pp);
-        }
+        if (wnext < pf_end) prefetch_l2(pf_col + wnext);
       }
+      w = wnext;
 
       // ---- closed reads: hot-EC cache first --------------------------------------------------------
-      reads_counted += __popc(__ballot_sync(ECB_FULL, ins));
       bool miss = ins;
+      if (ins) ++reads_counted;
       if (use_cache && ins) {
         const u32 cidx = (key.y >> 7) & (ECB_CACHE - 1);
         const u32 tag = key.w | 2u;
@@ -396,8 +418,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
           t = atomicCAS(&S.c_tag[cidx], 0u, 1u);
           if (t == 0u) {  // this lane installs the entry; its read becomes the key's representative
             S.c_key[cidx] = key;
-            S.c_rep[cidx] = s;
-            S.c_len[cidx] = len;
+            S.c_rep[cidx] = make_uint2(s, len);
             __threadfence_block();
             *reinterpret_cast<volatile u32*>(&S.c_tag[cidx]) = tag;
             t = tag;
@@ -418,41 +439,40 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         if (miss) {
           const u32 q = qn + __popc(mm & lt_mask);
           qk[q] = key;
-          qp[q] = s;
-          ql[q] = len;
-          prefetch_l2(P.table + (key_slot_hash(key_of(key)) & P.mask));
+          qr[q] = make_uint2(s, len);
+          prefetch_l2(P.table + ((key.x ^ key.w) & P.mask));
         }
         qn += __popc(mm);
         __syncwarp();
         if (qn >= 32u) {
           qn -= 32u;
-          insert_miss<WITH_CELLS>(P, qk[qn + lane], qp[qn + lane], ql[qn + lane]);
+          const uint2 r = qr[qn + lane];
+          insert_miss<WITH_CELLS>(P, qk[qn + lane], r.x, r.y);
           __syncwarp();
         }
       }
-
-      w = wnext;
-      rgv = nrg;
-      tgv = ntg;
-      hpv = nhp;
-    }
+    } while (w < ce);
   }
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
-  if ((u32)lane < qn) insert_miss<WITH_CELLS>(P, qk[lane], qp[lane], ql[lane]);
+  if ((u32)lane < qn) {
+    const uint2 r = qr[lane];
+    insert_miss<WITH_CELLS>(P, qk[lane], r.x, r.y);
+  }
+  reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
   __syncthreads();
   if (use_cache) {
     for (int i = tid; i < ECB_CACHE; i += ECB_GTHREADS) {
       const u32 cnt = S.c_cnt[i];
       if (cnt) {
-        const uint4 k = S.c_key[i];
-        const Key128 key = key_of(k);
-        const u32 first = S.c_first[i], rep = S.c_rep[i], rlen = S.c_len[i];
-        const u32 slot = global_upsert(P, key, cnt, first, rep, rlen);
+        const Key128 key = key_of(S.c_key[i]);
+        const u32 first = S.c_first[i];
+        const uint2 rep = S.c_rep[i];
+        const u32 slot = global_upsert(P, key, cnt, first, rep.x, rep.y);
         if (slot == ECB_NONE) {  // table too full: park the entry, the host grows the table and replays it
           const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
-          P.spill[si] = EcbSpill{key.lo, key.hi, cnt, first, rep, rlen};
+          P.spill[si] = EcbSpill{key.lo, key.hi, cnt, first, rep.x, rep.y};
         }
       }
     }
@@ -529,7 +549,7 @@ __global__ void __launch_bounds__(256) ecb_rehash_kernel(const EcbEntry* __restr
     load_entry_cg(old_table + i, k, first, cm1, aux);
     if (remap) remap[i] = ECB_NONE;
     if (key_empty(k)) continue;
-    u32 slot = key_slot_hash(k) & new_mask;
+    u32 slot = ec_slot_hash(k) & new_mask;
     for (;;) {
       Key128 old = atomic_cas128(new_table + slot, Key128{~0ull, ~0ull}, k);
       if (key_empty(old)) break;
