@@ -32,7 +32,7 @@
 #define ECB_GWARPS 32                  // warps per CTA of the grouping kernel
 #define ECB_GTHREADS (32 * ECB_GWARPS)
 #define ECB_CACHE 4096                 // per-CTA hot-EC cache entries
-#define ECB_MQ 64                      // per-warp miss-queue ring (entries)
+#define ECB_MQ 96                      // per-warp miss queue (entries); 64 are inserted at a time, two per lane
 #define ECB_PF_DIST 256                // L2 prefetch distance of the column stream (alignments)
 
 // A hot-cache entry that could not be flushed because the table was too full (replayed after growth).
@@ -66,15 +66,12 @@ struct GroupParams {
   u32 push_id;
 };
 
-// Find `key` or claim an empty slot for it.  Returns the slot, or ECB_NONE when ECB_MAX_PROBE
-// slots were tried.  first_seen = the entry's `first` as loaded (+inf when unknown/new).
-template <bool EC = false>
-__device__ __forceinline__ u32 table_find_or_claim(EcbEntry* table, u32 mask, const Key128& key,
-                                                   bool& claimed, u64& first_seen) {
-  u32 slot = (EC ? ec_slot_hash(key) : key_slot_hash(key)) & mask;
-  claimed = false;
-  first_seen = ~0ull;
-  for (int p = 0; p < ECB_MAX_PROBE; ++p) {
+// Probe for `key` from `slot` on (linear probing, at most max_probe slots): find it or claim the
+// first empty slot.  Returns the slot or ECB_NONE; first_seen = the entry's `first` as loaded (+inf
+// when unknown/new).
+__device__ __forceinline__ u32 table_probe_from(EcbEntry* table, u32 mask, const Key128& key, u32 slot,
+                                                int max_probe, bool& claimed, u64& first_seen) {
+  for (int p = 0; p < max_probe; ++p) {
     EcbEntry* e = table + slot;
     Key128 k;
     u64 first;
@@ -95,6 +92,16 @@ __device__ __forceinline__ u32 table_find_or_claim(EcbEntry* table, u32 mask, co
     slot = (slot + 1) & mask;
   }
   return ECB_NONE;
+}
+
+// Find `key` or claim an empty slot for it.  EC selects the EC table's slot hash.
+template <bool EC = false>
+__device__ __forceinline__ u32 table_find_or_claim(EcbEntry* table, u32 mask, const Key128& key,
+                                                   bool& claimed, u64& first_seen) {
+  claimed = false;
+  first_seen = ~0ull;
+  const u32 slot = (EC ? ec_slot_hash(key) : key_slot_hash(key)) & mask;
+  return table_probe_from(table, mask, key, slot, ECB_MAX_PROBE, claimed, first_seen);
 }
 
 // Lookup only (no claim); ECB_NONE if absent.
@@ -172,13 +179,83 @@ __device__ __forceinline__ u32 global_upsert(const GroupParams& P, const Key128&
   return slot;
 }
 
+// Two reads per lane go into the HBM table together.  The probe sequences of a warp's lanes are
+// chains of dependent round trips to L2/HBM and every lane waits for the slowest, so the first
+// load and the first compare-and-swap of both reads are issued before either result is used: the
+// warp pays the chain once for 64 reads.  Returns the slots (ECB_NONE: absent read or table full).
+__device__ __forceinline__ void global_upsert2(const GroupParams& P, const Key128& keyA, u32 sA, u32 lenA, bool hasA,
+                                               const Key128& keyB, u32 sB, u32 lenB, bool hasB, u32& slotA,
+                                               u32& slotB) {
+  const Key128 EMPTY{~0ull, ~0ull};
+  const u32 hA = ec_slot_hash(keyA) & P.mask, hB = ec_slot_hash(keyB) & P.mask;
+  Key128 kA = EMPTY, kB = EMPTY;
+  u64 fA = ~0ull, fB = ~0ull;
+  u32 cm1, aux;
+  if (hasA) load_entry_cg(P.table + hA, kA, fA, cm1, aux);
+  if (hasB) load_entry_cg(P.table + hB, kB, fB, cm1, aux);
+  const bool eqA = hasA && key_eq(kA, keyA), eqB = hasB && key_eq(kB, keyB);
+  const bool casA = hasA && !eqA && key_empty(kA), casB = hasB && !eqB && key_empty(kB);
+  if (casA) kA = atomic_cas128(P.table + hA, EMPTY, keyA);
+  if (casB) kB = atomic_cas128(P.table + hB, EMPTY, keyB);
+  bool clA = casA && key_empty(kA), clB = casB && key_empty(kB);
+  if (casA) fA = ~0ull;  // the loaded `first` belongs to the empty state
+  if (casB) fB = ~0ull;
+  slotA = (eqA || clA || (casA && key_eq(kA, keyA))) ? hA : ECB_NONE;
+  slotB = (eqB || clB || (casB && key_eq(kB, keyB))) ? hB : ECB_NONE;
+  if (hasA && slotA == ECB_NONE) {  // the home slot holds another key: walk on
+    fA = ~0ull;
+    slotA = table_probe_from(P.table, P.mask, keyA, (hA + 1) & P.mask, ECB_MAX_PROBE - 1, clA, fA);
+  }
+  if (hasB && slotB == ECB_NONE) {
+    fB = ~0ull;
+    slotB = table_probe_from(P.table, P.mask, keyB, (hB + 1) & P.mask, ECB_MAX_PROBE - 1, clB, fB);
+  }
+  if (slotA != ECB_NONE) {
+    EcbEntry* e = P.table + slotA;
+    atomicAdd(&e->countm1, 1u);
+    const u64 pos = P.order_base + sA;
+    if (pos < fA) atomicMin(&e->first, pos);
+  }
+  if (slotB != ECB_NONE) {
+    EcbEntry* e = P.table + slotB;
+    atomicAdd(&e->countm1, 1u);
+    const u64 pos = P.order_base + sB;
+    if (pos < fB) atomicMin(&e->first, pos);
+  }
+  // provisional ids of the new ECs: one atomic for both halves
+  const u32 act = __activemask();
+  const u32 mA = __ballot_sync(act, clA), mB = __ballot_sync(act, clB);
+  if (mA | mB) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(act) - 1;
+    u32 base = 0;
+    if (lane == leader) base = atomicAdd(&P.ctr->n_ec, (u32)(__popc(mA) + __popc(mB)));
+    base = __shfl_sync(act, base, leader);
+    const u32 lt = (1u << lane) - 1u;
+    if (clA) {
+      const u32 id = base + (u32)__popc(mA & lt);
+      P.table[slotA].aux = id;
+      P.ec_slot[id] = slotA;
+      P.ec_rep[id] = sA;
+      P.ec_len[id] = lenA;
+    }
+    if (clB) {
+      const u32 id = base + (u32)__popc(mA) + (u32)__popc(mB & lt);
+      P.table[slotB].aux = id;
+      P.ec_slot[id] = slotB;
+      P.ec_rep[id] = sB;
+      P.ec_len[id] = lenB;
+    }
+  }
+}
+
 struct GroupSmem {
   // hot-EC cache of this CTA (direct mapped, first come first installed, flushed at the end)
-  alignas(16) uint4 c_key[ECB_CACHE];
-  u32 c_tag[ECB_CACHE];    // 0 = empty, 1 = being installed, else the ready entry's tag
-  u32 c_cnt[ECB_CACHE];    // reads counted in this entry
-  u32 c_first[ECB_CACHE];  // smallest offset (in this push) of a read with this key
-  alignas(8) uint2 c_rep[ECB_CACHE];  // offset and length of one read with this key (the installer's)
+  alignas(16) uint4 c_key[ECB_CACHE];  // all ones = empty; written once, by the lane that holds c_lock
+  u32 c_lock[ECB_CACHE];               // 0 = free, 1 = an installer owns the entry
+  u32 c_cnt[ECB_CACHE];                // reads counted in this entry
+  u32 c_first[ECB_CACHE];              // smallest offset (in this push) of a read with this key
+  alignas(8) uint2 c_rep[ECB_CACHE];   // offset and length of one read with this key (the installer's)
   // per-warp queues of reads that missed the cache
   alignas(16) uint4 q_key[ECB_GWARPS][ECB_MQ];
   alignas(8) uint2 q_rep[ECB_GWARPS][ECB_MQ];  // offset, length
@@ -194,17 +271,58 @@ __device__ __forceinline__ uint4 key_words(const Mix4& m) {
   if ((k.x & k.y & k.z & k.w) == 0xFFFFFFFFu) k.x = k.y = 0u;  // all-ones is the empty marker (as mix_to_key)
   return k;
 }
+// Column loads: read once (twice by overlapping windows, which L1 absorbs), so they are marked
+// evict-first in L2 and leave the cache to the EC table.
+#ifndef ECB_EVICT_FIRST
+#define ECB_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ u64 make_evict_first_policy() {
+  u64 pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int ld_col(const int32_t* p, u64 pol) {
+#if ECB_EVICT_FIRST
+  int v;
+  asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// One read that missed the cache goes into the HBM table.
+// Reads that missed the cache go into the HBM table, two per lane (entries qa and qb of the warp's queue).
 template <bool WITH_CELLS>
-__device__ __forceinline__ void insert_miss(const GroupParams& P, const uint4& kq, u32 s, u32 len) {
-  const u32 slot = global_upsert(P, key_of(kq), 1u, s, s, len);
-  if (slot == ECB_NONE) {  // table too full: the host grows it and replays the flagged reads
-    atomicOr(&P.overflow_bits[s >> 5], 1u << (s & 31));
-    atomicAdd(&P.ctr->n_overflow, 1u);
-  } else if (WITH_CELLS) {
-    triple_upsert(P, slot, (u32)P.cell[s], P.order_base + s);
+__device__ __forceinline__ void insert_misses(const GroupParams& P, const uint4* qk, const uint2* qr, u32 qa, bool hasA,
+                                              u32 qb, bool hasB) {
+  uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
+  uint2 rA = make_uint2(0u, 0u), rB = rA;
+  if (hasA) {
+    kA = qk[qa];
+    rA = qr[qa];
+  }
+  if (hasB) {
+    kB = qk[qb];
+    rB = qr[qb];
+  }
+  u32 slotA, slotB;
+  global_upsert2(P, key_of(kA), rA.x, rA.y, hasA, key_of(kB), rB.x, rB.y, hasB, slotA, slotB);
+  if (hasA) {
+    if (slotA == ECB_NONE) {  // table too full: the host grows it and replays the flagged reads
+      atomicOr(&P.overflow_bits[rA.x >> 5], 1u << (rA.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    } else if (WITH_CELLS) {
+      triple_upsert(P, slotA, (u32)P.cell[rA.x], P.order_base + rA.x);
+    }
+  }
+  if (hasB) {
+    if (slotB == ECB_NONE) {
+      atomicOr(&P.overflow_bits[rB.x >> 5], 1u << (rB.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    } else if (WITH_CELLS) {
+      triple_upsert(P, slotB, (u32)P.cell[rB.x], P.order_base + rB.x);
+    }
   }
 }
 
@@ -277,10 +395,12 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   const int32_t* const pf_col = (lane == 0 ? c_rg : (lane == 1 ? c_tg : c_hp)) + ECB_PF_DIST;
   const int pf_end = lane < 3 ? n - ECB_PF_DIST : 0;
   const int drop_pos = P.drop_last ? n - 1 : -1;  // the read that ends here is not counted
+  const u64 col_policy = make_evict_first_policy();
 
   if (use_cache) {
     for (int i = tid; i < ECB_CACHE; i += ECB_GTHREADS) {
-      S.c_tag[i] = 0u;
+      S.c_key[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      S.c_lock[i] = 0u;
       S.c_cnt[i] = 0u;
       S.c_first[i] = 0xFFFFFFFFu;
     }
@@ -320,9 +440,9 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
 
     int rgv = ECB_RG_SENTINEL, tgv = 0, hpv = 0;
     if (w + lane < n) {
-      rgv = c_rg[w + lane];
-      tgv = c_tg[w + lane];
-      hpv = c_hp[w + lane];
+      rgv = ld_col(c_rg + w + lane, col_policy);
+      tgv = ld_col(c_tg + w + lane, col_policy);
+      hpv = ld_col(c_hp + w + lane, col_policy);
     }
 
     // ---- windows of 32 alignments, each starting at a read start -------------------------------------
@@ -399,9 +519,9 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         const int np = wnext + lane;
         rgv = ECB_RG_SENTINEL;
         if (np < n) {
-          rgv = c_rg[np];
-          tgv = c_tg[np];
-          hpv = c_hp[np];
+          rgv = ld_col(c_rg + np, col_policy);
+          tgv = ld_col(c_tg + np, col_policy);
+          hpv = ld_col(c_hp + np, col_policy);
         }
         if (wnext < pf_end) prefetch_l2(pf_col + wnext);
       }
@@ -412,42 +532,38 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       if (ins) ++reads_counted;
       if (use_cache && ins) {
         const u32 cidx = (key.y >> 7) & (ECB_CACHE - 1);
-        const u32 tag = key.w | 2u;
-        u32 t = *reinterpret_cast<volatile u32*>(&S.c_tag[cidx]);
-        if (t == 0u) {
-          t = atomicCAS(&S.c_tag[cidx], 0u, 1u);
-          if (t == 0u) {  // this lane installs the entry; its read becomes the key's representative
-            S.c_key[cidx] = key;
+        const uint4 ck = S.c_key[cidx];
+        const u32 cf = *reinterpret_cast<volatile u32*>(&S.c_first[cidx]);
+        bool hit = ck.x == key.x && ck.y == key.y && ck.z == key.z && ck.w == key.w;
+        if (!hit && (ck.x & ck.y & ck.z & ck.w) == 0xFFFFFFFFu) {
+          // empty entry: one lane wins the lock, its read becomes the key's representative, and the
+          // single 128-bit store of the key publishes the entry
+          if (atomicCAS(&S.c_lock[cidx], 0u, 1u) == 0u) {
             S.c_rep[cidx] = make_uint2(s, len);
-            __threadfence_block();
-            *reinterpret_cast<volatile u32*>(&S.c_tag[cidx]) = tag;
-            t = tag;
+            S.c_key[cidx] = key;
+            hit = true;
           }
         }
-        if (t == tag) {
-          const uint4 ck = S.c_key[cidx];
-          if (ck.x == key.x && ck.y == key.y && ck.z == key.z && ck.w == key.w) {
-            atomicAdd(&S.c_cnt[cidx], 1u);
-            if (s < *reinterpret_cast<volatile u32*>(&S.c_first[cidx])) atomicMin(&S.c_first[cidx], s);
-            miss = false;
-          }
+        if (hit) {
+          atomicAdd(&S.c_cnt[cidx], 1u);
+          if (s < cf) atomicMin(&S.c_first[cidx], s);
+          miss = false;
         }
       }
-      // ---- misses: park in the warp's queue, insert into the HBM table 32 at a time -----------------
+      // ---- misses: park in the warp's queue (pulling their home slots into L2), insert 64 at a time --
       const u32 mm = __ballot_sync(ECB_FULL, miss);
       if (mm) {
         if (miss) {
           const u32 q = qn + __popc(mm & lt_mask);
           qk[q] = key;
           qr[q] = make_uint2(s, len);
-          prefetch_l2(P.table + ((key.x ^ key.w) & P.mask));
+          prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
         }
         qn += __popc(mm);
         __syncwarp();
-        if (qn >= 32u) {
-          qn -= 32u;
-          const uint2 r = qr[qn + lane];
-          insert_miss<WITH_CELLS>(P, qk[qn + lane], r.x, r.y);
+        if (qn >= 64u) {
+          qn -= 64u;
+          insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           __syncwarp();
         }
       }
@@ -455,10 +571,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
-  if ((u32)lane < qn) {
-    const uint2 r = qr[lane];
-    insert_miss<WITH_CELLS>(P, qk[lane], r.x, r.y);
-  }
+  if (qn) insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
   __syncthreads();
