@@ -46,7 +46,7 @@ struct ecb_ctx {
   bool group_attr_set = false;
   DevBuf arena;                              // uint2 pairs
   u64 arena_used = 0;
-  DevBuf long_list;
+  DevBuf long_list, mid_list, count_of;
   // triple table (cells)
   DevBuf ttable;
   u32 ttable_slots = 0;
@@ -199,6 +199,7 @@ int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
   CKR(ensure(c, c->row_len, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->row_off, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->long_list, (size_t)slots * 4, false));
+  CKR(ensure(c, c->mid_list, (size_t)slots * 4, false));
   return ECB_OK;
 }
 
@@ -318,6 +319,7 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   H.row_len = (u32*)c->row_len.p;
   H.row_off = (const u32*)c->row_off.p;
   H.long_list = (u32*)c->long_list.p;
+  H.mid_list = (u32*)c->mid_list.p;
   H.ctr = c->d_ctr;
   const u32 n_new = e1 - e0;
   u64 total = 0;
@@ -332,7 +334,8 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   CKR(sync_counters(c));
   CKR(check_device_error(c));
   if (c->h_ctr->scratch[1]) {
-    ecb_harvest_warp_kernel<<<grid_for((u64)n_new * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(H);
+    const u32 n_mid = c->h_ctr->scratch[1];
+    ecb_harvest_warp_kernel<<<grid_for((u64)n_mid * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(H, n_mid);
     LAUNCH_CHECK("harvest_warp");
     CK(cudaMemsetAsync(&c->d_ctr->scratch[1], 0, sizeof(u32), c->stream));
   }
@@ -717,7 +720,10 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   F.word_rank = (const u32*)c->word_rank.p;
   F.first_rel = (u64*)c->first_rel.p;
   F.ecid_of = (u32*)c->ecid_of.p;
-  F.long_rows_flag = &c->d_ctr->scratch[2];
+  F.wide_count = &c->d_ctr->scratch[2];
+  F.wide_list = (u32*)c->long_list.p;
+  CKR(ensure(c, c->count_of, (size_t)n_prov * 4));
+  F.count_of = (u32*)c->count_of.p;
   CK(cudaMemsetAsync(&c->d_ctr->scratch[2], 0, sizeof(u32), c->stream));
 
   CellResult cr{};
@@ -762,7 +768,9 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   LAUNCH_CHECK("fin_rows");
   CKR(sync_counters(c));
   if (c->h_ctr->scratch[2]) {
-    ecb_fin_rows_long_kernel<<<grid_for((u64)n_prov * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+    const u32 n_wide = c->h_ctr->scratch[2];
+    ecb_fin_rows_long_kernel<<<grid_for((u64)n_wide * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+        F, (const u32*)c->long_list.p, n_wide);
     LAUNCH_CHECK("fin_rows_long");
   }
 
@@ -983,6 +991,7 @@ static FinalizeParams global_params(ecb_ctx* c) {
   F.min_base = c->g_min_base;
   F.first_rel = (u64*)c->first_rel.p;
   F.ecid_of = (u32*)c->ecid_of.p;
+  F.count_of = (u32*)c->count_of.p;
   return F;
 }
 
@@ -993,6 +1002,7 @@ int ecb_global_mark(ecb_ctx* c, int64_t min_base, uint32_t* bitmap_device, int64
   if (c->n_ec == 0) return ECB_OK;
   CKR(ensure(c, c->first_rel, (size_t)c->n_ec * 8));
   CKR(ensure(c, c->ecid_of, (size_t)c->n_ec * 4));
+  CKR(ensure(c, c->count_of, (size_t)c->n_ec * 4));
   FinalizeParams F = global_params(c);
   F.bitmap = bitmap_device;
   ecb_fin_mark_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
@@ -1051,7 +1061,7 @@ int ecb_global_rows(ecb_ctx* c, const int32_t* indptr_device, int32_t* indices_d
   F.a_data = data_device;
   ecb_fin_rows_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rows");
-  ecb_fin_rows_long_kernel<<<grid_for((u64)c->n_ec * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
+  ecb_fin_rows_long_kernel<<<grid_for((u64)c->n_ec * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F, nullptr, 0u);
   LAUNCH_CHECK("fin_rows_long");
   CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;
@@ -1061,7 +1071,7 @@ int ecb_destroy(ecb_ctx* c) {
   if (!c) return ECB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list,
+  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->count_of,
                     &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,

@@ -26,21 +26,39 @@ struct FinalizeParams {
   int32_t* a_data;
   int32_t* n_indices;   // single-sample N matrix
   int32_t* n_data;
-  u32* long_rows_flag;  // set when some row has more than 8 entries
+  u32* wide_count;      // number of rows with more than 8 entries ...
+  u32* wide_list;       // ... and their provisional ids
+  u32* count_of;        // [n_ec] reads per EC (copied out of the table by the mark kernel)
 };
 
 __global__ void __launch_bounds__(256) ecb_fin_mark_kernel(const FinalizeParams P) {
   for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
-    const u64 rel = P.table[P.ec_slot[e]].first - P.min_base;
+    const EcbEntry* en = P.table + P.ec_slot[e];
+    const u64 rel = en->first - P.min_base;
     P.first_rel[e] = rel;
+    if (P.count_of) P.count_of[e] = en->countm1 + 1u;
     if (P.ec_keep == nullptr || P.ec_keep[e]) atomicOr(&P.bitmap[rel >> 5], 1u << (rel & 31));
   }
+}
+
+__device__ __forceinline__ void fin_warp_append(u32* list, u32* counter, bool take, u32 item) {
+  const u32 act = __activemask();
+  const u32 m = __ballot_sync(act, take);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
+  base = __shfl_sync(act, base, leader);
+  if (take) list[base + (u32)__popc(m & ((1u << lane) - 1u))] = item;
 }
 
 template <bool SINGLE_SAMPLE>
 __global__ void __launch_bounds__(256) ecb_fin_rank_kernel(const FinalizeParams P) {
   for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
-    if (P.ec_keep != nullptr && !P.ec_keep[e]) {
+    const bool kept = P.ec_keep == nullptr || P.ec_keep[e];
+    if (P.wide_list) fin_warp_append(P.wide_list, P.wide_count, kept && P.row_len[e] > 8, e);
+    if (!kept) {
       P.ecid_of[e] = ECB_NONE;
       continue;
     }
@@ -50,10 +68,9 @@ __global__ void __launch_bounds__(256) ecb_fin_rank_kernel(const FinalizeParams 
     P.ecid_of[e] = id;
     const u32 len = P.row_len[e];
     P.a_indptr[id] = (int32_t)len;
-    if (len > 8 && P.long_rows_flag && *P.long_rows_flag == 0u) *P.long_rows_flag = 1u;
     if (SINGLE_SAMPLE) {
       P.n_indices[id] = (int32_t)id;
-      P.n_data[id] = (int32_t)(P.table[P.ec_slot[e]].countm1 + 1u);
+      P.n_data[id] = (int32_t)P.count_of[e];
     }
   }
 }
@@ -76,11 +93,15 @@ __global__ void __launch_bounds__(256) ecb_fin_rows_kernel(const FinalizeParams 
   }
 }
 
-__global__ void __launch_bounds__(256) ecb_fin_rows_long_kernel(const FinalizeParams P) {
+// Rows with more than 8 entries: one warp per row.  With a list (n_wide entries of P.wide_list) only
+// those rows are visited; without one (list == NULL) every EC is looked at.
+__global__ void __launch_bounds__(256) ecb_fin_rows_long_kernel(const FinalizeParams P, const u32* list, u32 n_wide) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 e = warp_global; e < P.n_ec; e += n_warps) {
+  const u32 n_items = list ? n_wide : P.n_ec;
+  for (u32 i = warp_global; i < n_items; i += n_warps) {
+    const u32 e = list ? list[i] : i;
     const u32 len = P.row_len[e];
     if (len <= 8) continue;
     const u32 id = P.ecid_of[e];

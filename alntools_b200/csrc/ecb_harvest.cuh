@@ -26,6 +26,7 @@ struct HarvestParams {
   const u32* row_off;  // [capacity] absolute offsets inside the arena
   uint2* arena;      // (target, mask) pairs
   u32* long_list;    // provisional ids whose read has more than 32 alignments
+  u32* mid_list;     // provisional ids whose read has 9..32 alignments
   EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, n_long = #ECs with k > 32
 };
 
@@ -39,14 +40,25 @@ struct HarvestParams {
     b = hi_;                       \
   }
 
+// Append `item` to list[] for the lanes where `take` holds: one atomic per warp.
+__device__ __forceinline__ void warp_append(u32* list, u32* counter, bool take, u32 item) {
+  const u32 act = __activemask();
+  const u32 m = __ballot_sync(act, take);
+  if (!m) return;
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  u32 base = 0;
+  if (lane == leader) base = atomicAdd(counter, (u32)__popc(m));
+  base = __shfl_sync(act, base, leader);
+  if (take) list[base + (u32)__popc(m & ((1u << lane) - 1u))] = item;
+}
+
 __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestParams P) {
-  u32 n_mid = 0;
   for (u32 e = P.e0 + blockIdx.x * blockDim.x + threadIdx.x; e < P.e1; e += gridDim.x * blockDim.x) {
     const u32 k = P.ec_len[e];
+    warp_append(P.mid_list, &P.ctr->scratch[1], k > 8 && k <= 32, e);
     if (k > 8) {
-      if (k <= 32) {
-        ++n_mid;
-      } else {
+      if (k > 32) {
         if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
         P.long_list[atomicAdd(&P.ctr->n_long, 1u)] = e;
       }
@@ -81,18 +93,17 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
     if (cnt) out[cnt - 1] = make_uint2(prev_t, mask);
     P.row_len[e] = cnt;
   }
-  n_mid = __reduce_add_sync(ECB_FULL, n_mid);
-  if ((threadIdx.x & 31) == 0 && n_mid) atomicAdd(&P.ctr->scratch[1], n_mid);
 }
 
-// Rows of reads with 9..32 alignments: one warp per EC, one alignment per lane.
-__global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P) {
+// Rows of reads with 9..32 alignments (listed by the short kernel): one warp per EC, one alignment
+// per lane.
+__global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P, u32 n_mid) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 e = P.e0 + warp_global; e < P.e1; e += n_warps) {
+  for (u32 i = warp_global; i < n_mid; i += n_warps) {
+    const u32 e = P.mid_list[i];
     const int k = (int)P.ec_len[e];
-    if (k <= 8 || k > 32) continue;
     const int s = (int)P.ec_rep[e];
     const int t = lane < k ? P.tg[s + lane] : -1 - lane;
     const u32 hbit = lane < k ? (1u << P.hp[s + lane]) : 0u;

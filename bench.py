@@ -245,25 +245,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(builder, columns, steps, finalize):
+    def timed_once(builder, columns, steps, finalize):
         """K steps bracketed by barrier + synchronize, CUDA events on the library's stream."""
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         group_ms = []
-        e0.record(stream)
-        for _ in range(steps):
+        marks[0].record(stream)
+        for i in range(steps):
             builder.reset()
             builder.push(columns["read_group"], columns["target_idx"], columns["hap_idx"], order_base=order_base)
             res = finalize(builder)
             group_ms.append(builder.stats()["group_ms"])
-        e1.record(stream)
+            marks[i + 1].record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = marks[0].elapsed_time(marks[-1])
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, res, group_ms
+        return ms, res, group_ms, per_step
+
+    def timed(builder, columns, steps, finalize):
+        """timed_once; a region disturbed by a one-off stall (one step more than 3x the median step, seen
+        on shared boxes) is measured once more and the undisturbed region is kept, with a note."""
+        ms, res, group_ms, per_step = timed_once(builder, columns, steps, finalize)
+        note = None
+        med = sorted(per_step)[len(per_step) // 2]
+        flag = torch.tensor([1.0 if (steps >= 3 and max(per_step) > 3.0 * med) else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() > 0:
+            ms2, res, group_ms2, per_step2 = timed_once(builder, columns, steps, finalize)
+            note = {"remeasured": True, "first_try_ms_per_step": ms / steps, "first_try_max_step_ms": max(per_step)}
+            if ms2 < ms:
+                ms, group_ms, per_step = ms2, group_ms2, per_step2
+        return ms, res, group_ms, note
 
     # ---- device-resident arm ("value") --------------------------------------------------------------
     b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
@@ -272,7 +289,7 @@ def main():
     timed(b_dev, dev, args.warmup, lambda b: b.finalize_raw())
     launches0 = b_dev.stats()["kernel_launches"]
     with ClockSampler(local_rank) as clocks:
-        ms_dev, res_dev, group_ms = timed(b_dev, dev, args.steps, lambda b: b.finalize_raw())
+        ms_dev, res_dev, group_ms, note_dev = timed(b_dev, dev, args.steps, lambda b: b.finalize_raw())
     stats_dev = b_dev.stats()
     launches_per_step = stats_dev["kernel_launches"]  # stats are zeroed by reset(): this is the last step
     n_ec, nnz_a = int(res_dev.n_ec), int(res_dev.nnz_a)
@@ -283,7 +300,7 @@ def main():
     b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank, **opts)
     b_e2e.set_stream(stream.cuda_stream)
     timed(b_e2e, host, 1, lambda b: b.finalize_raw())
-    ms_e2e, res_e2e, _ = timed(b_e2e, host, args.steps, lambda b: b.finalize_raw())
+    ms_e2e, res_e2e, _, note_e2e = timed(b_e2e, host, args.steps, lambda b: b.finalize_raw())
     stats_e2e = b_e2e.stats()
     assert int(res_e2e.n_ec) == n_ec
     b_e2e.close()
@@ -322,6 +339,10 @@ def main():
                      "kernel_share_of_step": gms / (ms_dev / args.steps)},
         "clocks": clocks.summary(),
     }
+    if note_dev:
+        line["remeasured"] = note_dev
+    if note_e2e:
+        line["e2e"]["remeasured"] = note_e2e
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = run_cpu_arm(args.workload, 2, 0, args.cpu_sample_reads, max_seconds=60.0)
     print(json.dumps(line))
