@@ -33,6 +33,17 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the grouping kernel from the committed ncu capture (or None)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            t = json.load(fh)
+        return float(t["dram_bytes_per_launch"]) if t.get("workload") == workload else None
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -334,7 +345,7 @@ def main():
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "ecb_group_insert_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": peak_kind,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": gms,
                      "kernel_share_of_step": gms / (ms_dev / args.steps)},
         "clocks": clocks.summary(),
