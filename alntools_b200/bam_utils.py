@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-from . import bin_utils, emase, emitter, utils
+from . import bamcols, bin_utils, emase, emitter, utils
 from ._native import EcBuilder
 from .header import TargetTables
 
@@ -26,6 +26,23 @@ def _job_plan(num_chunks, number_processes):
         LOG.info("Modifying number of chunks from {} to 1000".format(num_chunks))
         num_chunks = 1000
     return num_chunks, min(num_processes, num_chunks)
+
+
+def _convert_python_emitter(bam_filename, target_filename, device, start_time):
+    """The same build fed by the record-level Python emitter (ALNTOOLS_B200_EMITTER=python)."""
+    temp_time = time.time()
+    header, records = emitter.read_bam(bam_filename)
+    tables = TargetTables(header.references, header.lengths, target_filename)
+    LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
+                                                        utils.format_time(start_time, time.time())))
+    cols = emitter.emit_single(records, tables)
+    if cols.valid_alignments == 0:
+        raise RuntimeError("The shape must be a tuple of three positive integers.")
+    with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False,
+                   alignments_hint=cols.valid_alignments, device=device) as builder:
+        builder.push(cols.read_group, cols.target_idx, cols.hap_idx, order_base=0)
+        res = builder.finalize()
+    return res, tables, cols.valid_alignments
 
 
 def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_processes=-1, temp_dir=None,
@@ -46,26 +63,30 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
 
     LOG.info("Parsing file information ...")
     temp_time = time.time()
-    header, records = emitter.read_bam(bam_filename)
-    tables = TargetTables(header.references, header.lengths, target_filename)
-    LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
-                                                        utils.format_time(start_time, time.time())))
-
-    temp_time = time.time()
-    cols = emitter.emit_single(records, tables)
-    LOG.info("Columns emitted in {}".format(utils.format_time(temp_time, time.time())))
-    if cols.valid_alignments == 0:
-        # the reference ends up with zero ECs and APM() raises (Sparse3DMatrix.py:45-46)
-        raise RuntimeError("The shape must be a tuple of three positive integers.")
-
-    temp_time = time.time()
-    with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False,
-                   alignments_hint=cols.valid_alignments, device=device) as builder:
-        builder.push(cols.read_group, cols.target_idx, cols.hap_idx, order_base=0)
-        res = builder.finalize()
+    if emitter.use_python_emitter():
+        res, tables, valid = _convert_python_emitter(bam_filename, target_filename, device, start_time)
+    else:
+        # native emitter: inflate threads + one record pass, streamed to the GPU in read-aligned chunks
+        import torch
+        with bamcols.BamColumnReader(bam_filename, n_threads=num_processes) as reader:
+            tables = TargetTables(reader.references, reader.lengths, target_filename)
+            reader.set_tables(tables)
+            LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
+                                                                utils.format_time(start_time, time.time())))
+            temp_time = time.time()
+            hint = max(1 << 20, os.path.getsize(bam_filename) // 16)
+            with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False, alignments_hint=hint,
+                           device=device) as builder:
+                chunk_rows = int(min(1 << 23, max(1 << 16, os.path.getsize(bam_filename) // 2)))
+                valid = emitter.stream_single(reader, builder, chunk_rows=chunk_rows,
+                                              pinned=torch.cuda.is_available())
+                if valid == 0:
+                    # the reference ends up with zero ECs and APM() raises (Sparse3DMatrix.py:45-46)
+                    raise RuntimeError("The shape must be a tuple of three positive integers.")
+                res = builder.finalize()
     LOG.info("All results combined in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
                                                                  utils.format_time(start_time, time.time())))
-    LOG.info("# Valid Alignments: {:,}".format(cols.valid_alignments))
+    LOG.info("# Valid Alignments: {:,}".format(valid))
     LOG.info("# Main Targets: {:,}".format(tables.num_targets))
     LOG.info("# Haplotypes: {:,}".format(tables.num_haplotypes))
     LOG.info("# Equivalence Classes: {:,}".format(res["n_ec"]))

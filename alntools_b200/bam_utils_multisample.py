@@ -7,7 +7,7 @@ import glob
 import os
 import time
 
-from . import bin_utils, emase, emitter, utils
+from . import bamcols, bin_utils, emase, emitter, utils
 from ._native import EcBuilder
 from .header import TargetTables
 
@@ -18,27 +18,40 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
     """The reference's convert() after its glob: files are merged in the given order
     (bam_utils_multisample.py:503-560)."""
     start_time = time.time()
-    header, _ = emitter.read_bam(bam_files[0])                # tables from the first file only (:399)
-    tables = TargetTables(header.references, header.lengths, target_filename)
-    cell_ids = {}
     per_file = []
     total_valid = 0
-    for bam_file in bam_files:
-        _, records = emitter.read_bam(bam_file)
-        cols = emitter.emit_multisample(records, tables, cell_ids)
-        per_file.append(cols)
-        total_valid += cols.valid_alignments
-    cell_names = [None] * len(cell_ids)
-    for name, idx in cell_ids.items():
-        cell_names[idx] = name
+    if emitter.use_python_emitter():
+        header, _ = emitter.read_bam(bam_files[0])            # tables from the first file only (:399)
+        tables = TargetTables(header.references, header.lengths, target_filename)
+        cell_ids = {}
+        for bam_file in bam_files:
+            _, records = emitter.read_bam(bam_file)
+            cols = emitter.emit_multisample(records, tables, cell_ids)
+            per_file.append((cols.read_group, cols.target_idx, cols.hap_idx, cols.cell_idx))
+            total_valid += cols.valid_alignments
+        cell_names = [None] * len(cell_ids)
+        for name, idx in cell_ids.items():
+            cell_names[idx] = name
+    else:
+        cells = bamcols.CellDictionary()
+        tables = None
+        for bam_file in bam_files:
+            with bamcols.BamColumnReader(bam_file) as reader:
+                if tables is None:                            # tables from the first file only (:399)
+                    tables = TargetTables(reader.references, reader.lengths, target_filename)
+                reader.set_tables(tables)
+                c = reader.read_all(cells=cells)
+            per_file.append((c["read_group"], c["target_idx"], c["hap_idx"], c["cell_idx"]))
+            total_valid += len(c["read_group"])
+        cell_names = cells.names()
+        cells.close()
 
     with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
                    alignments_hint=total_valid, device=device) as builder:
         base = 0
-        for cols in per_file:
-            builder.push(cols.read_group, cols.target_idx, cols.hap_idx, cols.cell_idx, order_base=base,
-                         drop_last_group=True)
-            base += cols.valid_alignments
+        for rg, tg, hp, cell in per_file:
+            builder.push(rg, tg, hp, cell, order_base=base, drop_last_group=True)
+            base += len(rg)
         res = builder.finalize(minimum_count)
 
     LOG.info("Number of alignments: {:,}".format(total_valid))

@@ -1,0 +1,171 @@
+"""ctypes binding of libbamcols.so (include/bamcols.h): the native host column emitter.
+
+BAM file -> int32 columns (read_group, target_idx, hap_idx[, cell_idx]) with the reference's filters
+and read-name grouping (alntools/bam_utils.py:253-306, bam_utils_multisample.py:209-300), decoded by
+a pool of inflate threads instead of one pysam object per alignment.  `emitter.py` holds the
+record-level Python statement of the same rules; tests/test_bamcols.py keeps the two identical.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbamcols.so")
+_lib = None
+
+_I32P = ctypes.POINTER(ctypes.c_int32)
+SIGNATURES = {
+    "bamcols_open": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_char_p, ctypes.c_int]),
+    "bamcols_close": (None, [ctypes.c_void_p]),
+    "bamcols_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "bamcols_n_references": (ctypes.c_int, [ctypes.c_void_p]),
+    "bamcols_reference_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_reference_length": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_set_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_cells_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
+    "bamcols_cells_destroy": (None, [ctypes.c_void_p]),
+    "bamcols_cells_count": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bamcols_cells_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int64]),
+    "bamcols_emit": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.POINTER(ctypes.c_int)]),
+    "bamcols_all_alignments": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bamcols_n_groups": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bamcols_phase_seconds": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+}
+
+BAMCOLS_ERR_IO, BAMCOLS_ERR_FORMAT, BAMCOLS_ERR_INVALID, BAMCOLS_ERR_CELL_FIELD, BAMCOLS_ERR_TID = -1, -2, -3, -4, -5
+
+
+def load_library(path=None):
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+    lib = ctypes.CDLL(p)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _raise(code, msg):
+    if code == BAMCOLS_ERR_CELL_FIELD:
+        raise IndexError(msg)                      # what the reference raises (bam_utils_multisample.py:273)
+    if code == BAMCOLS_ERR_IO:
+        raise IOError(msg)
+    raise ValueError(msg)
+
+
+class CellDictionary(object):
+    """Cell names of one per-cell job, dense ids in order of first appearance (shared by all files)."""
+
+    def __init__(self):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        self._lib.bamcols_cells_create(ctypes.byref(h))
+        self._h = h
+
+    def __len__(self):
+        return int(self._lib.bamcols_cells_count(self._h))
+
+    def names(self):
+        return [self._lib.bamcols_cells_name(self._h, i).decode() for i in range(len(self))]
+
+    def close(self):
+        if self._h:
+            self._lib.bamcols_cells_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+class BamColumnReader(object):
+    """One BAM file.  `references` / `lengths` as pysam's; set_tables() then emit()/read_all()."""
+
+    def __init__(self, filename, n_threads=0):
+        self._h = None
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self._lib.bamcols_open(ctypes.byref(h), os.fsencode(filename), int(n_threads))
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(None).decode())
+        self._h = h
+        n = self._lib.bamcols_n_references(h)
+        self.references = tuple(self._lib.bamcols_reference_name(h, i).decode() for i in range(n))
+        self.lengths = tuple(self._lib.bamcols_reference_length(h, i) for i in range(n))
+
+    def set_tables(self, tables):
+        tt = np.ascontiguousarray(tables.tid_target, dtype=np.int32)
+        th = np.ascontiguousarray(tables.tid_hap, dtype=np.int32)
+        rc = self._lib.bamcols_set_tables(self._h, tt.ctypes.data, th.ctypes.data, len(tt))
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(self._h).decode())
+
+    def emit(self, read_group, target_idx, hap_idx, cell_idx=None, cells=None):
+        """Fill the given int32 arrays (numpy or pinned torch tensors) with the next whole reads.
+        Returns (rows, done)."""
+        cap = int(read_group.shape[0])
+        done = ctypes.c_int(0)
+        ptr = lambda a: None if a is None else (a.ctypes.data if isinstance(a, np.ndarray) else a.data_ptr())
+        n = self._lib.bamcols_emit(self._h, cells._h if cells is not None else None, ptr(read_group),
+                                   ptr(target_idx), ptr(hap_idx), ptr(cell_idx), cap, ctypes.byref(done))
+        if n < 0:
+            _raise(int(n), self._lib.bamcols_last_error(self._h).decode())
+        return int(n), bool(done.value)
+
+    def read_all(self, cells=None, chunk=1 << 20):
+        """The whole file as numpy columns: dict(read_group, target_idx, hap_idx[, cell_idx])."""
+        parts = []
+        while True:
+            bufs = [np.empty(chunk, dtype=np.int32) for _ in range(4 if cells is not None else 3)]
+            try:
+                n, done = self.emit(bufs[0], bufs[1], bufs[2], bufs[3] if cells is not None else None, cells)
+            except ValueError as exc:
+                if "buffers hold" in str(exc) and chunk < (1 << 28):   # a read longer than the chunk
+                    chunk *= 4
+                    continue
+                raise
+            parts.append([b[:n] for b in bufs])
+            if done:
+                break
+        cols = [np.concatenate([p[i] for p in parts]) if len(parts) > 1 else parts[0][i]
+                for i in range(len(parts[0]))]
+        out = {"read_group": cols[0], "target_idx": cols[1], "hap_idx": cols[2]}
+        if cells is not None:
+            out["cell_idx"] = cols[3]
+        return out
+
+    @property
+    def all_alignments(self):
+        return int(self._lib.bamcols_all_alignments(self._h))
+
+    def phase_seconds(self):
+        """dict phase -> wall-clock seconds so far (single-sample path)."""
+        out = (ctypes.c_double * 6)()
+        self._lib.bamcols_phase_seconds(self._h, out)
+        return dict(zip(("inflate", "record_hop", "validity", "read_starts", "rows", "copy_out"), list(out)))
+
+    @property
+    def n_groups(self):
+        return int(self._lib.bamcols_n_groups(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.bamcols_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        self.close()

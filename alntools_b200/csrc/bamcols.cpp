@@ -1,0 +1,692 @@
+// bamcols.cpp — libbamcols.so: BGZF/BAM decode + the reference's per-alignment filters and read-name
+// grouping, emitting the int32 columns libecb200 consumes (C ABI in include/bamcols.h).
+//
+// Replaces the front half of alntools/bam_utils.py:253-306 and bam_utils_multisample.py:209-300, which
+// the reference runs one pysam object at a time inside Python.  Here: the file is memory-mapped,
+// BGZF blocks are inflated a batch at a time by a pool of worker threads (blocks are independent
+// deflate streams, SAM spec 4.1), and one pass over the fixed-offset record fields produces the rows.
+#include <zlib.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "../../include/bamcols.h"
+
+namespace {
+
+thread_local std::string g_open_error;
+
+inline uint32_t le32(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }
+inline uint32_t le16(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+
+struct BlockJob {
+  const uint8_t* src;
+  uint32_t src_len;
+  uint32_t isize;
+  size_t dst_off;
+};
+
+// One completed or growing read: its rows (the read_group value is the same for all of them).
+struct GroupRows {
+  std::vector<int32_t> tg, hp, cell;
+  int32_t group = 0;
+  size_t size() const { return tg.size(); }
+  void clear() { tg.clear(); hp.clear(); cell.clear(); }
+};
+
+}  // namespace
+
+struct bamcols_cells {
+  std::unordered_map<std::string, int32_t> ids;
+  std::vector<std::string> names;
+  int32_t id_of(const char* s, size_t n) {
+    std::string key(s, n);
+    auto it = ids.find(key);
+    if (it != ids.end()) return it->second;
+    const int32_t id = (int32_t)names.size();
+    ids.emplace(key, id);
+    names.push_back(std::move(key));
+    return id;
+  }
+};
+
+struct bamcols {
+  int fd = -1;
+  const uint8_t* file = nullptr;
+  size_t file_size = 0;
+  size_t cpos = 0;               // compressed offset of the next BGZF block
+  bool file_done = false;        // every block has been inflated
+  std::vector<uint8_t> win;      // inflated window
+  size_t wpos = 0, wend = 0;     // unread part of the window
+  int n_threads = 1;
+  size_t batch_blocks = 2048;    // up to 128 MiB inflated per refill
+  // header
+  std::vector<std::string> ref_names;
+  std::vector<int32_t> ref_lengths;
+  std::vector<int32_t> tid_target, tid_hap;
+  // grouping state (persists across emit calls)
+  bool started = false;          // a valid alignment has been seen
+  std::string current;           // remembered read name
+  int64_t group = -1;
+  bool pending = false;          // per-cell: the current read's cell is resolved at the next valid alignment
+  int32_t cell = 0;
+  GroupRows cur, ready;
+  bool records_done = false, all_flushed = false;
+  int64_t all_alignments = 0;
+  // single-sample batch path: rows of the current inflated window, produced by all worker threads
+  std::vector<int32_t> st_rg, st_tg, st_hp;
+  size_t st_pos = 0;             // next row to hand out
+  size_t st_whole = 0;           // rows [st_pos, st_whole) are whole reads; [st_whole, size) is the open last read
+  std::vector<size_t> rec_off;   // scratch: record offsets of the window
+  std::vector<uint8_t> rec_flag; // scratch: bit 0 valid, bit 1 starts a read
+  int mode = 0;                  // 0 undecided, 1 single-sample, 2 per-cell
+  size_t grain = 4096;           // records per worker thread below which no further thread is used
+  double phase_s[6] = {0, 0, 0, 0, 0, 0};  // inflate, record hop, validity, read starts, rows, copy-out
+  std::string err;
+};
+
+namespace {
+
+struct PhaseTimer {
+  double* acc;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  explicit PhaseTimer(double* a) : acc(a) {}
+  ~PhaseTimer() { *acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+int fail(bamcols* r, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (r) r->err = buf; else g_open_error = buf;
+  return code;
+}
+
+// Locate the next BGZF block at `off`: payload pointer/length and inflated size.  0 = ok, 1 = clean
+// end of file, <0 = error.
+int parse_block(bamcols* r, size_t off, BlockJob* job, size_t* bsize_out) {
+  const size_t n = r->file_size;
+  if (off == n) return 1;
+  if (off + 18 > n) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BGZF block header at offset %zu", off);
+  const uint8_t* p = r->file + off;
+  if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4))
+    return fail(r, BAMCOLS_ERR_FORMAT, "not a BGZF block at offset %zu", off);
+  const size_t xlen = le16(p + 10);
+  if (off + 12 + xlen > n) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BGZF extra field at offset %zu", off);
+  size_t bsize = 0;
+  for (size_t q = 12; q + 4 <= 12 + xlen;) {
+    const size_t slen = le16(p + q + 2);
+    if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2) bsize = (size_t)le16(p + q + 4) + 1;
+    q += 4 + slen;
+  }
+  if (bsize == 0) return fail(r, BAMCOLS_ERR_FORMAT, "BGZF block without BC field at offset %zu", off);
+  if (bsize < 12 + xlen + 8 || off + bsize > n)
+    return fail(r, BAMCOLS_ERR_FORMAT, "truncated BGZF block at offset %zu", off);
+  job->src = p + 12 + xlen;
+  job->src_len = (uint32_t)(bsize - 12 - xlen - 8);
+  job->isize = le32(p + bsize - 4);
+  // the spec caps ISIZE at 64 KiB, but writers that ignore the cap exist (and inflate does not care)
+  if (job->isize > (1u << 30)) return fail(r, BAMCOLS_ERR_FORMAT, "BGZF block at offset %zu claims %u bytes", off, job->isize);
+  *bsize_out = bsize;
+  return 0;
+}
+
+bool inflate_block(z_stream* zs, const BlockJob& job, uint8_t* dst) {
+  if (job.isize == 0) return true;
+  if (inflateReset(zs) != Z_OK) return false;
+  zs->next_in = const_cast<Bytef*>(job.src);
+  zs->avail_in = job.src_len;
+  zs->next_out = dst;
+  zs->avail_out = job.isize;
+  const int rc = inflate(zs, Z_FINISH);
+  return rc == Z_STREAM_END && zs->avail_out == 0;
+}
+
+// Inflate the next batch of blocks behind the unread part of the window.  Returns 0, or <0 on error;
+// sets file_done when the file has no more blocks.
+int refill(bamcols* r) {
+  if (r->file_done) return 0;
+  PhaseTimer timer(&r->phase_s[0]);
+  // keep the unread tail at the front
+  const size_t keep = r->wend - r->wpos;
+  if (r->wpos > 0 && keep > 0) memmove(r->win.data(), r->win.data() + r->wpos, keep);
+  r->wpos = 0;
+  r->wend = keep;
+  std::vector<BlockJob> jobs;
+  jobs.reserve(r->batch_blocks);
+  size_t total = 0;
+  while (jobs.size() < r->batch_blocks) {
+    BlockJob job;
+    size_t bsize = 0;
+    const int rc = parse_block(r, r->cpos, &job, &bsize);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      r->file_done = true;
+      break;
+    }
+    job.dst_off = keep + total;
+    total += job.isize;
+    r->cpos += bsize;
+    jobs.push_back(job);
+  }
+  if (jobs.empty()) return 0;
+  if (r->win.size() < keep + total) r->win.resize(keep + total);
+  uint8_t* base = r->win.data();
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, (jobs.size() + 15) / 16));
+  std::atomic<size_t> next(0);
+  std::atomic<int> bad(0);
+  auto work = [&]() {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) {
+      bad.store(1);
+      return;
+    }
+    for (;;) {
+      const size_t i0 = next.fetch_add(8);
+      if (i0 >= jobs.size()) break;
+      const size_t i1 = std::min(jobs.size(), i0 + 8);
+      for (size_t i = i0; i < i1; ++i)
+        if (!inflate_block(&zs, jobs[i], base + jobs[i].dst_off)) bad.store(1);
+    }
+    inflateEnd(&zs);
+  };
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  if (bad.load()) return fail(r, BAMCOLS_ERR_FORMAT, "corrupt BGZF block (inflate failed) before offset %zu", r->cpos);
+  r->wend = keep + total;
+  return 0;
+}
+
+// Make at least `need` unread bytes available.  Returns 1 if they are, 0 at a clean end of data
+// (fewer than `need` bytes left in the whole file), <0 on error.
+int ensure_bytes(bamcols* r, size_t need) {
+  while (r->wend - r->wpos < need) {
+    if (r->file_done) return 0;
+    const int rc = refill(r);
+    if (rc < 0) return rc;
+  }
+  return 1;
+}
+
+int read_header(bamcols* r) {
+  int rc = ensure_bytes(r, 12);
+  if (rc < 0) return rc;
+  if (rc == 0 || memcmp(r->win.data() + r->wpos, "BAM\1", 4) != 0) return fail(r, BAMCOLS_ERR_FORMAT, "not a BAM stream");
+  const size_t l_text = le32(r->win.data() + r->wpos + 4);
+  rc = ensure_bytes(r, 12 + l_text);
+  if (rc <= 0) return rc < 0 ? rc : fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM header");
+  const size_t n_ref = le32(r->win.data() + r->wpos + 8 + l_text);
+  r->wpos += 12 + l_text;
+  r->ref_names.reserve(n_ref);
+  r->ref_lengths.reserve(n_ref);
+  for (size_t i = 0; i < n_ref; ++i) {
+    rc = ensure_bytes(r, 4);
+    if (rc <= 0) return rc < 0 ? rc : fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM reference list");
+    const size_t l_name = le32(r->win.data() + r->wpos);
+    rc = ensure_bytes(r, 8 + l_name);
+    if (rc <= 0) return rc < 0 ? rc : fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM reference list");
+    const uint8_t* p = r->win.data() + r->wpos;
+    r->ref_names.emplace_back((const char*)p + 4, l_name ? l_name - 1 : 0);
+    r->ref_lengths.push_back((int32_t)le32(p + 4 + l_name));
+    r->wpos += 8 + l_name;
+  }
+  return 0;
+}
+
+// bam_utils.py:301-304: cut the name at the first blank unless the blank is its first character.
+inline size_t trimmed_len(const char* s, size_t n) {
+  const void* sp = memchr(s, ' ', n);
+  if (!sp) return n;
+  const size_t i = (const char*)sp - s;
+  return i > 0 ? i : n;
+}
+
+// Field 14 of name.split('|||') (bam_utils_multisample.py:273).  false: fewer than 15 fields.
+bool cell_field(const std::string& name, const char** out, size_t* len) {
+  size_t start = 0;
+  for (int f = 0; f < 14; ++f) {
+    const size_t p = name.find("|||", start);
+    if (p == std::string::npos) return false;
+    start = p + 3;
+  }
+  const size_t e = name.find("|||", start);
+  *out = name.data() + start;
+  *len = (e == std::string::npos ? name.size() : e) - start;
+  return true;
+}
+
+template <class F>
+void parallel_for(int nt, F fn) {
+  if (nt <= 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t) pool.emplace_back(fn, t);
+  for (auto& t : pool) t.join();
+}
+
+// Single-sample rules (bam_utils.py:258-328) over every whole record of the inflated window, on all
+// worker threads: (1) one sequential hop over the block_size fields finds the records, (2) validity
+// per record, (3) "starts a read" per valid record = its trimmed name differs from the previous valid
+// record's, (4) rows written at their final position (prefix sums over the threads).  The open last
+// read is held back (st_whole) until the next window or the end of the file closes it.
+int process_window_single(bamcols* r) {
+  // rows still waiting from the previous window go to the front
+  const size_t left = r->st_rg.size() - r->st_pos;
+  if (r->st_pos > 0) {
+    memmove(r->st_rg.data(), r->st_rg.data() + r->st_pos, left * 4);
+    memmove(r->st_tg.data(), r->st_tg.data() + r->st_pos, left * 4);
+    memmove(r->st_hp.data(), r->st_hp.data() + r->st_pos, left * 4);
+  }
+  r->st_rg.resize(left);
+  r->st_tg.resize(left);
+  r->st_hp.resize(left);
+  r->st_whole -= r->st_pos;
+  r->st_pos = 0;
+
+  // (1) records of the window
+  if (r->wend - r->wpos < 4 || r->wend - r->wpos < 4 + (size_t)le32(r->win.data() + r->wpos)) {
+    const int rc = refill(r);
+    if (rc < 0) return rc;
+  }
+  const uint8_t* base = r->win.data();
+  std::vector<size_t>& off = r->rec_off;
+  off.clear();
+  size_t p = r->wpos;
+  {
+    PhaseTimer timer(&r->phase_s[1]);
+    while (p + 4 <= r->wend) {
+      const size_t bs = le32(base + p);
+      if (bs < 32) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", bs);
+      if (p + 4 + bs > r->wend) break;
+      off.push_back(p);
+      p += 4 + bs;
+    }
+  }
+  r->wpos = p;
+  const size_t n = off.size();
+  if (n == 0) {
+    if (r->file_done) {
+      if (r->wend != r->wpos) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM record at the end of the file");
+      r->records_done = true;
+      r->st_whole = r->st_rg.size();  // the end of the file closes the last read
+    }
+    return 0;
+  }
+  r->all_alignments += (int64_t)n;
+  std::vector<uint8_t>& fl = r->rec_flag;
+  fl.assign(n, 0);
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, n / r->grain + 1));
+  const int32_t n_ref = (int32_t)r->tid_target.size();
+  std::vector<size_t> n_valid(nt + 1, 0), n_start(nt + 1, 0);
+  std::atomic<int> bad(0);
+  auto lo = [&](int t) { return n * (size_t)t / (size_t)nt; };
+  // (2) validity (bam_utils.py:264-270)
+  PhaseTimer* timer = new PhaseTimer(&r->phase_s[2]);
+  parallel_for(nt, [&](int t) {
+    size_t cnt = 0;
+    for (size_t i = lo(t); i < lo(t + 1); ++i) {
+      const uint8_t* q = base + off[i] + 4;
+      const size_t bs = le32(base + off[i]);
+      const int32_t tid = (int32_t)le32(q);
+      const size_t l_name = q[8];
+      const uint32_t flag = le16(q + 14);
+      const int32_t ntid = (int32_t)le32(q + 20), npos = (int32_t)le32(q + 24);
+      if (32 + l_name > bs || l_name == 0) { bad.store(1); continue; }
+      if (flag & 0x4) continue;
+      if ((flag & 0x1) && ((flag & 0x80) || !(flag & 0x2) || tid != ntid || npos < 0)) continue;
+      if (tid < 0 || tid >= n_ref) { bad.store(2); continue; }
+      fl[i] = 1;
+      ++cnt;
+    }
+    n_valid[t + 1] = cnt;
+  });
+  delete timer;
+  if (bad.load() == 1) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with a bad read-name length");
+  if (bad.load() == 2) return fail(r, BAMCOLS_ERR_TID, "alignment with a reference id outside the header's %d references", n_ref);
+  // (3) read starts (bam_utils.py:301-306)
+  const bool had_prev = r->started;
+  const std::string prev_name = r->current;
+  timer = new PhaseTimer(&r->phase_s[3]);
+  parallel_for(nt, [&](int t) {
+    const char* pn = nullptr;  // trimmed name of the previous valid record
+    size_t pl = 0;
+    bool have = false;
+    for (size_t j = lo(t); j-- > 0;)
+      if (fl[j]) {
+        const uint8_t* q = base + off[j] + 4;
+        pn = (const char*)q + 32;
+        pl = trimmed_len(pn, (size_t)q[8] - 1);
+        have = true;
+        break;
+      }
+    if (!have && had_prev) {
+      pn = prev_name.data();
+      pl = prev_name.size();
+      have = true;
+    }
+    size_t cnt = 0;
+    for (size_t i = lo(t); i < lo(t + 1); ++i) {
+      if (!fl[i]) continue;
+      const uint8_t* q = base + off[i] + 4;
+      const char* nm = (const char*)q + 32;
+      const size_t nl = trimmed_len(nm, (size_t)q[8] - 1);
+      if (!have || nl != pl || memcmp(nm, pn, nl) != 0) {
+        fl[i] |= 2;
+        ++cnt;
+      }
+      pn = nm;
+      pl = nl;
+      have = true;
+    }
+    n_start[t + 1] = cnt;
+  });
+  delete timer;
+  for (int t = 0; t < nt; ++t) {
+    n_valid[t + 1] += n_valid[t];
+    n_start[t + 1] += n_start[t];
+  }
+  const size_t rows = n_valid[nt];
+  if (rows) {
+    const size_t row0 = r->st_rg.size();
+    r->st_rg.resize(row0 + rows);
+    r->st_tg.resize(row0 + rows);
+    r->st_hp.resize(row0 + rows);
+    const int64_t group0 = r->group;  // id of the read that is open when the window begins (-1: none)
+    int32_t* rg = r->st_rg.data() + row0;
+    int32_t* tg = r->st_tg.data() + row0;
+    int32_t* hp = r->st_hp.data() + row0;
+    // (4) rows
+    PhaseTimer rows_timer(&r->phase_s[4]);
+    parallel_for(nt, [&](int t) {
+      size_t k = n_valid[t];
+      int64_t g = group0 + (int64_t)n_start[t];
+      for (size_t i = lo(t); i < lo(t + 1); ++i) {
+        if (!fl[i]) continue;
+        if (fl[i] & 2) ++g;
+        const int32_t tid = (int32_t)le32(base + off[i] + 4);
+        rg[k] = (int32_t)g;
+        tg[k] = r->tid_target[tid];
+        hp[k] = r->tid_hap[tid];
+        ++k;
+      }
+    });
+    r->group = group0 + (int64_t)n_start[nt];
+    // remember the last valid record's trimmed name for the next window
+    for (size_t j = n; j-- > 0;)
+      if (fl[j]) {
+        const uint8_t* q = base + off[j] + 4;
+        const char* nm = (const char*)q + 32;
+        r->current.assign(nm, trimmed_len(nm, (size_t)q[8] - 1));
+        break;
+      }
+    r->started = true;
+    // whole reads = everything before the start of the last read
+    size_t w = r->st_rg.size();
+    const int32_t last = r->st_rg[w - 1];
+    while (w > 0 && r->st_rg[w - 1] == last) --w;
+    r->st_whole = w;
+  }
+  return 0;
+}
+
+int64_t emit_single(bamcols* r, int32_t* read_group, int32_t* target_idx, int32_t* hap_idx, int64_t capacity, int* done) {
+  int64_t rows = 0;
+  for (;;) {
+    const size_t avail = r->st_whole - r->st_pos;
+    if (avail > 0) {
+      size_t take = std::min<size_t>(avail, (size_t)(capacity - rows));
+      if (take < avail)  // stop at the start of a read
+        while (take > 0 && r->st_rg[r->st_pos + take] == r->st_rg[r->st_pos + take - 1]) --take;
+      if (take == 0) {
+        if (rows == 0) return fail(r, BAMCOLS_ERR_INVALID, "a read has more alignments than the buffers hold (%lld rows)", (long long)capacity);
+        return rows;
+      }
+      PhaseTimer timer(&r->phase_s[5]);
+      memcpy(read_group + rows, r->st_rg.data() + r->st_pos, take * 4);
+      memcpy(target_idx + rows, r->st_tg.data() + r->st_pos, take * 4);
+      memcpy(hap_idx + rows, r->st_hp.data() + r->st_pos, take * 4);
+      rows += (int64_t)take;
+      r->st_pos += take;
+      if (rows == capacity) return rows;
+      continue;
+    }
+    if (r->records_done) {
+      *done = 1;
+      return rows;
+    }
+    const int rc = process_window_single(r);
+    if (rc < 0) return rc;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bamcols_last_error(const bamcols* r) { return r ? r->err.c_str() : g_open_error.c_str(); }
+
+int bamcols_open(bamcols** out, const char* path, int n_threads) {
+  if (!out || !path) return fail(nullptr, BAMCOLS_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  bamcols* r = new bamcols();
+  auto bail = [&](int code) {
+    g_open_error = r->err;
+    bamcols_close(r);
+    return code;
+  };
+  r->fd = open(path, O_RDONLY);
+  if (r->fd < 0) {
+    fail(r, BAMCOLS_ERR_IO, "cannot open %s", path);
+    return bail(BAMCOLS_ERR_IO);
+  }
+  struct stat st;
+  if (fstat(r->fd, &st) != 0 || st.st_size <= 0) {
+    fail(r, BAMCOLS_ERR_IO, "cannot stat %s (or it is empty)", path);
+    return bail(BAMCOLS_ERR_IO);
+  }
+  r->file_size = (size_t)st.st_size;
+  void* m = mmap(nullptr, r->file_size, PROT_READ, MAP_PRIVATE, r->fd, 0);
+  if (m == MAP_FAILED) {
+    fail(r, BAMCOLS_ERR_IO, "cannot mmap %s", path);
+    return bail(BAMCOLS_ERR_IO);
+  }
+  r->file = (const uint8_t*)m;
+  madvise(m, r->file_size, MADV_SEQUENTIAL);
+  if (const char* g = getenv("BAMCOLS_GRAIN")) r->grain = (size_t)std::max(1L, atol(g));  // tests: split tiny inputs too
+  const unsigned hw = std::thread::hardware_concurrency();
+  r->n_threads = n_threads > 0 ? n_threads : (hw ? (int)hw : 1);
+  if (r->file_size < 4 || r->file[0] != 0x1f || r->file[1] != 0x8b) {
+    fail(r, BAMCOLS_ERR_FORMAT, "File %s is not a BAM file", path);
+    return bail(BAMCOLS_ERR_FORMAT);
+  }
+  // the header rarely needs more than a few blocks: start with a small batch
+  const size_t full_batch = r->batch_blocks;
+  r->batch_blocks = 16;
+  const int rc = read_header(r);
+  r->batch_blocks = full_batch;
+  if (rc < 0) return bail(rc);
+  *out = r;
+  return BAMCOLS_OK;
+}
+
+void bamcols_close(bamcols* r) {
+  if (!r) return;
+  if (r->file) munmap(const_cast<uint8_t*>(r->file), r->file_size);
+  if (r->fd >= 0) close(r->fd);
+  delete r;
+}
+
+int bamcols_n_references(const bamcols* r) { return r ? (int)r->ref_names.size() : (int64_t)BAMCOLS_ERR_INVALID; }
+
+const char* bamcols_reference_name(const bamcols* r, int tid) {
+  if (!r || tid < 0 || (size_t)tid >= r->ref_names.size()) return nullptr;
+  return r->ref_names[tid].c_str();
+}
+
+int bamcols_reference_length(const bamcols* r, int tid) {
+  if (!r || tid < 0 || (size_t)tid >= r->ref_lengths.size()) return BAMCOLS_ERR_INVALID;
+  return r->ref_lengths[tid];
+}
+
+int bamcols_set_tables(bamcols* r, const int32_t* tid_target, const int32_t* tid_hap, int n_references) {
+  if (!r || !tid_target || !tid_hap) return BAMCOLS_ERR_INVALID;
+  if ((size_t)n_references != r->ref_names.size())
+    return fail(r, BAMCOLS_ERR_INVALID, "tables have %d entries, the header has %zu references", n_references,
+                r->ref_names.size());
+  r->tid_target.assign(tid_target, tid_target + n_references);
+  r->tid_hap.assign(tid_hap, tid_hap + n_references);
+  return BAMCOLS_OK;
+}
+
+int bamcols_cells_create(bamcols_cells** out) {
+  if (!out) return BAMCOLS_ERR_INVALID;
+  *out = new bamcols_cells();
+  return BAMCOLS_OK;
+}
+void bamcols_cells_destroy(bamcols_cells* c) { delete c; }
+int64_t bamcols_cells_count(const bamcols_cells* c) { return c ? (int64_t)c->names.size() : (int64_t)BAMCOLS_ERR_INVALID; }
+const char* bamcols_cells_name(const bamcols_cells* c, int64_t idx) {
+  if (!c || idx < 0 || (size_t)idx >= c->names.size()) return nullptr;
+  return c->names[(size_t)idx].c_str();
+}
+
+int bamcols_phase_seconds(const bamcols* r, double* out6) {
+  if (!r || !out6) return BAMCOLS_ERR_INVALID;
+  for (int i = 0; i < 6; ++i) out6[i] = r->phase_s[i];
+  return BAMCOLS_OK;
+}
+
+int64_t bamcols_all_alignments(const bamcols* r) { return r ? r->all_alignments : (int64_t)BAMCOLS_ERR_INVALID; }
+int64_t bamcols_n_groups(const bamcols* r) { return r ? r->group + 1 : (int64_t)BAMCOLS_ERR_INVALID; }
+
+int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int32_t* target_idx, int32_t* hap_idx,
+                     int32_t* cell_idx, int64_t capacity, int* done) {
+  if (!r || !read_group || !target_idx || !hap_idx || !done || capacity < 1) return BAMCOLS_ERR_INVALID;
+  if (cells && !cell_idx) return fail(r, BAMCOLS_ERR_INVALID, "per-cell mode needs a cell_idx buffer");
+  if (r->tid_target.empty() && !r->ref_names.empty()) return fail(r, BAMCOLS_ERR_INVALID, "bamcols_set_tables was not called");
+  *done = 0;
+  const int want_mode = cells ? 2 : 1;
+  if (r->mode == 0) r->mode = want_mode;
+  if (r->mode != want_mode) return fail(r, BAMCOLS_ERR_INVALID, "a reader cannot switch between single-sample and per-cell rules");
+  if (!cells) return emit_single(r, read_group, target_idx, hap_idx, capacity, done);
+  // ---- per-cell rules: one sequential pass (the cell dictionary and the remembered-name quirk chain
+  // every read to the previous one) ------------------------------------------------------------------
+  const int32_t n_ref = (int32_t)r->tid_target.size();
+  int64_t rows = 0;
+  for (;;) {
+    // a finished read waits for room in the caller's buffers
+    if (r->ready.size()) {
+      const int64_t k = (int64_t)r->ready.size();
+      if (rows + k > capacity) {
+        if (rows == 0) return fail(r, BAMCOLS_ERR_INVALID, "a read has %lld alignments but the buffers hold %lld rows", (long long)k, (long long)capacity);
+        return rows;
+      }
+      for (int64_t i = 0; i < k; ++i) read_group[rows + i] = r->ready.group;
+      memcpy(target_idx + rows, r->ready.tg.data(), (size_t)k * 4);
+      memcpy(hap_idx + rows, r->ready.hp.data(), (size_t)k * 4);
+      if (cells) memcpy(cell_idx + rows, r->ready.cell.data(), (size_t)k * 4);
+      rows += k;
+      r->ready.clear();
+    }
+    if (r->records_done) {
+      if (!r->all_flushed) {  // the last read of the file
+        r->all_flushed = true;
+        std::swap(r->cur, r->ready);
+        continue;
+      }
+      *done = 1;
+      return rows;
+    }
+    // ---- next record --------------------------------------------------------------------------------
+    int rc = ensure_bytes(r, 4);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (r->wend != r->wpos) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM record at the end of the file");
+      r->records_done = true;
+      continue;
+    }
+    const size_t bs = le32(r->win.data() + r->wpos);
+    if (bs < 32) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", bs);
+    rc = ensure_bytes(r, 4 + bs);
+    if (rc < 0) return rc;
+    if (rc == 0) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM record at the end of the file");
+    const uint8_t* p = r->win.data() + r->wpos + 4;
+    r->wpos += 4 + bs;
+    r->all_alignments++;
+    const int32_t tid = (int32_t)le32(p);
+    const size_t l_name = p[8];
+    const uint32_t flag = le16(p + 14);
+    const int32_t ntid = (int32_t)le32(p + 20), npos = (int32_t)le32(p + 24);
+    if (32 + l_name > bs || l_name == 0) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with a bad read-name length");
+    // bam_utils.py:264-270
+    if (flag & 0x4) continue;
+    if ((flag & 0x1) && ((flag & 0x80) || !(flag & 0x2) || tid != ntid || npos < 0)) continue;
+    const char* qname = (const char*)p + 32;
+    const size_t qlen = l_name - 1;  // the stored name without its terminating NUL
+    const size_t tlen = trimmed_len(qname, qlen);
+    if (tid < 0 || tid >= n_ref) return fail(r, BAMCOLS_ERR_TID, "alignment with reference id %d outside the header's %d references", tid, n_ref);
+
+    bool sw;
+    if (!cells) {
+      // bam_utils.py:301-306
+      sw = !r->started || r->current.size() != tlen || memcmp(r->current.data(), qname, tlen) != 0;
+      if (sw) r->current.assign(qname, tlen);
+    } else {
+      // bam_utils_multisample.py:258-300 (see alntools_b200/emitter.py:emit_multisample)
+      const char* cf;
+      size_t cl;
+      if (!r->started) {
+        r->current.assign(qname, tlen);
+        if (!cell_field(r->current, &cf, &cl)) return fail(r, BAMCOLS_ERR_CELL_FIELD, "list index out of range");
+        r->cell = cells->id_of(cf, cl);
+      } else if (r->pending) {
+        if (!cell_field(r->current, &cf, &cl)) return fail(r, BAMCOLS_ERR_CELL_FIELD, "list index out of range");
+        r->cell = cells->id_of(cf, cl);
+        r->cur.cell.back() = r->cell;  // the row that opened the read (always the last one written)
+        r->pending = false;
+      }
+      sw = r->started && (r->current.size() != tlen || memcmp(r->current.data(), qname, tlen) != 0);
+      if (sw) {
+        r->current.assign(qname, qlen);  // :292 keeps the untrimmed name
+        r->pending = true;
+        r->cell = 0;
+      }
+      if (!r->started) sw = true;  // opens read 0 (no pending cell: it was resolved above)
+    }
+    if (sw) {
+      if (r->started) std::swap(r->cur, r->ready);  // the previous read is complete
+      r->cur.clear();
+      r->started = true;
+      r->group++;
+      r->cur.group = (int32_t)r->group;
+    }
+    r->cur.tg.push_back(r->tid_target[tid]);
+    r->cur.hp.push_back(r->tid_hap[tid]);
+    if (cells) r->cur.cell.push_back(r->cell);
+  }
+}
+
+}  // extern "C"

@@ -102,6 +102,60 @@ def emit_multisample(records, tables, cell_ids):
                    cells, total, group + 1)
 
 
+def use_python_emitter():
+    """ALNTOOLS_B200_EMITTER=python selects the record-level Python emitter above (slow; kept as the
+    readable statement of the rules and as a cross-check); the default is the native one (bamcols)."""
+    import os
+    return os.environ.get("ALNTOOLS_B200_EMITTER", "native").lower() == "python"
+
+
+def _column_buffers(rows, with_cells, pinned):
+    n = 4 if with_cells else 3
+    if pinned:
+        import torch
+        return [torch.empty(rows, dtype=torch.int32).pin_memory() for _ in range(n)]
+    return [np.empty(rows, dtype=np.int32) for _ in range(n)]
+
+
+def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
+    """Decode `reader` (bamcols.BamColumnReader, tables set) on a worker thread into a small ring of
+    pinned buffers and push every filled buffer to the GPU while the next one is being decoded.
+    Chunks end on read boundaries (bamcols_emit never splits a read), order_base = rows pushed so far,
+    so the result equals one push of the whole file.  Returns the number of valid alignments."""
+    import queue
+    import threading
+    free, full = queue.Queue(), queue.Queue()
+    for _ in range(depth):
+        free.put(_column_buffers(chunk_rows, False, pinned))
+
+    def produce():
+        try:
+            while True:
+                bufs = free.get()
+                n, done = reader.emit(bufs[0], bufs[1], bufs[2])
+                full.put((bufs, n, done, None))
+                if done:
+                    return
+        except BaseException as exc:                      # re-raised by the consumer
+            full.put((None, 0, True, exc))
+
+    worker = threading.Thread(target=produce, daemon=True)
+    worker.start()
+    pushed = 0
+    while True:
+        bufs, n, done, exc = full.get()
+        if exc is not None:
+            raise exc
+        if n:
+            builder.push(bufs[0], bufs[1], bufs[2], order_base=pushed, n=n)
+            pushed += n
+        free.put(bufs)
+        if done:
+            break
+    worker.join()
+    return pushed
+
+
 def read_bam(filename):
     """(BamHeader, record iterator) using the built-in reader."""
     raw = bam_io.inflate_file(filename)

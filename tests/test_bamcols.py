@@ -1,0 +1,202 @@
+"""libbamcols.so (native host column emitter, include/bamcols.h) against the record-level Python
+statement of the same rules (alntools_b200/emitter.py), on the reference's golden BAMs and on
+generated BAMs that exercise the filters, the name trimming, the per-cell quirks, records that
+straddle BGZF blocks and reads that straddle emit() calls.  No GPU involved."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, load_records
+from alntools_b200 import bam_io, bamcols, emitter
+from alntools_b200.header import TargetTables
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(built):
+    bamcols.load_library()
+
+
+def _native_single(path, tables=None, chunk=1 << 20, n_threads=0):
+    with bamcols.BamColumnReader(path, n_threads) as r:
+        t = tables or TargetTables(r.references, r.lengths, None)
+        r.set_tables(t)
+        cols = r.read_all(chunk=chunk)
+        return cols, r.all_alignments, r.n_groups, r.references, r.lengths
+
+
+def _python_single(path, tables=None):
+    header, recs = load_records(path)
+    t = tables or TargetTables(header.references, header.lengths, None)
+    return emitter.emit_single(recs, t), header
+
+
+def _same_single(path, **kw):
+    cols, all_aln, n_groups, refs, lens = _native_single(path, **kw)
+    want, header = _python_single(path)
+    assert refs == tuple(header.references) and lens == tuple(header.lengths)
+    assert np.array_equal(cols["read_group"], want.read_group)
+    assert np.array_equal(cols["target_idx"], want.target_idx)
+    assert np.array_equal(cols["hap_idx"], want.hap_idx)
+    assert all_aln == want.all_alignments and n_groups == want.n_groups
+    return cols
+
+
+@pytest.mark.parametrize("case", golden_cases("single"), ids=lambda c: c["name"])
+def test_golden_single(case):
+    _same_single(os.path.join(GOLDEN, case["bam"]))
+    _same_single(os.path.join(GOLDEN, case["bam"]), n_threads=1)
+
+
+@pytest.mark.parametrize("case", golden_cases("multisample"), ids=lambda c: c["name"])
+def test_golden_multisample(case):
+    tables, cell_ids = None, {}
+    cells = bamcols.CellDictionary()
+    for fn in case["file_order"]:
+        path = os.path.join(GOLDEN, case["dir"], fn)
+        header, recs = load_records(path)
+        if tables is None:
+            tables = TargetTables(header.references, header.lengths, None)
+        want = emitter.emit_multisample(recs, tables, cell_ids)
+        with bamcols.BamColumnReader(path) as r:
+            r.set_tables(tables)
+            got = r.read_all(cells=cells)
+        for k, w in (("read_group", want.read_group), ("target_idx", want.target_idx),
+                     ("hap_idx", want.hap_idx), ("cell_idx", want.cell_idx)):
+            assert np.array_equal(got[k], w), (fn, k)
+    assert cells.names() == [n for n, _ in sorted(cell_ids.items(), key=lambda kv: kv[1])]
+
+
+REFS = [("T%d_%s" % (t, h), 100 + t) for t in range(6) for h in "AB"]
+
+
+def _write(tmp_path, alignments, name="x.bam", block_payload=60000):
+    p = str(tmp_path / name)
+    bam_io.write_bam(p, REFS, alignments, block_payload=block_payload)
+    return p
+
+
+def test_filters_trimming_and_tiny_blocks(tmp_path, monkeypatch):
+    """Unmapped / read2 / improper / mate-elsewhere alignments are skipped, names are cut at the first
+    blank (not at a leading one), and with 70-byte BGZF blocks nearly every record straddles blocks."""
+    rng = np.random.default_rng(5)
+    alns = []
+    for i in range(400):
+        name = ["r%d" % (i // 3), "r%d extra words" % (i // 3), " lead%d" % (i // 2), "q%d x" % i][int(rng.integers(0, 4))]
+        flag = int(rng.choice([0, 16, 4, 1 | 2 | 64, 1 | 2 | 128, 1 | 64, 1 | 2 | 64 | 16]))
+        tid = int(rng.integers(0, len(REFS)))
+        ntid = tid if rng.random() < 0.7 else int(rng.integers(0, len(REFS)))
+        npos = int(rng.choice([-1, 5, 100]))
+        alns.append((name, flag, tid, 7, ntid, npos))
+    for bp in (70, 300, 60000):
+        _same_single(_write(tmp_path, alns, "f%d.bam" % bp, block_payload=bp))
+    # every worker thread gets a handful of records: thread boundaries fall inside reads
+    monkeypatch.setenv("BAMCOLS_GRAIN", "7")
+    for nt in (2, 3, 8):
+        _same_single(_write(tmp_path, alns, "g%d.bam" % nt, block_payload=300), n_threads=nt)
+
+
+def test_reads_are_never_split_between_emit_calls(tmp_path):
+    rng = np.random.default_rng(9)
+    alns = []
+    for read in range(300):
+        for _ in range(int(rng.integers(1, 9))):
+            alns.append(("read%05d" % read, 0, int(rng.integers(0, len(REFS)))))
+    path = _write(tmp_path, alns)
+    want, _ = _python_single(path)
+    with bamcols.BamColumnReader(path) as r:
+        r.set_tables(TargetTables(r.references, r.lengths, None))
+        rg_all = []
+        bufs = [np.empty(11, dtype=np.int32) for _ in range(3)]
+        while True:
+            n, done = r.emit(*bufs)
+            part = bufs[0][:n].copy()
+            if n:
+                assert not rg_all or part[0] != rg_all[-1][-1]       # a new read starts every call
+            if n:
+                rg_all.append(part)
+            if done:
+                break
+        assert np.array_equal(np.concatenate(rg_all), want.read_group)
+    with bamcols.BamColumnReader(path) as r:                       # a read longer than the buffers
+        r.set_tables(TargetTables(r.references, r.lengths, None))
+        small = [np.empty(1, dtype=np.int32) for _ in range(3)]
+        with pytest.raises(ValueError):
+            while not r.emit(*small)[1]:
+                pass
+
+
+def _cell_name(read, cell, extra=""):
+    return "%s|||CR|||x|||CY|||x|||UR|||x|||UY|||x|||BC|||x|||QT|||x|||CID|||%s%s" % (read, cell, extra)
+
+
+def test_per_cell_quirks(tmp_path):
+    """The remembered name stays untrimmed after the first switch (names with blanks open a read per
+    alignment), the cell is taken from the remembered name, ids follow first appearance."""
+    rng = np.random.default_rng(11)
+    alns = []
+    for read in range(200):
+        cell = "CELL%02d" % int(rng.integers(0, 7))
+        extra = " tail" if read % 5 == 0 else ""
+        for _ in range(int(rng.integers(1, 4))):
+            alns.append((_cell_name("q%04d" % read, cell, extra), 0, int(rng.integers(0, len(REFS)))))
+    path = _write(tmp_path, alns, block_payload=500)
+    header, recs = load_records(path)
+    tables = TargetTables(header.references, header.lengths, None)
+    cell_ids = {}
+    want = emitter.emit_multisample(recs, tables, cell_ids)
+    cells = bamcols.CellDictionary()
+    with bamcols.BamColumnReader(path) as r:
+        r.set_tables(tables)
+        got = r.read_all(cells=cells, chunk=64)
+    assert np.array_equal(got["read_group"], want.read_group)
+    assert np.array_equal(got["cell_idx"], want.cell_idx)
+    assert np.array_equal(got["target_idx"], want.target_idx)
+    assert cells.names() == [n for n, _ in sorted(cell_ids.items(), key=lambda kv: kv[1])]
+
+
+def test_per_cell_short_name_raises_index_error_like_the_reference(tmp_path):
+    alns = [(_cell_name("a", "C1"), 0, 0), ("only|||three|||fields", 0, 1), (_cell_name("b", "C2"), 0, 2)]
+    path = _write(tmp_path, alns)
+    header, recs = load_records(path)
+    tables = TargetTables(header.references, header.lengths, None)
+    with pytest.raises(IndexError):
+        emitter.emit_multisample(recs, tables, {})
+    with bamcols.BamColumnReader(path) as r:
+        r.set_tables(tables)
+        with pytest.raises(IndexError):
+            r.read_all(cells=bamcols.CellDictionary())
+
+
+def test_not_a_bam_and_missing_file(tmp_path):
+    p = tmp_path / "junk.bam"
+    p.write_bytes(b"this is not a bam file at all")
+    with pytest.raises(ValueError):
+        bamcols.BamColumnReader(str(p))
+    with pytest.raises(IOError):
+        bamcols.BamColumnReader(str(tmp_path / "absent.bam"))
+    good = _write(tmp_path, [("r", 0, 0)])
+    data = open(good, "rb").read()
+    cut = tmp_path / "cut.bam"
+    cut.write_bytes(data[:len(data) - 40])                          # EOF block and part of the last block gone
+    with pytest.raises(ValueError):
+        with bamcols.BamColumnReader(str(cut)) as r:
+            r.set_tables(TargetTables(r.references, r.lengths, None))
+            r.read_all()
+
+
+def test_large_synthetic_multi_batch(tmp_path):
+    """More than one inflate batch (> 2048 blocks) and all worker threads."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(120000, 300, 2, seed=3, mode="diploid")
+    path = str(tmp_path / "big.bam")
+    bam_io.write_bam_columns(path, synth.reference_names(300, 2), cols["read_group"],
+                             np.zeros(len(cols["read_group"]), dtype=np.uint16),
+                             cols["target_idx"].astype(np.int64) * 2 + cols["hap_idx"], block_payload=4000)
+    with bamcols.BamColumnReader(path) as r:
+        tables = TargetTables(r.references, r.lengths, None)
+        r.set_tables(tables)
+        got = r.read_all(chunk=1 << 16)
+    assert np.array_equal(got["read_group"], cols["read_group"])
+    assert np.array_equal(got["target_idx"], cols["target_idx"])
+    assert np.array_equal(got["hap_idx"], cols["hap_idx"])
