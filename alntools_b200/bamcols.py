@@ -21,6 +21,8 @@ SIGNATURES = {
     "bamcols_n_references": (ctypes.c_int, [ctypes.c_void_p]),
     "bamcols_reference_name": (ctypes.c_char_p, [ctypes.c_void_p, ctypes.c_int]),
     "bamcols_reference_length": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_reference_blob": (ctypes.c_int64, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_set_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "bamcols_cells_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_cells_destroy": (None, [ctypes.c_void_p]),
@@ -98,8 +100,10 @@ class BamColumnReader(object):
             _raise(rc, self._lib.bamcols_last_error(None).decode())
         self._h = h
         n = self._lib.bamcols_n_references(h)
-        self.references = tuple(self._lib.bamcols_reference_name(h, i).decode() for i in range(n))
-        self.lengths = tuple(self._lib.bamcols_reference_length(h, i) for i in range(n))
+        names, lens = ctypes.c_void_p(), ctypes.c_void_p()
+        nbytes = self._lib.bamcols_reference_blob(h, ctypes.byref(names), ctypes.byref(lens))
+        self.references = tuple(ctypes.string_at(names, nbytes).decode().split("\0")[:n]) if n else ()
+        self.lengths = tuple((ctypes.c_int32 * n).from_address(lens.value)) if n else ()
 
     def set_tables(self, tables):
         tt = np.ascontiguousarray(tables.tid_target, dtype=np.int32)

@@ -17,6 +17,34 @@ def _i32(arr):
     return np.ascontiguousarray(arr, dtype="<i4").tobytes()
 
 
+def _target_section(target_names, lengths, n_haps):
+    """T x [len(name), name bytes, H x length] (bin_utils.py:153-159).  ASCII names (every aligner
+    index) are laid out with numpy scatters; anything else takes the per-name loop."""
+    joined = "".join(target_names)
+    n = len(target_names)
+    if n == 0:
+        return b""
+    if not joined.isascii():
+        parts = []
+        for idx, name in enumerate(target_names):
+            parts.append(struct.pack("<i", len(name)))
+            parts.append(name.encode("utf-8"))
+            parts.append(_i32(lengths[idx, :n_haps]))
+        return b"".join(parts)
+    nb = np.fromiter(map(len, target_names), dtype=np.int64, count=n)
+    rec = 4 + nb + 4 * n_haps
+    start = np.cumsum(rec) - rec
+    out = np.empty(int(rec.sum()), dtype=np.uint8)
+    out[start[:, None] + np.arange(4)] = nb.astype("<i4").view(np.uint8).reshape(n, 4)
+    name_first = np.cumsum(nb) - nb
+    out[np.repeat(start + 4 - name_first, nb) + np.arange(int(nb.sum()))] = np.frombuffer(joined.encode("ascii"),
+                                                                                         dtype=np.uint8)
+    if n_haps:
+        lens = np.ascontiguousarray(lengths[:, :n_haps], dtype="<i4").view(np.uint8).reshape(n, 4 * n_haps)
+        out[(start + 4 + nb)[:, None] + np.arange(4 * n_haps)] = lens
+    return out.tobytes()
+
+
 def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names, a_csr, n_csc):
     """a_csr / n_csc: (indptr, indices, data) int32 arrays."""
     with open(ec_filename, "wb") as fh:
@@ -27,12 +55,7 @@ def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names,
             fh.write(hap.encode("utf-8"))
         lengths = np.asarray(lengths).astype(int)
         fh.write(struct.pack("<i", len(target_names)))
-        parts = []
-        for idx, name in enumerate(target_names):
-            parts.append(struct.pack("<i", len(name)))
-            parts.append(name.encode("utf-8"))
-            parts.append(_i32(lengths[idx, :len(haplotypes)]))
-        fh.write(b"".join(parts))
+        fh.write(_target_section(target_names, lengths, len(haplotypes)))
         fh.write(struct.pack("<i", len(sample_names)))
         parts = []
         for sample in sample_names:

@@ -76,6 +76,7 @@ struct bamcols {
   // header
   std::vector<std::string> ref_names;
   std::vector<int32_t> ref_lengths;
+  std::string ref_blob;          // every reference name followed by a NUL, in tid order
   std::vector<int32_t> tid_target, tid_hap;
   // grouping state (persists across emit calls)
   bool started = false;          // a valid alignment has been seen
@@ -248,6 +249,8 @@ int read_header(bamcols* r) {
     if (rc <= 0) return rc < 0 ? rc : fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM reference list");
     const uint8_t* p = r->win.data() + r->wpos;
     r->ref_names.emplace_back((const char*)p + 4, l_name ? l_name - 1 : 0);
+    r->ref_blob.append(r->ref_names.back());
+    r->ref_blob.push_back('\0');
     r->ref_lengths.push_back((int32_t)le32(p + 4 + l_name));
     r->wpos += 8 + l_name;
   }
@@ -544,6 +547,13 @@ int bamcols_n_references(const bamcols* r) { return r ? (int)r->ref_names.size()
 const char* bamcols_reference_name(const bamcols* r, int tid) {
   if (!r || tid < 0 || (size_t)tid >= r->ref_names.size()) return nullptr;
   return r->ref_names[tid].c_str();
+}
+
+int64_t bamcols_reference_blob(const bamcols* r, const char** names, const int32_t** lengths) {
+  if (!r || !names || !lengths) return BAMCOLS_ERR_INVALID;
+  *names = r->ref_blob.data();
+  *lengths = r->ref_lengths.data();
+  return (int64_t)r->ref_blob.size();
 }
 
 int bamcols_reference_length(const bamcols* r, int tid) {

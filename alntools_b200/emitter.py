@@ -113,7 +113,7 @@ def _column_buffers(rows, with_cells, pinned):
     n = 4 if with_cells else 3
     if pinned:
         import torch
-        return [torch.empty(rows, dtype=torch.int32).pin_memory() for _ in range(n)]
+        return [torch.empty(rows, dtype=torch.int32, pin_memory=True) for _ in range(n)]
     return [np.empty(rows, dtype=np.int32) for _ in range(n)]
 
 
@@ -125,13 +125,22 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
     import queue
     import threading
     free, full = queue.Queue(), queue.Queue()
-    for _ in range(depth):
-        free.put(_column_buffers(chunk_rows, False, pinned))
+    allocated = [0]
+
+    def next_buffers():
+        """A free buffer set; a new one is pinned only when all existing ones are in flight."""
+        try:
+            return free.get_nowait()
+        except queue.Empty:
+            if allocated[0] < depth:
+                allocated[0] += 1
+                return _column_buffers(chunk_rows, False, pinned)
+            return free.get()
 
     def produce():
         try:
             while True:
-                bufs = free.get()
+                bufs = next_buffers()
                 n, done = reader.emit(bufs[0], bufs[1], bufs[2])
                 full.put((bufs, n, done, None))
                 if done:

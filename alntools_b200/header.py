@@ -24,36 +24,33 @@ class TargetTables(object):
             if len(main_targets) == 0:
                 LOG.error("Unable to parse target file")
                 sys.exit(-1)
-        pieces = []
-        haplotypes = set()
-        for name in references:                               # :582-600
-            i = name.rfind("_")
-            target, hap = (name[:i], name[i + 1:]) if i > 0 else (name, "")
-            pieces.append((target, hap))
-            haplotypes.add(hap)
+        refs = list(references)
+        cut = [name.rfind("_") for name in refs]              # :584-591: split at the LAST '_' unless it leads
+        targets = [name[:i] if i > 0 else name for name, i in zip(refs, cut)]
+        haps = [name[i + 1:] if i > 0 else "" for name, i in zip(refs, cut)]
+        for target in dict.fromkeys(targets):                 # :596-598: unseen targets in header order
             if target not in main_targets:
                 main_targets[target] = len(main_targets)
         self.main_targets = main_targets
-        self.haplotypes = sorted(haplotypes)                  # :602 ('' sorts first)
+        self.haplotypes = sorted(set(haps))                   # :602 ('' sorts first)
         hap_idx = {h: i for i, h in enumerate(self.haplotypes)}
-        n = len(references)
-        self.lengths = np.zeros((len(main_targets), len(self.haplotypes)), dtype=np.int32)  # :605
-        self.tid_target = np.empty(n, dtype=np.int32)
-        self.tid_hap = np.empty(n, dtype=np.int32)
-        for tid, (target, hap) in enumerate(pieces):          # :615-633
-            t, h = main_targets[target], hap_idx[hap]
-            self.lengths[t, h] = ref_lengths[tid]
-            self.tid_target[tid] = t
-            self.tid_hap[tid] = h
+        n = len(refs)
+        self.tid_target = np.fromiter(map(main_targets.__getitem__, targets), dtype=np.int32, count=n)
+        self.tid_hap = np.fromiter(map(hap_idx.__getitem__, haps), dtype=np.int32, count=n)
         # The reference rebuilds '<target>_<hap>' and looks the name up again (bam_utils.py:800-811);
         # that only differs from the direct tid -> (target, hap) map when two @SQ names collapse to the
         # same pair (e.g. 'a' and 'a_'), which no aligner index produces.  Refuse instead of guessing.
-        seen = {}
-        for tid, pair in enumerate(pieces):
-            if pair in seen:
-                raise ValueError("@SQ names %r and %r map to the same (target, haplotype)"
-                                 % (references[seen[pair]], references[tid]))
-            seen[pair] = tid
+        pair = self.tid_target.astype(np.int64) * len(self.haplotypes) + self.tid_hap
+        ordered = np.sort(pair)
+        if n > 1 and bool((ordered[1:] == ordered[:-1]).any()):
+            seen = {}
+            for tid, key in enumerate(pair.tolist()):
+                if key in seen:
+                    raise ValueError("@SQ names %r and %r map to the same (target, haplotype)"
+                                     % (refs[seen[key]], refs[tid]))
+                seen[key] = tid
+        self.lengths = np.zeros((len(main_targets), len(self.haplotypes)), dtype=np.int32)  # :605
+        self.lengths[self.tid_target, self.tid_hap] = np.asarray(ref_lengths, dtype=np.int32)  # :615-633
 
     @property
     def num_targets(self):

@@ -51,6 +51,9 @@ const char* bamcols_last_error(const bamcols* r); /* r == NULL: error of the las
 int bamcols_n_references(const bamcols* r);
 const char* bamcols_reference_name(const bamcols* r, int tid);
 int bamcols_reference_length(const bamcols* r, int tid);
+/* All names at once: *names = every name followed by a NUL, in tid order; *lengths = int32[n_references];
+ * returns the byte length of *names.  The pointers stay valid until bamcols_close. */
+int64_t bamcols_reference_blob(const bamcols* r, const char** names, const int32_t** lengths);
 
 /* tid -> (main-target index, haplotype index) lookups built by the host from the header
  * (alntools/bam_utils.py:561-633).  Copied. */
