@@ -74,9 +74,10 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
             LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
                                                                 utils.format_time(start_time, time.time())))
             temp_time = time.time()
-            hint = max(1 << 20, os.path.getsize(bam_filename) // 16)
-            with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False, alignments_hint=hint,
-                           device=device) as builder:
+            # no alignment count is known up front: the library sizes its table from the first chunk and
+            # grows it ahead of later ones; one finalize per context, so results skip the pinning cost
+            with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False, alignments_hint=0,
+                           device=device, pageable_results=1) as builder:
                 chunk_rows = int(min(1 << 23, max(1 << 16, os.path.getsize(bam_filename) // 2)))
                 valid = emitter.stream_single(reader, builder, chunk_rows=chunk_rows,
                                               pinned=torch.cuda.is_available())

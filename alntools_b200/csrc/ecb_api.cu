@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,6 +39,7 @@ struct ecb_ctx {
   int64_t opt_table_slots = 0, opt_pair_slots = 0, opt_grid = 0, opt_chunk_len = 0;
   int use_cache = 1;
   int verify_keys = 0;
+  int pageable_results = 0;
   // EC table
   DevBuf table;
   u32 table_slots = 0;
@@ -116,24 +118,24 @@ int fail(ecb_ctx* c, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(c, ECB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
+// Device memory comes from the stream-ordered allocator (cudaMallocAsync on the context's stream):
+// growing a buffer costs no device-wide synchronisation and memory released by one context is
+// reused by the next one in the process (ecb_create raises the pool's release threshold).
 int ensure(ecb_ctx* c, DevBuf& b, size_t bytes, bool preserve = false) {
   if (bytes <= b.bytes) return ECB_OK;
   size_t want = std::max(bytes, b.bytes + b.bytes / 2);
   want = (want + 255) & ~(size_t)255;
   void* np = nullptr;
-  CK(cudaMalloc(&np, want));
+  CK(cudaMallocAsync(&np, want, c->stream));
   if (preserve && b.p && b.bytes) CK(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream));
-  if (b.p) {
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaFree(b.p));
-  }
+  if (b.p) CK(cudaFreeAsync(b.p, c->stream));
   b.p = np;
   b.bytes = want;
   return ECB_OK;
 }
 
-void release(DevBuf& b) {
-  if (b.p) cudaFree(b.p);
+void release(ecb_ctx* c, DevBuf& b) {
+  if (b.p) cudaFreeAsync(b.p, c->stream);
   b.p = nullptr;
   b.bytes = 0;
 }
@@ -203,8 +205,13 @@ int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
   return ECB_OK;
 }
 
-int init_table(ecb_ctx* c) {
-  u64 want = c->opt_table_slots > 0 ? (u64)c->opt_table_slots : std::max<u64>(1u << 16, (u64)c->hint / 8);
+// first_n: alignments of the push that triggers the allocation (0 when unknown).  With a hint the
+// table gets hint/8 slots (ECs are a small fraction of the alignments of a whole job); without one
+// only the first push is known and a job's early part is EC-rich, so first_n/4.
+int init_table(ecb_ctx* c, int64_t first_n = 0) {
+  u64 want = c->opt_table_slots > 0 ? (u64)c->opt_table_slots
+             : c->hint > 0          ? std::max<u64>(1u << 16, (u64)c->hint / 8)
+                                    : std::max<u64>(1u << 16, (u64)first_n / 4);
   c->table_slots = std::max<u32>(1u << 10, pow2_ceil(want));
   CKR(ensure(c, c->table, (size_t)c->table_slots * sizeof(EcbEntry)));
   CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
@@ -232,7 +239,7 @@ int rebuild_triple_table(ecb_ctx* c, u32 new_slots, const u32* remap) {
       (const EcbEntry*)c->ttable.p, c->ttable_slots, (EcbEntry*)nt.p, new_slots - 1, remap);
   LAUNCH_CHECK("triple_remap");
   CK(cudaStreamSynchronize(c->stream));
-  release(c->ttable);
+  release(c, c->ttable);
   c->ttable = nt;
   c->ttable_slots = new_slots;
   return ECB_OK;
@@ -250,13 +257,13 @@ int grow_table(ecb_ctx* c, u32 new_slots) {
       (u32*)remap.p, c->d_ctr);
   LAUNCH_CHECK("rehash");
   CK(cudaStreamSynchronize(c->stream));
-  release(c->table);
+  release(c, c->table);
   c->table = nt;
   c->table_slots = new_slots;
   c->stats.table_grows++;
   if (c->with_cells) {
     CKR(rebuild_triple_table(c, c->ttable_slots, (const u32*)remap.p));
-    release(remap);
+    release(c, remap);
   }
   return ECB_OK;
 }
@@ -505,7 +512,7 @@ void cells_release(ecb_ctx* c) {
   CellScratch& S = c->cells;
   DevBuf* bufs[] = {&S.fe_table, &S.pair_table, &S.cell_key, &S.cell_total, &S.cell_new, &S.sort_k[0], &S.sort_k[1],
                     &S.sort_v[0], &S.sort_v[1], &S.hist, &S.flags, &S.offsets};
-  for (DevBuf* b : bufs) release(*b);
+  for (DevBuf* b : bufs) release(c, *b);
 }
 
 }  // namespace
@@ -544,6 +551,14 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
     return code;
   };
   if (cudaSetDevice(device) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaSetDevice failed"); return bail(ECB_ERR_CUDA); }
+  {
+    // keep released device memory in the pool instead of handing it back to the driver on every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaStreamCreate failed"); return bail(ECB_ERR_CUDA); }
   c->stream = c->own_stream;
   for (auto& e : c->ev)
@@ -570,6 +585,9 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
+    case ECB_OPT_PAGEABLE_RESULTS:
+      if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
+      c->pageable_results = value ? 1 : 0; break;
     default: return fail(c, ECB_ERR_INVALID, "unknown option %d", option);
   }
   return ECB_OK;
@@ -592,7 +610,7 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
   if (c->with_cells && n > 0 && !cell_idx) return fail(c, ECB_ERR_INVALID, "context has cells but cell_idx is NULL");
   if (!c->with_cells && cell_idx) return fail(c, ECB_ERR_INVALID, "cell_idx given but context was created without cells");
   CK(cudaSetDevice(c->device));
-  if (!c->table_slots) CKR(init_table(c));
+  if (!c->table_slots) CKR(init_table(c, n));
   const u32 push_id = c->push_count++;
   if (n == 0) return ECB_OK;
 
@@ -618,8 +636,14 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
     if (!on_device) c->stats.h2d_bytes += (int64_t)col_bytes * (cell ? 4 : 3);
   }
 
-  // capacity: keep the EC table at most half full before the push starts
+  // capacity: at most half full before the push starts, and - going by the ECs per alignment seen so
+  // far - at most about 60 % full after it (a growth in the middle of a push costs a replay)
   while ((u64)c->n_ec * 2 > c->table_slots) CKR(grow_table(c, c->table_slots * 2));
+  if (c->n_alignments > 0 && !c->opt_table_slots) {
+    const double rate = (double)c->n_ec / (double)c->n_alignments;
+    const u64 projected = (u64)c->n_ec + (u64)(rate * (double)n);
+    if (projected * 5 > (u64)c->table_slots * 3 && c->table_slots < (1u << 31)) CKR(grow_table(c, pow2_ceil(projected * 2)));
+  }
   if (c->with_cells) {
     // the triple table must be able to absorb one new entry per alignment without filling up
     u64 need = ((u64)c->n_triples + (u64)n) * 2;
@@ -669,7 +693,7 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
     CKR(sync_counters(c));
     CKR(check_device_error(c));
   }
-  release(spill_in);
+  release(c, spill_in);
   if (c->h_ctr->n_triple_overflow) return fail(c, ECB_ERR_LIMIT, "(file, EC, cell) table ran out of probes");
   c->n_ec = c->h_ctr->n_ec;
   c->n_triples = c->h_ctr->n_triples;
@@ -806,10 +830,17 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
     size_t total = 0, offs[7];
     for (int i = 0; i < 7; ++i) { offs[i] = total; total += (sizes[i] + 63) & ~(size_t)63; }
     if (total > c->h_res_bytes) {
-      if (c->h_res) CK(cudaFreeHost(c->h_res));
+      if (c->h_res) {
+        if (c->pageable_results) free(c->h_res); else CK(cudaFreeHost(c->h_res));
+      }
       c->h_res = nullptr;
       c->h_res_bytes = 0;
-      CK(cudaMallocHost(&c->h_res, total + total / 4));
+      if (c->pageable_results) {
+        c->h_res = malloc(total + total / 4);
+        if (!c->h_res) return fail(c, ECB_ERR_CUDA, "out of host memory for %zu result bytes", total);
+      } else {
+        CK(cudaMallocHost(&c->h_res, total + total / 4));
+      }
       c->h_res_bytes = total + total / 4;
     }
     char* base = (char*)c->h_res;
@@ -1076,11 +1107,14 @@ int ecb_destroy(ecb_ctx* c) {
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,
                     &c->r_n_data, &c->r_cell_order, &c->x_meta, &c->x_rows, &c->x_counts, &c->x_base};
-  for (DevBuf* b : bufs) release(*b);
+  for (DevBuf* b : bufs) release(c, *b);
   cells_release(c);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
-  if (c->h_res) cudaFreeHost(c->h_res);
+  if (c->h_res) {
+    if (c->pageable_results) free(c->h_res); else cudaFreeHost(c->h_res);
+  }
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);

@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_diploid_30M", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--bam-sample-reads", type=int, default=8_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--grid-ctas", type=int, default=0)
@@ -380,7 +381,7 @@ def main():
     if note_e2e:
         line["e2e"]["remeasured"] = note_e2e
     if world == 1 and not args.no_cpu_baseline:
-        line["bam_e2e"] = run_bam_e2e(args.workload, args.cpu_sample_reads, local_rank)
+        line["bam_e2e"] = run_bam_e2e(args.workload, args.bam_sample_reads, local_rank)
         line["cpu_baseline"] = run_cpu_arm(args.workload, 2, 0, args.cpu_sample_reads, max_seconds=60.0)
     print(json.dumps(line))
     if world > 1:
