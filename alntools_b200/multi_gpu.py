@@ -30,6 +30,11 @@ def distributed_finalize(local, make_owner, device, group=None):
     Returns dict(a_indptr, a_indices, a_data, n_data, n_ec, nnz_a) of int32 tensors on `device`,
     identical on every rank."""
     world = dist.get_world_size(group)
+    # library kernels and torch's collectives must be ordered against each other: both builders work
+    # on torch's current stream from here on (NCCL orders itself against that stream)
+    cur = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else None
+    if cur is not None:
+        local.set_stream(cur)
     meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
 
     # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
@@ -41,6 +46,8 @@ def distributed_finalize(local, make_owner, device, group=None):
     dist.all_to_all_single(rows_in, rows, output_split_sizes=recv_rows, input_split_sizes=row_counts, group=group)
 
     owner = make_owner()
+    if cur is not None:
+        owner.set_stream(cur)
     owner.import_entries(meta_in, rows_in, recv_ec, recv_rows)
 
     # ---- global EC ids from the OR-ed first-occurrence bitmap ------------------------------------

@@ -223,7 +223,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     config = {"workload": args.workload, "reads_per_gpu": wl["n_reads"], "n_targets": wl["n_targets"],
-              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU",
+              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU; N > 1: + all-to-all of hash-partitioned local ECs, owner merge, "
+                                                              "global ids and CSR on every rank",
               "l2": "inputs (>= 700 MB per GPU) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -319,28 +320,64 @@ def main():
                 ms, group_ms, per_step = ms2, group_ms2, per_step2
         return ms, res, group_ms, note
 
+    # With several GPUs a step also runs the exchange: local ECs hash-partitioned to their owner rank
+    # (NCCL all-to-all), owner-side merge, global EC ids and the final CSR on every rank
+    # (alntools_b200/multi_gpu.py).  The owner context is reused from step to step like the local one.
+    owner = None
+    if world > 1:
+        from alntools_b200 import multi_gpu
+        owner = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank, **opts)
+        owner.set_stream(stream.cuda_stream)
+        dev_t = torch.device("cuda", local_rank)
+
+    class _Res(object):
+        def __init__(self, d):
+            self.n_ec, self.nnz_a = d["n_ec"], d["nnz_a"]
+
+    def fin_device(b):
+        if world == 1:
+            return b.finalize_raw()
+        owner.reset()
+        return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t))
+
+    def fin_host(b):
+        if world == 1:
+            return b.finalize_raw()
+        owner.reset()
+        out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t)
+        if rank == 0:   # the job's result leaves the device once, on rank 0
+            for k in ("a_indptr", "a_indices", "a_data", "n_data"):
+                out[k + "_host"] = out[k].cpu()
+        return _Res(out)
+
     # ---- device-resident arm ("value") --------------------------------------------------------------
     b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
                       result_on_device=1, **opts)
     b_dev.set_stream(stream.cuda_stream)
-    timed_once(b_dev, dev, args.warmup, lambda b: b.finalize_raw())
-    launches0 = b_dev.stats()["kernel_launches"]
+    timed_once(b_dev, dev, args.warmup, fin_device)
     with ClockSampler(local_rank) as clocks:
-        ms_dev, res_dev, group_ms, note_dev = timed(b_dev, dev, args.steps, lambda b: b.finalize_raw())
+        ms_dev, res_dev, group_ms, note_dev = timed(b_dev, dev, args.steps, fin_device)
     stats_dev = b_dev.stats()
     launches_per_step = stats_dev["kernel_launches"]  # stats are zeroed by reset(): this is the last step
+    if owner is not None:
+        launches_per_step += owner.stats()["kernel_launches"]
     n_ec, nnz_a = int(res_dev.n_ec), int(res_dev.nnz_a)
     b_dev.close()
-    del launches0
 
     # ---- end-to-end arm: host columns in, host matrices out ----------------------------------------
-    b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank, **opts)
+    b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
+                      result_on_device=1 if world > 1 else 0, **opts)
     b_e2e.set_stream(stream.cuda_stream)
-    timed_once(b_e2e, host, args.warmup, lambda b: b.finalize_raw())
-    ms_e2e, res_e2e, _, note_e2e = timed(b_e2e, host, args.steps, lambda b: b.finalize_raw())
+    timed_once(b_e2e, host, args.warmup, fin_host)
+    ms_e2e, res_e2e, _, note_e2e = timed(b_e2e, host, args.steps, fin_host)
     stats_e2e = b_e2e.stats()
     assert int(res_e2e.n_ec) == n_ec
+    d2h_e2e = stats_e2e["d2h_bytes"]
+    if world > 1:
+        d2h_e2e += 4 * (n_ec + 1) + 8 * nnz_a + 4 * n_ec   # rank 0's copy of the global result
     b_e2e.close()
+    if owner is not None:
+        owner.close()
 
     if rank != 0:
         if world > 1:
@@ -367,7 +404,7 @@ def main():
         "config": dict(config, alignments_per_gpu=n_aln, n_ec=n_ec, nnz_a=nnz_a,
                        table_slots=stats_dev["table_slots"], table_grows=stats_dev["table_grows"]),
         "e2e": {"value": total_aln * args.steps / (ms_e2e * 1e-3), "unit": "alignments/s",
-                "h2d_bytes_per_step": stats_e2e["h2d_bytes"], "d2h_bytes_per_step": stats_e2e["d2h_bytes"],
+                "h2d_bytes_per_step": stats_e2e["h2d_bytes"], "d2h_bytes_per_step": d2h_e2e,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "ecb_group_insert_kernel", "achieved": achieved, "peak": peak,

@@ -289,9 +289,9 @@ def test_multigpu_exchange_matches_oracle(native):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                           "--master-addr", "127.0.0.1", "--master-port", "29533",
                           os.path.join(ROOT, "tests", "multigpu_check.py"), "300000"],
-                         capture_output=True, text=True, timeout=900)
+                         capture_output=True, text=True, timeout=400)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("OK") == 2
+    assert out.stdout.count("OK") == 3
 
 
 def test_exchange_primitives_single_gpu(native):
