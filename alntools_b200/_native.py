@@ -181,6 +181,11 @@ class EcBuilder(object):
             self._result_on_device = bool(value)
 
     def set_stream(self, cuda_stream):
+        """cuda_stream: a cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream), or None for
+        the library's own stream.  torch reports its default stream as handle 0, which the C ABI reads
+        as "own stream"; it is passed as cudaStreamLegacy (0x1), the explicit name of the same stream."""
+        if cuda_stream is not None and int(cuda_stream) == 0:
+            cuda_stream = 1
         self._check(self._lib.ecb_set_stream(self._ctx, cuda_stream))
 
     def push(self, read_group, target_idx, hap_idx, cell_idx=None, order_base=0, drop_last_group=False,
@@ -234,8 +239,10 @@ class EcBuilder(object):
         exp = EcbExport()
         self._check(self._lib.ecb_export_partition(self._ctx, int(world), ctypes.byref(exp)))
         dev = torch.device("cuda", torch.cuda.current_device())
-        meta = _device_view(ctypes.cast(exp.meta, ctypes.c_void_p).value, (exp.n_ec, 5), "<i8", torch.int64, dev)
-        rows = _device_view(ctypes.cast(exp.rows, ctypes.c_void_p).value, (exp.n_rows, 2), "<i4", torch.int32, dev)
+        # copies into torch-owned memory: the collectives then only ever see torch allocations, and the
+        # library is free to reuse its export buffers
+        meta = _device_view(ctypes.cast(exp.meta, ctypes.c_void_p).value, (exp.n_ec, 5), "<i8", torch.int64, dev).clone()
+        rows = _device_view(ctypes.cast(exp.rows, ctypes.c_void_p).value, (exp.n_rows, 2), "<i4", torch.int32, dev).clone()
         ec_counts = [int(exp.part_ec_counts[i]) for i in range(world)]
         row_counts = [int(exp.part_row_counts[i]) for i in range(world)]
         return meta, rows, ec_counts, row_counts, int(exp.min_base), int(exp.max_end)

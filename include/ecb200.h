@@ -107,7 +107,8 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
 int ecb_set_option(ecb_ctx* ctx, int option, int64_t value);
 
 /* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*),
- * e.g. torch.cuda.current_stream().cuda_stream.  NULL restores the context's own stream. */
+ * e.g. torch.cuda.current_stream().cuda_stream.  NULL restores the context's own stream; the legacy
+ * default stream must be named explicitly (cudaStreamLegacy), because its plain handle is NULL too. */
 int ecb_set_stream(ecb_ctx* ctx, void* cuda_stream);
 
 /*
