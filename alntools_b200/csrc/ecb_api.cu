@@ -1001,7 +1001,7 @@ int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* ro
     CKR(device_scan<false>(c, (const u32*)c->row_len.p + e0, (u32*)c->row_off.p + e0, e1 - e0, (u32)c->arena_used, &total));
     if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
     CKR(ensure(c, c->arena, std::max<u64>(c->arena_used + total, 1) * sizeof(uint2), true));
-    ecb_import_rows_kernel<<<grid_for((u64)(e1 - e0) * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+    ecb_import_rows_kernel<<<grid_for(e1 - e0, 256, c->sm_count * 16), 256, 0, c->stream>>>(
         (const long long*)meta_device, (const int2*)rows_device, parts, (const u32*)c->ec_rep.p,
         (const u32*)c->row_len.p, (const u32*)c->row_off.p, (uint2*)c->arena.p, e0, e1);
     LAUNCH_CHECK("import_rows");

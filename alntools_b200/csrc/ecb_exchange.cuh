@@ -33,31 +33,60 @@ struct ExportParams {
   int2* rows;
 };
 
+// Both export kernels aggregate per CTA in shared memory: a plain atomicAdd per EC on the `world`
+// owner counters would serialise millions of operations on a handful of addresses.
 __global__ void __launch_bounds__(256) ecb_export_count_kernel(const ExportParams P) {
+  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];
+  for (u32 i = threadIdx.x; i < 2 * P.world; i += blockDim.x) s_cnt[i] = 0u;
+  __syncthreads();
   for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
     const EcbEntry* en = P.table + P.ec_slot[e];
     const u32 owner = ecb_owner_of(Key128{en->key_lo, en->key_hi}, P.world);
-    atomicAdd(&P.counts[owner], 1u);
-    atomicAdd(&P.counts[P.world + owner], P.row_len[e]);
+    atomicAdd(&s_cnt[owner], 1u);
+    atomicAdd(&s_cnt[P.world + owner], P.row_len[e]);
   }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < 2 * P.world; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&P.counts[i], s_cnt[i]);
 }
 
 __global__ void __launch_bounds__(256) ecb_export_fill_kernel(const ExportParams P) {
-  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < P.n_ec; e += gridDim.x * blockDim.x) {
-    const EcbEntry en = P.table[P.ec_slot[e]];
-    const u32 owner = ecb_owner_of(Key128{en.key_lo, en.key_hi}, P.world);
-    const u32 len = P.row_len[e];
-    const u32 idx = atomicAdd(&P.counts[owner], 1u);
-    const u32 roff = atomicAdd(&P.counts[P.world + owner], len);
-    long long* m = P.meta + (P.base[owner] + idx) * ECB_META_WORDS;
-    m[0] = (long long)en.key_lo;
-    m[1] = (long long)en.key_hi;
-    m[2] = (long long)en.first;
-    m[3] = (long long)(((u64)(en.countm1 + 1u) << 32) | len);
-    m[4] = (long long)roff;
-    const uint2* src = P.arena + P.row_off[e];
-    int2* dst = P.rows + P.base[P.world + owner] + roff;
-    for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];   // per tile: ECs / rows per owner, then their global bases
+  const u32 tiles = (P.n_ec + blockDim.x - 1) / blockDim.x;
+  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (u32 i = threadIdx.x; i < 2 * P.world; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+    const u32 e = tile * blockDim.x + threadIdx.x;
+    const bool live = e < P.n_ec;
+    EcbEntry en{};
+    u32 owner = 0, len = 0, idx = 0, roff = 0;
+    if (live) {
+      en = P.table[P.ec_slot[e]];
+      owner = ecb_owner_of(Key128{en.key_lo, en.key_hi}, P.world);
+      len = P.row_len[e];
+      idx = atomicAdd(&s_cnt[owner], 1u);
+      roff = atomicAdd(&s_cnt[P.world + owner], len);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < 2 * P.world; i += blockDim.x) {
+      const u32 c = s_cnt[i];
+      s_cnt[i] = c ? atomicAdd(&P.counts[i], c) : 0u;
+    }
+    __syncthreads();
+    if (live) {
+      idx += s_cnt[owner];
+      roff += s_cnt[P.world + owner];
+      long long* m = P.meta + (P.base[owner] + idx) * ECB_META_WORDS;
+      m[0] = (long long)en.key_lo;
+      m[1] = (long long)en.key_hi;
+      m[2] = (long long)en.first;
+      m[3] = (long long)(((u64)(en.countm1 + 1u) << 32) | len);
+      m[4] = (long long)roff;
+      const uint2* src = P.arena + P.row_off[e];
+      int2* dst = P.rows + P.base[P.world + owner] + roff;
+      for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+    }
+    __syncthreads();
   }
 }
 
@@ -89,8 +118,8 @@ __global__ void __launch_bounds__(256) ecb_import_insert_kernel(const ImportPara
     EcbEntry* e = P.table + slot;
     atomicAdd(&e->countm1, count);
     if (first < seen) atomicMin(&e->first, first);
+    const u32 ecl = alloc_ec_ids(P.ctr, claimed);  // one atomic per warp, not per new EC
     if (claimed) {
-      const u32 ecl = atomicAdd(&P.ctr->n_ec, 1u);
       e->aux = ecl;
       P.ec_slot[ecl] = slot;
       P.ec_rep[ecl] = i;
@@ -105,22 +134,22 @@ struct PartTable {
   u32 n;
 };
 
-// Copy the rows of the ECs created by this import from the receive buffer into the arena.
+// Copy the rows of the ECs created by this import from the receive buffer into the arena.  One
+// thread per EC: rows are a few entries long and the chain record -> offset -> row is all latency, so
+// millions of independent threads beat a warp per EC.
 __global__ void __launch_bounds__(256) ecb_import_rows_kernel(const long long* __restrict__ meta,
                                                               const int2* __restrict__ rows, const PartTable parts,
                                                               const u32* __restrict__ ec_rep,
                                                               const u32* __restrict__ row_len,
                                                               const u32* __restrict__ row_off, uint2* arena, u32 e0,
                                                               u32 e1) {
-  const int lane = threadIdx.x & 31;
-  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 e = e0 + warp_global; e < e1; e += n_warps) {
+  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
     const u32 rec = ec_rep[e];
     u32 part = 0;
     while (part + 1 < parts.n && (long long)rec >= parts.ec_end[part]) ++part;
     const int2* src = rows + parts.row_base[part] + meta[(size_t)rec * ECB_META_WORDS + 4];
     uint2* dst = arena + row_off[e];
-    for (u32 j = lane; j < row_len[e]; j += 32) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
+    const u32 len = row_len[e];
+    for (u32 j = 0; j < len; ++j) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
   }
 }

@@ -14,41 +14,79 @@ torch.distributed is the plumbing (process group, collectives on device tensors)
 step is a libecb200 kernel behind the C ABI.  The same orchestration runs on gloo/CPU in the tests
 with a stand-in for the kernels.
 """
+import os
+import time
+
 import torch
 import torch.distributed as dist
 
+_TIMING = bool(os.environ.get("ECB_MGPU_TIMING"))
+
+
+class _Phases(object):
+    """Per-phase wall clock of distributed_finalize (ECB_MGPU_TIMING=1; synchronises after every phase)."""
+
+    def __init__(self, device):
+        self.device, self.t, self.rows = device, time.perf_counter(), []
+
+    def mark(self, name):
+        if _TIMING:
+            torch.cuda.synchronize(self.device)
+            now = time.perf_counter()
+            self.rows.append((name, 1e3 * (now - self.t)))
+            self.t = now
+
+    def report(self):
+        if _TIMING and dist.get_rank() == 0:
+            print("distributed_finalize: " + ", ".join("%s %.2f ms" % r for r in self.rows), flush=True)
+
 
 def _all_to_all_counts(counts, device, group):
+    """counts: world * k values, k per destination rank -> the world * k values the peers sent here."""
     send = torch.tensor(counts, dtype=torch.int64, device=device)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
     return recv.tolist()
 
 
-def distributed_finalize(local, make_owner, device, group=None):
+def _combine(t, group, result_on):
+    """SUM of arrays with disjoint supports: everywhere, or only where the result is needed."""
+    if result_on == "rank0":
+        dist.reduce(t, dst=dist.get_global_rank(group, 0) if group is not None else 0, op=dist.ReduceOp.SUM,
+                    group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def distributed_finalize(local, make_owner, device, group=None, result_on="all"):
     """local: builder holding this rank's shard; make_owner(): fresh builder for the owner role.
     Returns dict(a_indptr, a_indices, a_data, n_data, n_ec, nnz_a) of int32 tensors on `device`,
-    identical on every rank."""
+    identical on every rank (result_on="all") or complete on rank 0 only (result_on="rank0": the rank
+    that writes the EC file; the other ranks then hold partial a_indices / a_data / n_data)."""
     world = dist.get_world_size(group)
     # library kernels and torch's collectives must be ordered against each other: both builders work
     # on torch's current stream from here on (NCCL orders itself against that stream)
     cur = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else None
     if cur is not None:
         local.set_stream(cur)
+    ph = _Phases(device)
     meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
+    ph.mark("export")
 
     # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
-    recv_ec = _all_to_all_counts(ec_counts, device, group)
-    recv_rows = _all_to_all_counts(row_counts, device, group)
+    both = _all_to_all_counts([v for pair in zip(ec_counts, row_counts) for v in pair], device, group)
+    recv_ec, recv_rows = both[0::2], both[1::2]
     meta_in = torch.empty((sum(recv_ec), 5), dtype=torch.int64, device=device)
     rows_in = torch.empty((sum(recv_rows), 2), dtype=torch.int32, device=device)
     dist.all_to_all_single(meta_in, meta, output_split_sizes=recv_ec, input_split_sizes=ec_counts, group=group)
     dist.all_to_all_single(rows_in, rows, output_split_sizes=recv_rows, input_split_sizes=row_counts, group=group)
 
+    ph.mark("all_to_all")
     owner = make_owner()
     if cur is not None:
         owner.set_stream(cur)
     owner.import_entries(meta_in, rows_in, recv_ec, recv_rows)
+    ph.mark("import")
 
     # ---- global EC ids from the OR-ed first-occurrence bitmap ------------------------------------
     span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
@@ -60,19 +98,24 @@ def distributed_finalize(local, make_owner, device, group=None):
     bitmap = torch.zeros(n_words, dtype=torch.int32, device=device)
     owner.global_mark(g_min, bitmap)
     dist.all_reduce(bitmap, op=dist.ReduceOp.SUM, group=group)   # disjoint bits: SUM == OR
+    ph.mark("bitmap")
     n_ec = owner.global_count(bitmap)
+    ph.mark("count")
 
     lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=device)
     counts = torch.zeros(n_ec, dtype=torch.int32, device=device)
     owner.global_lens(lens, counts)
-    dist.all_reduce(lens, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(lens, op=dist.ReduceOp.SUM, group=group)     # every owner needs the global indptr
+    _combine(counts, group, result_on)
+    ph.mark("lens")
     nnz = owner.global_indptr(lens)                              # lens becomes indptr in place
     indices = torch.zeros(max(nnz, 1), dtype=torch.int32, device=device)
     data = torch.zeros(max(nnz, 1), dtype=torch.int32, device=device)
     owner.global_rows(lens, indices, data)
-    dist.all_reduce(indices, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(data, op=dist.ReduceOp.SUM, group=group)
+    _combine(indices, group, result_on)
+    _combine(data, group, result_on)
+    ph.mark("rows")
+    ph.report()
     return {"a_indptr": lens, "a_indices": indices[:nnz], "a_data": data[:nnz], "n_data": counts,
             "n_ec": n_ec, "nnz_a": nnz}
 

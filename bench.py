@@ -251,6 +251,8 @@ def main():
         raise SystemExit("bench.py needs a B200: there is no CPU path for the EC build")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic shard of this rank (weak scaling: fixed reads per GPU) --------------------------
@@ -330,6 +332,8 @@ def main():
         owner.set_stream(stream.cuda_stream)
         dev_t = torch.device("cuda", local_rank)
 
+    pinned_out = {}
+
     class _Res(object):
         def __init__(self, d):
             self.n_ec, self.nnz_a = d["n_ec"], d["nnz_a"]
@@ -338,16 +342,20 @@ def main():
         if world == 1:
             return b.finalize_raw()
         owner.reset()
-        return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t))
+        return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0"))
 
     def fin_host(b):
         if world == 1:
             return b.finalize_raw()
         owner.reset()
-        out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t)
-        if rank == 0:   # the job's result leaves the device once, on rank 0
+        out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0")
+        if rank == 0:   # the job's result leaves the device once, on rank 0, into pinned memory
             for k in ("a_indptr", "a_indices", "a_data", "n_data"):
-                out[k + "_host"] = out[k].cpu()
+                t = out[k]
+                if k not in pinned_out or pinned_out[k].numel() < t.numel():
+                    pinned_out[k] = torch.empty(int(t.numel() * 1.25) + 1, dtype=t.dtype, pin_memory=True)
+                pinned_out[k][:t.numel()].copy_(t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
         return _Res(out)
 
     # ---- device-resident arm ("value") --------------------------------------------------------------
