@@ -10,11 +10,11 @@ import pytest
 from conftest import ROOT
 
 
-def _declared_symbols():
-    with open(os.path.join(ROOT, "include", "ecb200.h")) as fh:
+def _declared_symbols(header="ecb200.h", prefix="ecb_"):
+    with open(os.path.join(ROOT, "include", header)) as fh:
         text = fh.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(ecb_[a-z_0-9]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(%s[a-z_0-9]+)\s*\(" % prefix, text)))
 
 
 def test_header_declares_the_expected_entry_points():
@@ -30,6 +30,17 @@ def test_library_exports_every_declared_symbol(built):
         assert hasattr(lib, name), "libecb200.so does not export %s" % name
         assert name in _native.SIGNATURES, "no ctypes signature for %s" % name
     assert lib.ecb_version() >= 1000
+
+
+def test_host_emitter_library_exports_every_declared_symbol(built):
+    from alntools_b200 import bamcols
+    lib = bamcols.load_library()
+    syms = _declared_symbols("bamcols.h", "bamcols_")
+    for must in ("bamcols_open", "bamcols_emit", "bamcols_set_tables", "bamcols_close"):
+        assert must in syms
+    for name in syms:
+        assert hasattr(lib, name), "libbamcols.so does not export %s" % name
+        assert name in bamcols.SIGNATURES, "no ctypes signature for %s" % name
 
 
 def test_library_contains_sm100a_code(built):
