@@ -320,6 +320,7 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   if (e1 <= e0) return ECB_OK;
   HarvestParams H{};
   H.rg = rg; H.tg = tg; H.hp = hp; H.n = (int)n;
+  H.n_targets = c->n_targets; H.n_haps = c->n_haps;
   H.ec_rep = (const u32*)c->ec_rep.p;
   H.ec_len = (const u32*)c->ec_len.p;
   H.e0 = e0; H.e1 = e1;

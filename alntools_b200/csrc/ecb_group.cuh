@@ -31,7 +31,16 @@
 
 #define ECB_GWARPS 32                  // warps per CTA of the grouping kernel
 #define ECB_GTHREADS (32 * ECB_GWARPS)
+#ifndef ECB_SHUFFLE_DEDUP
+#define ECB_SHUFFLE_DEDUP 1
+#endif
+#ifndef ECB_ADMIT_SECOND
+#define ECB_ADMIT_SECOND 1             // a key enters the hot-EC cache on its second miss in the CTA
+#endif
+#define ECB_SEEN_WORDS 2048            // 64 Kbit "missed once already" filter per CTA
+#ifndef ECB_CACHE
 #define ECB_CACHE 4096                 // per-CTA hot-EC cache entries
+#endif
 #define ECB_MQ 96                      // per-warp miss queue (entries); 64 are inserted at a time, two per lane
 #define ECB_PF_DIST 256                // L2 prefetch distance of the column stream (alignments)
 
@@ -256,10 +265,48 @@ struct GroupSmem {
   u32 c_cnt[ECB_CACHE];                // reads counted in this entry
   u32 c_first[ECB_CACHE];              // smallest offset (in this push) of a read with this key
   alignas(8) uint2 c_rep[ECB_CACHE];   // offset and length of one read with this key (the installer's)
+  u32 seen[ECB_SEEN_WORDS];            // one bit per key hash: a read with such a key missed before
   // per-warp queues of reads that missed the cache
   alignas(16) uint4 q_key[ECB_GWARPS][ECB_MQ];
   alignas(8) uint2 q_rep[ECB_GWARPS][ECB_MQ];  // offset, length
 };
+
+// Shared-memory accesses of the hot loop through 32-bit shared-window addresses (computed once per
+// thread): generic pointers cost an address-space conversion per access.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(u32 a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(u32 a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ u32 lds32(u32 a) {
+  u32 v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(u32 a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(u32 a, u32 x, u32 y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void reds_add(u32 a, u32 v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void reds_min(u32 a, u32 v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 atoms_or(u32 a, u32 v) {
+  u32 old;
+  asm volatile("atom.shared.or.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ u32 atoms_cas(u32 a, u32 cmp, u32 v) {
+  u32 old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(v) : "memory");
+  return old;
+}
 
 #define ECB_RG_SENTINEL ((int)0x80000000)  // stands for read_group beyond the end of the push
 
@@ -294,17 +341,17 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // Reads that missed the cache go into the HBM table, two per lane (entries qa and qb of the warp's queue).
 template <bool WITH_CELLS>
-__device__ __forceinline__ void insert_misses(const GroupParams& P, const uint4* qk, const uint2* qr, u32 qa, bool hasA,
-                                              u32 qb, bool hasB) {
+__device__ __forceinline__ void insert_misses(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb,
+                                              bool hasB) {
   uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
   uint2 rA = make_uint2(0u, 0u), rB = rA;
   if (hasA) {
-    kA = qk[qa];
-    rA = qr[qa];
+    kA = lds128(qk + qa * 16u);
+    rA = lds64(qr + qa * 8u);
   }
   if (hasB) {
-    kB = qk[qb];
-    rB = qr[qb];
+    kB = lds128(qk + qb * 16u);
+    rB = lds64(qr + qb * 8u);
   }
   u32 slotA, slotB;
   global_upsert2(P, key_of(kA), rA.x, rA.y, hasA, key_of(kB), rB.x, rB.y, hasB, slotA, slotB);
@@ -404,11 +451,14 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       S.c_cnt[i] = 0u;
       S.c_first[i] = 0xFFFFFFFFu;
     }
+    for (int i = tid; i < ECB_SEEN_WORDS; i += ECB_GTHREADS) S.seen[i] = 0u;
   }
   __syncthreads();
 
-  uint4* const qk = S.q_key[warp];
-  uint2* const qr = S.q_rep[warp];
+  const u32 qk = smem_u32(S.q_key[warp]);  // this warp's miss queue (shared-window addresses)
+  const u32 qr = smem_u32(S.q_rep[warp]);
+  const u32 a_key = smem_u32(S.c_key), a_lock = smem_u32(S.c_lock), a_cnt = smem_u32(S.c_cnt);
+  const u32 a_first = smem_u32(S.c_first), a_rep = smem_u32(S.c_rep), a_seen = smem_u32(S.seen);
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
   u32 reads_counted = 0;  // per lane
 
@@ -468,16 +518,44 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         const int st = 31 - __clz(hb & le_mask);       // lane of this alignment's read start
         const bool active = lane < last_head;
         const u32 code = ecb_code(tgv, hpv);
-        if (active && ((u32)tgv >= (u32)P.n_targets || (u32)hpv >= (u32)P.n_haps))
-          atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
-        // an element counts once per read: drop it if a lower lane of the same read has the same code
-        const u32 same = __match_any_sync(ECB_FULL, code);
-        const bool contrib = active && ((same & lt_mask) >> st) == 0u;
+        // (target / haplotype bounds are checked by the harvest kernels: every distinct element of the
+        // input is part of the representative read of some new EC)
+        // an element counts once per read: drop it if a lower lane of the same read has the same code.
+        // Windows whose complete reads have at most 8 alignments (the usual case) compare against the
+        // up to 7 lanes below with shuffles; match_any, which walks the distinct values of the warp one
+        // by one, is kept for windows with longer reads.
+        u32 run = ~hb & ((1u << last_head) - 1u);  // lanes that continue a read
+        const u32 run2 = run & (run >> 1), run4 = run2 & (run2 >> 2);
+        bool dup = false;
+#if ECB_SHUFFLE_DEDUP
+        if ((run4 & (run4 >> 4)) == 0u) {
+          const int reach = lane - st;  // lanes of the same read below this one
+#define ECB_DUP_STEP(D) dup |= (__shfl_up_sync(ECB_FULL, code, D) == code) && reach >= D;
+          if (run) {
+            ECB_DUP_STEP(1)
+            if (run2) {
+              ECB_DUP_STEP(2)
+              ECB_DUP_STEP(3)
+              if (run4) {
+                ECB_DUP_STEP(4)
+                ECB_DUP_STEP(5)
+                ECB_DUP_STEP(6)
+                ECB_DUP_STEP(7)
+              }
+            }
+          }
+#undef ECB_DUP_STEP
+        } else
+#endif
+        {
+          const u32 same = __match_any_sync(ECB_FULL, code);
+          dup = ((same & lt_mask) >> st) != 0u;
+        }
+        const bool contrib = active && !dup;
         Mix4 X = ecb_mix(code);
         if (!contrib) X = mix_zero();
         // segmented inclusive scan over the lanes of each read, with only as many doubling steps as
         // the longest complete read of the window needs (warp-uniform, from the head ballot)
-        u32 run = ~hb & ((1u << last_head) - 1u);  // lanes that continue a read
 #define ECB_SEG_STEP(D)                                \
   {                                                    \
     const u32 va = __shfl_up_sync(ECB_FULL, X.a, D);   \
@@ -490,13 +568,11 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
         if (run) {
           ECB_SEG_STEP(1)
-          run &= run >> 1;
-          if (run) {
+          if (run2) {
             ECB_SEG_STEP(2)
-            run &= run >> 2;
-            if (run) {
+            if (run4) {
               ECB_SEG_STEP(4)
-              run &= run >> 4;
+              run = run4 & (run4 >> 4);
               if (run) {
                 ECB_SEG_STEP(8)
                 run &= run >> 8;
@@ -532,21 +608,29 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       if (ins) ++reads_counted;
       if (use_cache && ins) {
         const u32 cidx = (key.y >> 7) & (ECB_CACHE - 1);
-        const uint4 ck = S.c_key[cidx];
-        const u32 cf = *reinterpret_cast<volatile u32*>(&S.c_first[cidx]);
+        const uint4 ck = lds128(a_key + cidx * 16u);
+        const u32 cf = lds32(a_first + cidx * 4u);
         bool hit = ck.x == key.x && ck.y == key.y && ck.z == key.z && ck.w == key.w;
         if (!hit && (ck.x & ck.y & ck.z & ck.w) == 0xFFFFFFFFu) {
-          // empty entry: one lane wins the lock, its read becomes the key's representative, and the
-          // single 128-bit store of the key publishes the entry
-          if (atomicCAS(&S.c_lock[cidx], 0u, 1u) == 0u) {
-            S.c_rep[cidx] = make_uint2(s, len);
-            S.c_key[cidx] = key;
+          // empty entry.  Most keys occur once in a CTA's share of the stream and would only use up
+          // the cache: a key is admitted when a read with the same hash bits has missed before.
+          // Then one lane wins the lock, its read becomes the key's representative, and the single
+          // 128-bit store of the key publishes the entry.
+#if ECB_ADMIT_SECOND
+          const u32 sbit = 1u << (key.z & 31u);
+          const bool again = (atoms_or(a_seen + ((key.z >> 5) & (ECB_SEEN_WORDS - 1)) * 4u, sbit) & sbit) != 0u;
+#else
+          const bool again = true;
+#endif
+          if (again && atoms_cas(a_lock + cidx * 4u, 0u, 1u) == 0u) {
+            sts64(a_rep + cidx * 8u, s, len);
+            sts128(a_key + cidx * 16u, key);
             hit = true;
           }
         }
         if (hit) {
-          atomicAdd(&S.c_cnt[cidx], 1u);
-          if (s < cf) atomicMin(&S.c_first[cidx], s);
+          reds_add(a_cnt + cidx * 4u, 1u);
+          if (s < cf) reds_min(a_first + cidx * 4u, s);
           miss = false;
         }
       }
@@ -555,8 +639,8 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       if (mm) {
         if (miss) {
           const u32 q = qn + __popc(mm & lt_mask);
-          qk[q] = key;
-          qr[q] = make_uint2(s, len);
+          sts128(qk + q * 16u, key);
+          sts64(qr + q * 8u, s, len);
           prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
         }
         qn += __popc(mm);

@@ -25,6 +25,7 @@ struct HarvestParams {
   u32* row_len;      // [capacity] out: row length
   const u32* row_off;  // [capacity] absolute offsets inside the arena
   uint2* arena;      // (target, mask) pairs
+  int n_targets, n_haps;  // bounds of the column values (checked here, off the streaming path)
   u32* long_list;    // provisional ids whose read has more than 32 alignments
   u32* mid_list;     // provisional ids whose read has 9..32 alignments
   EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, n_long = #ECs with k > 32
@@ -66,8 +67,17 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
     }
     const int s = (int)P.ec_rep[e];
     u32 c[8];
+    bool bad = false;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c[j] = (u32)j < k ? ecb_code(P.tg[s + j], P.hp[s + j]) : 0xFFFFFFFFu;
+    for (int j = 0; j < 8; ++j) {
+      c[j] = 0xFFFFFFFFu;
+      if ((u32)j < k) {
+        const int t = P.tg[s + j], h = P.hp[s + j];
+        bad |= (u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps;
+        c[j] = ecb_code(t, h);
+      }
+    }
+    if (bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
     // Batcher odd-even merge sort network for 8 keys (19 comparators)
     ECB_CSWAP(c[0], c[1]) ECB_CSWAP(c[2], c[3]) ECB_CSWAP(c[4], c[5]) ECB_CSWAP(c[6], c[7])
     ECB_CSWAP(c[0], c[2]) ECB_CSWAP(c[1], c[3]) ECB_CSWAP(c[4], c[6]) ECB_CSWAP(c[5], c[7])
@@ -106,7 +116,9 @@ __global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestPara
     const int k = (int)P.ec_len[e];
     const int s = (int)P.ec_rep[e];
     const int t = lane < k ? P.tg[s + lane] : -1 - lane;
-    const u32 hbit = lane < k ? (1u << P.hp[s + lane]) : 0u;
+    const int h = lane < k ? P.hp[s + lane] : 0;
+    if (lane < k && ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps)) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+    const u32 hbit = lane < k ? (1u << (h & 31)) : 0u;
     const u32 grp = __match_any_sync(ECB_FULL, t);
     const u32 mask = __reduce_or_sync(grp, hbit);
     const bool leader = lane < k && lane == __ffs(grp) - 1;
@@ -133,8 +145,15 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
     const u32 k = min(P.ec_len[e], (u32)HARVEST_LONG_MAX);
     u32 np2 = 64;
     while (np2 < k) np2 <<= 1;
-    for (u32 i = threadIdx.x; i < np2; i += blockDim.x)
-      sm_codes[i] = i < k ? ecb_code(P.tg[s + i], P.hp[s + i]) : 0xFFFFFFFFu;
+    for (u32 i = threadIdx.x; i < np2; i += blockDim.x) {
+      u32 code = 0xFFFFFFFFu;
+      if (i < k) {
+        const int t = P.tg[s + i], h = P.hp[s + i];
+        if ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+        code = ecb_code(t, h);
+      }
+      sm_codes[i] = code;
+    }
     __syncthreads();
     for (u32 size = 2; size <= np2; size <<= 1) {
       for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
