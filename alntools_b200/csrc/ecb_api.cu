@@ -48,7 +48,7 @@ struct ecb_ctx {
   bool group_attr_set = false;
   DevBuf arena;                              // uint2 pairs
   u64 arena_used = 0;
-  DevBuf long_list, mid_list, count_of;
+  DevBuf long_list, mid_list, big_list, count_of;
   // triple table (cells)
   DevBuf ttable;
   u32 ttable_slots = 0;
@@ -202,6 +202,7 @@ int alloc_ec_arrays(ecb_ctx* c, u32 slots, bool preserve) {
   CKR(ensure(c, c->row_off, (size_t)slots * 4, preserve));
   CKR(ensure(c, c->long_list, (size_t)slots * 4, false));
   CKR(ensure(c, c->mid_list, (size_t)slots * 4, false));
+  CKR(ensure(c, c->big_list, (size_t)slots * 4, false));
   return ECB_OK;
 }
 
@@ -328,6 +329,7 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   H.row_off = (const u32*)c->row_off.p;
   H.long_list = (u32*)c->long_list.p;
   H.mid_list = (u32*)c->mid_list.p;
+  H.big_list = (u32*)c->big_list.p;
   H.ctr = c->d_ctr;
   const u32 n_new = e1 - e0;
   u64 total = 0;
@@ -346,6 +348,13 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
     ecb_harvest_warp_kernel<<<grid_for((u64)n_mid * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(H, n_mid);
     LAUNCH_CHECK("harvest_warp");
     CK(cudaMemsetAsync(&c->d_ctr->scratch[1], 0, sizeof(u32), c->stream));
+  }
+  if (c->h_ctr->scratch[3]) {
+    const u32 n_big = c->h_ctr->scratch[3];
+    const size_t smem = (size_t)8 * HARVEST_WSORT_MAX * 4;
+    ecb_harvest_wsort_kernel<<<grid_for((u64)n_big * 32, 256, c->sm_count * 6), 256, smem, c->stream>>>(H, n_big);
+    LAUNCH_CHECK("harvest_wsort");
+    CK(cudaMemsetAsync(&c->d_ctr->scratch[3], 0, sizeof(u32), c->stream));
   }
   const u32 n_long = c->h_ctr->n_long;
   if (n_long) {
@@ -1103,7 +1112,7 @@ int ecb_destroy(ecb_ctx* c) {
   if (!c) return ECB_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->count_of,
+  DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->big_list, &c->count_of,
                     &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,

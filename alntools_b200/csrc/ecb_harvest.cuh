@@ -9,7 +9,8 @@
 // exclusive scan of those lengths (an upper bound of the row length).
 //   k <= 8        one thread per EC: 8-element sorting network in registers
 //   8 < k <= 32   one warp per EC: __match_any_sync / __reduce_or_sync, rank by counting
-//   k > 32        one CTA per EC: bitonic sort in shared memory (up to ECB_MAX_READ_ALIGNMENTS)
+//   32 < k <= 1024  one warp per EC: warp-synchronous bitonic sort in shared memory (no CTA barrier)
+//   k > 1024      one CTA per EC: bitonic sort in shared memory (up to ECB_MAX_READ_ALIGNMENTS)
 #pragma once
 #include "ecb_common.cuh"
 #include "ecb_scan.cuh"
@@ -28,10 +29,13 @@ struct HarvestParams {
   int n_targets, n_haps;  // bounds of the column values (checked here, off the streaming path)
   u32* long_list;    // provisional ids whose read has more than 32 alignments
   u32* mid_list;     // provisional ids whose read has 9..32 alignments
-  EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, n_long = #ECs with k > 32
+  u32* big_list;     // provisional ids whose read has 33..HARVEST_WSORT_MAX alignments
+  EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, scratch[3] = #ECs with 32 < k <= HARVEST_WSORT_MAX,
+                     // n_long = #ECs with more
 };
 
 #define HARVEST_LONG_MAX 16384
+#define HARVEST_WSORT_MAX 1024   // longest read whose row one warp sorts on its own
 
 #define ECB_CSWAP(a, b)            \
   {                                \
@@ -58,8 +62,9 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
   for (u32 e = P.e0 + blockIdx.x * blockDim.x + threadIdx.x; e < P.e1; e += gridDim.x * blockDim.x) {
     const u32 k = P.ec_len[e];
     warp_append(P.mid_list, &P.ctr->scratch[1], k > 8 && k <= 32, e);
+    warp_append(P.big_list, &P.ctr->scratch[3], k > 32 && k <= HARVEST_WSORT_MAX, e);
     if (k > 8) {
-      if (k > 32) {
+      if (k > HARVEST_WSORT_MAX) {
         if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
         P.long_list[atomicAdd(&P.ctr->n_long, 1u)] = e;
       }
@@ -133,7 +138,73 @@ __global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestPara
   }
 }
 
-// Rows of long reads (33 .. HARVEST_LONG_MAX alignments): one CTA per EC, bitonic sort of the element
+// Rows of reads with 33..HARVEST_WSORT_MAX alignments (heavy multimapping): one WARP per EC.  The
+// element codes are sorted with a bitonic network in the warp's own slice of shared memory, so the only
+// synchronisation is __syncwarp; then one entry per distinct target.
+__global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestParams P, u32 n_big) {
+  extern __shared__ u32 sm_all[];
+  const int lane = threadIdx.x & 31;
+  u32* codes = sm_all + (threadIdx.x >> 5) * HARVEST_WSORT_MAX;
+  const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+  const u32 lt = (1u << lane) - 1u;
+  for (u32 li = warp_global; li < n_big; li += n_warps) {
+    const u32 e = P.big_list[li];
+    const int s = (int)P.ec_rep[e];
+    const u32 k = P.ec_len[e];
+    u32 np2 = 64;
+    while (np2 < k) np2 <<= 1;
+    bool bad = false;
+    for (u32 i = lane; i < np2; i += 32) {
+      u32 code = 0xFFFFFFFFu;
+      if (i < k) {
+        const int t = P.tg[s + i], h = P.hp[s + i];
+        bad |= (u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps;
+        code = ecb_code(t, h);
+      }
+      codes[i] = code;
+    }
+    if (bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+    __syncwarp();
+    for (u32 size = 2; size <= np2; size <<= 1) {
+      for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+        for (u32 i = lane; i < (np2 >> 1); i += 32) {
+          const u32 lo = 2 * i - (i & (stride - 1));
+          const u32 hi = lo + stride;
+          const bool up = (lo & size) == 0;
+          const u32 a = codes[lo], b = codes[hi];
+          if ((a > b) == up) {
+            codes[lo] = b;
+            codes[hi] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    uint2* out = P.arena + (size_t)P.row_off[e];
+    u32 run = 0;
+    for (u32 base = 0; base < k; base += 32) {
+      const u32 i = base + lane;
+      u32 code = 0xFFFFFFFFu;
+      bool start = false;
+      if (i < k) {
+        code = codes[i];
+        start = (i == 0) || ((codes[i - 1] >> 5) != (code >> 5));
+      }
+      const u32 m = __ballot_sync(ECB_FULL, start);
+      if (start) {
+        u32 mask = 0;
+        for (u32 j = i; j < k && (codes[j] >> 5) == (code >> 5); ++j) mask |= 1u << (codes[j] & 31u);
+        out[run + (u32)__popc(m & lt)] = make_uint2(code >> 5, mask);
+      }
+      run += (u32)__popc(m);
+    }
+    if (lane == 0) P.row_len[e] = run;
+    __syncwarp();
+  }
+}
+
+// Rows of long reads (HARVEST_WSORT_MAX+1 .. HARVEST_LONG_MAX alignments): one CTA per EC, bitonic sort of the element
 // codes in shared memory, then one entry per distinct target.
 __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestParams P, u32 n_long) {
   extern __shared__ u32 sm_codes[];
