@@ -450,14 +450,16 @@ int cells_prepare(ecb_ctx* c, int64_t min_cell_count, CellResult* cr) {
   if (n_cells == 0 || n_cells > 0x7FFFFFFFu) return fail(c, ECB_ERR_INVALID, "invalid cell ids (negative?)");
   cr->n_cells = n_cells;
   CKR(ensure(c, S.cell_key, (size_t)n_cells * 8));
-  CKR(ensure(c, S.cell_total, (size_t)n_cells * 8));
+  CKR(ensure(c, S.cell_total, (size_t)n_cells * 8 * CELLS_TOTAL_REPLICAS));
   CKR(ensure(c, S.cell_new, (size_t)n_cells * 4));
   CKR(ensure(c, c->r_cell_order, (size_t)n_cells * 4));
   CK(cudaMemsetAsync(S.cell_key.p, 0xFF, (size_t)n_cells * 8, c->stream));
-  CK(cudaMemsetAsync(S.cell_total.p, 0, (size_t)n_cells * 8, c->stream));
+  CK(cudaMemsetAsync(S.cell_total.p, 0, (size_t)n_cells * 8 * CELLS_TOTAL_REPLICAS, c->stream));
   P = make_cell_params(c, cr);
   cells_pass2_kernel<<<g_t, 256, 0, c->stream>>>(P);
   LAUNCH_CHECK("cells_pass2");
+  cells_total_reduce_kernel<<<grid_for(n_cells, 256, c->sm_count * 8), 256, 0, c->stream>>>((u64*)S.cell_total.p, n_cells);
+  LAUNCH_CHECK("cells_total_reduce");
 
   // order the cells by their nested first-occurrence key
   CKR(ensure(c, S.sort_k[0], (size_t)n_cells * 8));

@@ -16,6 +16,11 @@
 #include "ecb_common.cuh"
 #include "ecb_group.cuh"
 
+// Cell totals are accumulated in this many replicas (picked by CTA) and summed afterwards: the
+// cell-size distribution of real data is heavy-tailed and one counter per cell would serialise a
+// large share of all updates on a few addresses.
+#define CELLS_TOTAL_REPLICAS 32
+
 struct CellScratch {
   DevBuf fe_table, pair_table, cell_key, cell_total, cell_new, sort_k[2], sort_v[2], hist, flags, offsets;
   u32 fe_slots = 0, pair_slots = 0;
@@ -33,7 +38,7 @@ struct CellParams {
   EcbEntry* fe_table;      u32 fe_mask;
   EcbEntry* pair_table;    u32 pair_mask;
   u64* cell_key;           // [n_cells]
-  u64* cell_total;         // [n_cells]
+  u64* cell_total;         // [CELLS_TOTAL_REPLICAS * n_cells]: replica r of cell c at r * n_cells + c
   int32_t* cell_new;       // [n_cells] output column or -1
   u32* ec_keep;            // [n_prov]
   const u32* ecid_of;
@@ -79,8 +84,8 @@ __global__ void __launch_bounds__(256) cells_pass2_kernel(const CellParams P) {
     const u32 fs = table_find(P.fe_table, P.fe_mask, Key128{(u64)slot, k.hi});
     const u64 ec_first = P.fe_table[fs].first;
     const u64 cand = ((ec_first - P.min_base) << 32) | (first - P.min_base);
-    atomicMin(&P.cell_key[cell], cand);
-    atomicAdd(&P.cell_total[cell], (u64)count);
+    if (cand < *reinterpret_cast<volatile u64*>(&P.cell_key[cell])) atomicMin(&P.cell_key[cell], cand);
+    atomicAdd(&P.cell_total[(size_t)(blockIdx.x % CELLS_TOTAL_REPLICAS) * P.n_cells + cell], (u64)count);
     bool claimed;
     u64 seen;
     const u32 ps = table_find_or_claim(P.pair_table, P.pair_mask, Key128{k.lo, 0ull}, claimed, seen);
@@ -89,6 +94,15 @@ __global__ void __launch_bounds__(256) cells_pass2_kernel(const CellParams P) {
       continue;
     }
     atomicAdd(&P.pair_table[ps].countm1, count);
+  }
+}
+
+// cell_total[c] = sum of its replicas.
+__global__ void __launch_bounds__(256) cells_total_reduce_kernel(u64* __restrict__ cell_total, u32 n_cells) {
+  for (u32 c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += gridDim.x * blockDim.x) {
+    u64 t = 0;
+    for (u32 r = 0; r < CELLS_TOTAL_REPLICAS; ++r) t += cell_total[(size_t)r * n_cells + c];
+    cell_total[c] = t;
   }
 }
 

@@ -30,6 +30,10 @@ WORKLOADS = {
     "cfg2_diploid_30M": dict(n_reads=30_000_000, n_targets=100_000, n_haps=2, mode="diploid", seed=2),
     "cfg1_small_1M": dict(n_reads=1_000_000, n_targets=2_000, n_haps=2, mode="light", seed=1),
     "cfg3_do8_heavy": dict(n_reads=3_000_000, n_targets=140_000, n_haps=8, mode="heavy", seed=3),
+    # BASELINE.json configs[3], scaled to one GPU: per-cell counts, 50k cells (Zipf sizes), 4 files, the
+    # last read of every file dropped, cells below 1000 reads filtered out
+    "cfg4_cells_50k": dict(n_reads=20_000_000, n_targets=140_000, n_haps=8, mode="diploid", seed=4,
+                           n_cells=50_000, n_files=4, min_count=1000),
 }
 
 
@@ -256,9 +260,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic shard of this rank (weak scaling: fixed reads per GPU) --------------------------
-    cols = synth.make_columns(wl["n_reads"], wl["n_targets"], wl["n_haps"], wl["seed"] + 7919 * rank, mode=wl["mode"])
+    n_cells = int(wl.get("n_cells", 0))
+    cols = synth.make_columns(wl["n_reads"], wl["n_targets"], wl["n_haps"], wl["seed"] + 7919 * rank, mode=wl["mode"],
+                              n_cells=n_cells)
     n_aln = int(len(cols["read_group"]))
-    names = ("read_group", "target_idx", "hap_idx")
+    names = ("read_group", "target_idx", "hap_idx") + (("cell_idx",) if n_cells else ())
+    if n_cells and world > 1:
+        raise SystemExit("the per-cell path is single-GPU in this round")
+    # per-cell workloads arrive as several files: read-aligned pieces, one push each
+    file_cuts = [0, n_aln]
+    if n_cells:
+        file_cuts = [0]
+        for k in range(1, int(wl["n_files"])):
+            c = n_aln * k // int(wl["n_files"])
+            while c < n_aln and cols["read_group"][c] == cols["read_group"][c - 1]:
+                c += 1
+            file_cuts.append(c)
+        file_cuts.append(n_aln)
+    min_count = int(wl.get("min_count", 0))
     host = {k: torch.from_numpy(cols[k]).pin_memory() for k in names}
     dev = {k: host[k].cuda(non_blocking=True) for k in names}
     torch.cuda.synchronize()
@@ -293,7 +312,12 @@ def main():
         marks[0].record(stream)
         for i in range(steps):
             builder.reset()
-            builder.push(columns["read_group"], columns["target_idx"], columns["hap_idx"], order_base=order_base)
+            if n_cells:
+                for a, b in zip(file_cuts[:-1], file_cuts[1:]):
+                    builder.push(columns["read_group"][a:b], columns["target_idx"][a:b], columns["hap_idx"][a:b],
+                                 columns["cell_idx"][a:b], order_base=order_base + a, drop_last_group=True)
+            else:
+                builder.push(columns["read_group"], columns["target_idx"], columns["hap_idx"], order_base=order_base)
             res = finalize(builder)
             group_ms.append(builder.stats()["group_ms"])
             marks[i + 1].record(stream)
@@ -340,13 +364,13 @@ def main():
 
     def fin_device(b):
         if world == 1:
-            return b.finalize_raw()
+            return b.finalize_raw(min_count)
         owner.reset()
         return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0"))
 
     def fin_host(b):
         if world == 1:
-            return b.finalize_raw()
+            return b.finalize_raw(min_count)
         owner.reset()
         out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0")
         if rank == 0:   # the job's result leaves the device once, on rank 0, into pinned memory
@@ -359,8 +383,8 @@ def main():
         return _Res(out)
 
     # ---- device-resident arm ("value") --------------------------------------------------------------
-    b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
-                      result_on_device=1, **opts)
+    b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], with_cells=bool(n_cells), alignments_hint=n_aln,
+                      device=local_rank, result_on_device=1, **opts)
     b_dev.set_stream(stream.cuda_stream)
     timed_once(b_dev, dev, args.warmup, fin_device)
     with ClockSampler(local_rank) as clocks:
@@ -373,8 +397,8 @@ def main():
     b_dev.close()
 
     # ---- end-to-end arm: host columns in, host matrices out ----------------------------------------
-    b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], alignments_hint=n_aln, device=local_rank,
-                      result_on_device=1 if world > 1 else 0, **opts)
+    b_e2e = EcBuilder(wl["n_targets"], wl["n_haps"], with_cells=bool(n_cells), alignments_hint=n_aln,
+                      device=local_rank, result_on_device=1 if world > 1 else 0, **opts)
     b_e2e.set_stream(stream.cuda_stream)
     timed_once(b_e2e, host, args.warmup, fin_host)
     ms_e2e, res_e2e, _, note_e2e = timed(b_e2e, host, args.steps, fin_host)
@@ -394,7 +418,8 @@ def main():
 
     peak, peak_kind = measured_peak_gbs()
     gms = sorted(group_ms)[len(group_ms) // 2]
-    algo_bytes = 12.0 * n_aln  # three int32 columns read once by the grouping kernel
+    # three (four with cells) int32 columns read once by the grouping kernel; group_ms is the LAST push's kernel
+    algo_bytes = (16.0 if n_cells else 12.0) * (file_cuts[-1] - file_cuts[-2])
     achieved = algo_bytes / (gms * 1e-3) / 1e9
     line = {
         "metric": "bam2ec alignments/sec (EC build)",
