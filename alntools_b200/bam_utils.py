@@ -54,8 +54,8 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
     temporary BAM is written.  `device` selects the GPU.
     """
     start_time = time.time()
-    if range_filename is not None:
-        raise NotImplementedError("--rangefile is not part of the GPU EC path yet")
+    if range_filename is not None and emitter.use_python_emitter():
+        raise NotImplementedError("--rangefile needs the native emitter (unset ALNTOOLS_B200_EMITTER)")
     num_chunks, num_processes = _job_plan(num_chunks, number_processes)
     if sample is None:                                        # bam_utils.py:552-554
         sample = os.path.basename(bam_filename)
@@ -71,6 +71,8 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
         with bamcols.BamColumnReader(bam_filename, n_threads=num_processes) as reader:
             tables = TargetTables(reader.references, reader.lengths, target_filename)
             reader.set_tables(tables)
+            if range_filename is not None:
+                reader.track_ranges(True)
             LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
                                                                 utils.format_time(start_time, time.time())))
             temp_time = time.time()
@@ -85,6 +87,10 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
                     # the reference ends up with zero ECs and APM() raises (Sparse3DMatrix.py:45-46)
                     raise RuntimeError("The shape must be a tuple of three positive integers.")
                 res = builder.finalize()
+            if range_filename is not None:                     # bam_utils.py:735-766
+                lo, hi = reader.ranges()
+                utils.write_range_file(range_filename, list(tables.main_targets.keys()), tables.haplotypes,
+                                       reader.references, lo, hi)
     LOG.info("All results combined in {}, total time: {}".format(utils.format_time(temp_time, time.time()),
                                                                  utils.format_time(start_time, time.time())))
     LOG.info("# Valid Alignments: {:,}".format(valid))

@@ -7,6 +7,8 @@ import glob
 import os
 import time
 
+import numpy as np
+
 from . import bamcols, bin_utils, emase, emitter, utils
 from ._native import EcBuilder
 from .header import TargetTables
@@ -14,7 +16,8 @@ from .header import TargetTables
 LOG = utils.get_logger()
 
 
-def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename=None, device=0):
+def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename=None, device=0,
+                  range_filename=None):
     """The reference's convert() after its glob: files are merged in the given order
     (bam_utils_multisample.py:503-560)."""
     start_time = time.time()
@@ -35,16 +38,27 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
     else:
         cells = bamcols.CellDictionary()
         tables = None
+        range_lo = range_hi = references = None
         for bam_file in bam_files:
             with bamcols.BamColumnReader(bam_file) as reader:
                 if tables is None:                            # tables from the first file only (:399)
                     tables = TargetTables(reader.references, reader.lengths, target_filename)
+                    references = reader.references
                 reader.set_tables(tables)
+                if range_filename is not None:
+                    reader.track_ranges(True)
                 c = reader.read_all(cells=cells)
+                if range_filename is not None:                # merged over the files (:568-576)
+                    lo, hi = reader.ranges()
+                    range_lo = lo if range_lo is None else np.minimum(range_lo, lo)
+                    range_hi = hi if range_hi is None else np.maximum(range_hi, hi)
             per_file.append((c["read_group"], c["target_idx"], c["hap_idx"], c["cell_idx"]))
             total_valid += len(c["read_group"])
         cell_names = cells.names()
         cells.close()
+        if range_filename is not None:                        # :638-668
+            utils.write_range_file(range_filename, list(tables.main_targets.keys()), tables.haplotypes,
+                                   references, range_lo, range_hi)
 
     with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
                    alignments_hint=total_valid, device=device) as builder:
@@ -91,6 +105,7 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks, minimum_count
     if len(bam_files) == 0:
         LOG.error('No bam files found in directory: {}'.format(bam_filename))
         return None
-    if range_filename is not None:
-        raise NotImplementedError("--rangefile is not part of the GPU EC path yet")
-    return convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename, device)
+    if range_filename is not None and emitter.use_python_emitter():
+        raise NotImplementedError("--rangefile needs the native emitter (unset ALNTOOLS_B200_EMITTER)")
+    return convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_filename, device,
+                         range_filename)

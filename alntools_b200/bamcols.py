@@ -33,6 +33,8 @@ SIGNATURES = {
                                       ctypes.POINTER(ctypes.c_int)]),
     "bamcols_all_alignments": (ctypes.c_int64, [ctypes.c_void_p]),
     "bamcols_n_groups": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bamcols_track_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_phase_seconds": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -149,6 +151,22 @@ class BamColumnReader(object):
     @property
     def all_alignments(self):
         return int(self._lib.bamcols_all_alignments(self._h))
+
+    def track_ranges(self, enable=True):
+        rc = self._lib.bamcols_track_ranges(self._h, 1 if enable else 0)
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(self._h).decode())
+
+    def ranges(self):
+        """(min_pos, max_pos) int32 arrays per reference; min > max where no valid alignment was seen."""
+        lo, hi = ctypes.c_void_p(), ctypes.c_void_p()
+        n = self._lib.bamcols_ranges(self._h, ctypes.byref(lo), ctypes.byref(hi))
+        if n < 0:
+            raise ValueError("ranges were not tracked")
+        if n == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32)
+        return (np.array((ctypes.c_int32 * n).from_address(lo.value), dtype=np.int32),
+                np.array((ctypes.c_int32 * n).from_address(hi.value), dtype=np.int32))
 
     def phase_seconds(self):
         """dict phase -> wall-clock seconds so far (single-sample path)."""

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <climits>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -96,6 +97,9 @@ struct bamcols {
   int mode = 0;                  // 0 undecided, 1 single-sample, 2 per-cell
   size_t grain = 4096;           // records per worker thread below which no further thread is used
   double phase_s[6] = {0, 0, 0, 0, 0, 0};  // inflate, record hop, validity, read starts, rows, copy-out
+  // --rangefile (bam_utils.py:282-286): smallest / largest reference_start of the valid alignments per tid
+  bool track_ranges = false;
+  std::vector<int32_t> range_min, range_max;
   std::string err;
 };
 
@@ -279,6 +283,19 @@ bool cell_field(const std::string& name, const char** out, size_t* len) {
   return true;
 }
 
+// Lock-free min / max on plain int32 slots shared by the worker threads (updates are rare after the
+// first few alignments of a reference).
+inline void note_position(bamcols* r, int32_t tid, int32_t pos) {
+  int32_t* lo = &r->range_min[(size_t)tid];
+  int32_t* hi = &r->range_max[(size_t)tid];
+  int32_t cur = __atomic_load_n(lo, __ATOMIC_RELAXED);
+  while (pos < cur && !__atomic_compare_exchange_n(lo, &cur, pos, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  cur = __atomic_load_n(hi, __ATOMIC_RELAXED);
+  while (pos > cur && !__atomic_compare_exchange_n(hi, &cur, pos, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+}
+
 template <class F>
 void parallel_for(int nt, F fn) {
   if (nt <= 1) {
@@ -361,6 +378,7 @@ int process_window_single(bamcols* r) {
       if (flag & 0x4) continue;
       if ((flag & 0x1) && ((flag & 0x80) || !(flag & 0x2) || tid != ntid || npos < 0)) continue;
       if (tid < 0 || tid >= n_ref) { bad.store(2); continue; }
+      if (r->track_ranges) note_position(r, tid, (int32_t)le32(q + 4));
       fl[i] = 1;
       ++cnt;
     }
@@ -583,6 +601,24 @@ const char* bamcols_cells_name(const bamcols_cells* c, int64_t idx) {
   return c->names[(size_t)idx].c_str();
 }
 
+int bamcols_track_ranges(bamcols* r, int enable) {
+  if (!r) return BAMCOLS_ERR_INVALID;
+  if (r->mode != 0) return fail(r, BAMCOLS_ERR_INVALID, "bamcols_track_ranges must be called before the first bamcols_emit");
+  r->track_ranges = enable != 0;
+  if (r->track_ranges) {
+    r->range_min.assign(r->ref_names.size(), INT32_MAX);
+    r->range_max.assign(r->ref_names.size(), -1);
+  }
+  return BAMCOLS_OK;
+}
+
+int bamcols_ranges(const bamcols* r, const int32_t** min_pos, const int32_t** max_pos) {
+  if (!r || !min_pos || !max_pos || !r->track_ranges) return BAMCOLS_ERR_INVALID;
+  *min_pos = r->range_min.data();
+  *max_pos = r->range_max.data();
+  return (int)r->range_min.size();
+}
+
 int bamcols_phase_seconds(const bamcols* r, double* out6) {
   if (!r || !out6) return BAMCOLS_ERR_INVALID;
   for (int i = 0; i < 6; ++i) out6[i] = r->phase_s[i];
@@ -658,6 +694,7 @@ int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int3
     const size_t qlen = l_name - 1;  // the stored name without its terminating NUL
     const size_t tlen = trimmed_len(qname, qlen);
     if (tid < 0 || tid >= n_ref) return fail(r, BAMCOLS_ERR_TID, "alignment with reference id %d outside the header's %d references", tid, n_ref);
+    if (r->track_ranges) note_position(r, tid, (int32_t)le32(p + 4));
 
     bool sw;
     if (!cells) {

@@ -74,8 +74,17 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     ph.mark("export")
 
     # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
-    both = _all_to_all_counts([v for pair in zip(ec_counts, row_counts) for v in pair], device, group)
-    recv_ec, recv_rows = both[0::2], both[1::2]
+    # one all-gather carries every rank's partition sizes and its pushed position range
+    info = torch.tensor(list(ec_counts) + list(row_counts) + [min_base if max_end > min_base else (1 << 62), max_end],
+                        dtype=torch.int64, device=device)
+    gathered = [torch.empty_like(info) for _ in range(world)]
+    dist.all_gather(gathered, info, group=group)
+    g = torch.stack(gathered).tolist()
+    me = dist.get_rank(group)
+    recv_ec = [g[src][me] for src in range(world)]
+    recv_rows = [g[src][world + me] for src in range(world)]
+    g_min = min(row[2 * world] for row in g)
+    g_max = max(row[2 * world + 1] for row in g)
     meta_in = torch.empty((sum(recv_ec), 5), dtype=torch.int64, device=device)
     rows_in = torch.empty((sum(recv_rows), 2), dtype=torch.int32, device=device)
     dist.all_to_all_single(meta_in, meta, output_split_sizes=recv_ec, input_split_sizes=ec_counts, group=group)
@@ -89,9 +98,6 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     ph.mark("import")
 
     # ---- global EC ids from the OR-ed first-occurrence bitmap ------------------------------------
-    span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
-    dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)
-    g_min, g_max = -int(span[0].item()), int(span[1].item())
     if g_max <= g_min:
         raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
     n_words = (g_max - g_min + 31) // 32 + 1

@@ -54,3 +54,30 @@ def parse_targets(target_file):
                 continue
             targets[line.strip().split()[0]] = len(targets)
     return targets
+
+
+def write_range_file(range_filename, main_targets, haplotypes, references, range_min, range_max):
+    """The --rangefile report (alntools/bam_utils.py:735-766, bam_utils_multisample.py:638-668): one line
+    per main target, one column per haplotype: max(reference_start) - min(reference_start) + 1 over the
+    valid alignments of '<target>_<haplotype>' ('<target>' for the empty haplotype), 0 when that
+    reference does not exist or got no valid alignment."""
+    tid_of = {}
+    for tid, name in enumerate(references):
+        tid_of.setdefault(name, tid)                           # gettid: the first reference of that name
+    with open(range_filename, "w") as fw:
+        fw.write("#\t")
+        fw.write("\t".join(haplotypes))
+        fw.write("\n")
+        for main_target in main_targets:
+            vals = []
+            for haplotype in haplotypes:
+                name = main_target if len(haplotype) == 0 else "{}_{}".format(main_target, haplotype)
+                tid = tid_of.get(name, -1)
+                if tid < 0 or range_min[tid] > range_max[tid]:
+                    vals.append("0")
+                else:
+                    vals.append(str(int(range_max[tid]) - int(range_min[tid]) + 1))
+            fw.write(main_target)
+            fw.write("\t")
+            fw.write("\t".join(vals))
+            fw.write("\n")

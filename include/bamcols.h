@@ -77,6 +77,12 @@ int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int3
 int64_t bamcols_all_alignments(const bamcols* r);
 int64_t bamcols_n_groups(const bamcols* r);
 
+/* --rangefile support (alntools/bam_utils.py:282-286): record the smallest and largest reference_start
+ * of the valid alignments of every reference.  Enable before the first bamcols_emit; bamcols_ranges
+ * returns n_references and two int32[n_references] arrays (min > max: no valid alignment). */
+int bamcols_track_ranges(bamcols* r, int enable);
+int bamcols_ranges(const bamcols* r, const int32_t** min_pos, const int32_t** max_pos);
+
 /* Wall-clock seconds spent so far per phase: inflate, record hop, validity, read starts, row write,
  * copy-out (single-sample path; diagnostics for the host-side timing report). */
 int bamcols_phase_seconds(const bamcols* r, double* out6);

@@ -43,19 +43,20 @@ def patch_pep479(bam_utils):
 
 
 def bam2ec(bam_filename, ec_filename, num_chunks=1, number_processes=1, target_filename=None,
-           temp_dir=None):
+           temp_dir=None, range_filename=None):
     bam_utils, _ = _import_reference()
     patch_pep479(bam_utils)
     bam_utils.convert(bam_filename, ec_filename, None, num_chunks=num_chunks,
                       number_processes=number_processes,
                       temp_dir=temp_dir or os.path.dirname(ec_filename),
-                      target_filename=target_filename)
+                      range_filename=range_filename, target_filename=target_filename)
 
 
-def bam2ec_multisample(bam_dir, ec_filename, minimum_count, number_processes=1, target_filename=None):
+def bam2ec_multisample(bam_dir, ec_filename, minimum_count, number_processes=1, target_filename=None,
+                       range_filename=None):
     _, multi = _import_reference()
     multi.convert(bam_dir, ec_filename, None, 0, minimum_count, number_processes,
-                  os.path.dirname(ec_filename), None, target_filename)
+                  os.path.dirname(ec_filename), range_filename, target_filename)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,8 @@ def pytest_configure(config):
 def golden_cases(kind=None):
     with open(os.path.join(GOLDEN, "manifest.json")) as fh:
         cases = json.load(fh)
+    with open(os.path.join(GOLDEN, "manifest_range.json")) as fh:      # --rangefile goldens carry EC files too
+        cases += json.load(fh)
     return [c for c in cases if kind is None or c["kind"] == kind]
 
 

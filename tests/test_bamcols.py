@@ -200,3 +200,36 @@ def test_large_synthetic_multi_batch(tmp_path):
     assert np.array_equal(got["read_group"], cols["read_group"])
     assert np.array_equal(got["target_idx"], cols["target_idx"])
     assert np.array_equal(got["hap_idx"], cols["hap_idx"])
+
+
+def _range_cases():
+    import json
+    with open(os.path.join(GOLDEN, "manifest_range.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("case", _range_cases(), ids=lambda c: c["name"])
+def test_range_file_matches_the_reference(case, tmp_path):
+    """--rangefile (bam_utils.py:282-286,735-766): per-reference min/max of reference_start over the valid
+    alignments, written like the reference; goldens minted by oracle/make_golden_range.py."""
+    from alntools_b200 import utils
+    files = ([os.path.join(GOLDEN, case["bam"])] if case["kind"] == "single"
+             else [os.path.join(GOLDEN, case["dir"], fn) for fn in case["file_order"]])
+    tfile = os.path.join(GOLDEN, case["targets"]) if case.get("targets") else None
+    tables = lo = hi = refs = None
+    cells = bamcols.CellDictionary() if case["kind"] == "multisample" else None
+    for path in files:
+        with bamcols.BamColumnReader(path) as r:
+            if tables is None:
+                tables = TargetTables(r.references, r.lengths, tfile)
+                refs = r.references
+            r.set_tables(tables)
+            r.track_ranges(True)
+            r.read_all(cells=cells)
+            a, b = r.ranges()
+            lo = a if lo is None else np.minimum(lo, a)
+            hi = b if hi is None else np.maximum(hi, b)
+    out = str(tmp_path / "range.txt")
+    utils.write_range_file(out, list(tables.main_targets.keys()), tables.haplotypes, refs, lo, hi)
+    with open(out) as a, open(os.path.join(GOLDEN, case["range"])) as b:
+        assert a.read() == b.read()

@@ -65,6 +65,27 @@ def test_convert_reproduces_reference_file_multisample(native, case, tmp_path):
         assert a.read() == b.read()
 
 
+def test_convert_with_rangefile_reproduces_reference_files(native, tmp_path):
+    """EC file and --rangefile report together, single-sample and per-cell (goldens of make_golden_range.py)."""
+    import json
+    from alntools_b200 import bam_utils, bam_utils_multisample
+    with open(os.path.join(GOLDEN, "manifest_range.json")) as fh:
+        cases = json.load(fh)
+    for case in cases:
+        out, rng = str(tmp_path / (case["name"] + ".bin")), str(tmp_path / (case["name"] + ".range.txt"))
+        if case["kind"] == "single":
+            tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+            bam_utils.convert(os.path.join(GOLDEN, case["bam"]), out, None, num_chunks=1, number_processes=1,
+                              range_filename=rng, target_filename=tfile)
+        else:
+            files = [os.path.join(GOLDEN, case["dir"], fn) for fn in case["file_order"]]
+            bam_utils_multisample.convert_files(files, out, None, case["mincount"], range_filename=rng)
+        with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
+            assert a.read() == b.read(), case["name"]
+        with open(rng) as a, open(os.path.join(GOLDEN, case["range"])) as b:
+            assert a.read() == b.read(), case["name"]
+
+
 # ---------------------------------------------------------------- seeded columns vs the oracle
 @pytest.mark.parametrize("n_reads,n_targets,n_haps,mode,dup", [
     (1, 5, 2, "light", 0.0),
