@@ -53,7 +53,7 @@ class EcbStats(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64), ("table_slots", ctypes.c_int64),
         ("table_used", ctypes.c_int64), ("table_grows", ctypes.c_int64),
         ("overflow_reads", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64),
-        ("d2h_bytes", ctypes.c_int64),
+        ("d2h_bytes", ctypes.c_int64), ("row_entries", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -67,6 +67,14 @@ SIGNATURES = {
                                   ctypes.c_int, ctypes.c_int64]),
     "ecb_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
     "ecb_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "ecb_arena_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "ecb_arena_open_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "ecb_arena_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "ecb_export_to_arenas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                            ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
+                                            ctypes.POINTER(ctypes.c_int64)]),
+    "ecb_import_arena": (ctypes.c_int, [ctypes.c_void_p]),
     "ecb_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "ecb_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(EcbResult)]),
@@ -252,6 +260,34 @@ class EcBuilder(object):
         a = (ctypes.c_int64 * n)(*ec_counts)
         b = (ctypes.c_int64 * n)(*row_counts)
         self._check(self._lib.ecb_import_entries(self._ctx, meta.data_ptr(), rows.data_ptr(), a, b, n))
+
+    # ---- exchange over peer memory (CUDA IPC arenas, see include/ecb200.h) -------------------------
+    def arena_create(self, cap_records, cap_rows):
+        """-> (64-byte IPC handle, base address) of this OWNER context's arena."""
+        handle = ctypes.create_string_buffer(64)
+        base = ctypes.c_void_p()
+        self._check(self._lib.ecb_arena_create(self._ctx, int(cap_records), int(cap_rows), handle, ctypes.byref(base)))
+        return handle.raw, int(base.value)
+
+    def arena_open_peer(self, handle):
+        base = ctypes.c_void_p()
+        self._check(self._lib.ecb_arena_open_peer(self._ctx, ctypes.create_string_buffer(handle, 64), ctypes.byref(base)))
+        return int(base.value)
+
+    def arena_reset(self):
+        self._check(self._lib.ecb_arena_reset(self._ctx))
+
+    def export_to_arenas(self, bases, cap_records, cap_rows):
+        """Partition this LOCAL context's ECs by owner and store them into the owners' arenas.
+        -> (min_base, max_end) of the positions pushed here."""
+        arr = (ctypes.c_void_p * len(bases))(*bases)
+        lo, hi = ctypes.c_int64(), ctypes.c_int64()
+        self._check(self._lib.ecb_export_to_arenas(self._ctx, len(bases), arr, int(cap_records), int(cap_rows),
+                                                   ctypes.byref(lo), ctypes.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def import_arena(self):
+        self._check(self._lib.ecb_import_arena(self._ctx))
 
     def global_mark(self, min_base, bitmap):
         self._check(self._lib.ecb_global_mark(self._ctx, int(min_base), bitmap.data_ptr(), bitmap.numel()))

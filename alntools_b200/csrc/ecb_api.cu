@@ -79,9 +79,14 @@ struct ecb_ctx {
   bool long_attr_set = false;
   // multi-GPU exchange
   DevBuf x_meta, x_rows, x_counts, x_base;
+  // arena of the peer-memory exchange (plain cudaMalloc: must be exportable through CUDA IPC)
+  void* xa_base = nullptr;
+  int64_t xa_cap_ec = 0, xa_cap_rows = 0;
+  std::vector<void*> xa_opened;
   int64_t x_part_ec[ECB_MAX_WORLD], x_part_rows[ECB_MAX_WORLD];
   u64 g_min_base = 0;
   u64 g_n_ec_total = 0;
+  u32 g_n_wide = 0;
   std::string err;
 };
 
@@ -905,6 +910,7 @@ int ecb_get_stats(const ecb_ctx* c, ecb_stats* out) {
   *out = c->stats;
   out->table_slots = c->table_slots;
   out->table_used = c->n_ec;
+  out->row_entries = (int64_t)c->arena_used;
   return ECB_OK;
 }
 
@@ -1023,6 +1029,95 @@ int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* ro
   return ECB_OK;
 }
 
+int ecb_arena_create(ecb_ctx* c, int64_t cap_records, int64_t cap_rows, void* ipc_handle_out, void** base_out) {
+  if (!c || cap_records < 1 || cap_rows < 1 || !base_out) return ECB_ERR_INVALID;
+  if (c->xa_base) return fail(c, ECB_ERR_STATE, "this context already has an arena");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_META_WORDS * 8 + (size_t)cap_rows * 8;
+  CK(cudaMalloc(&c->xa_base, bytes));
+  CK(cudaMemset(c->xa_base, 0, ECB_ARENA_HEADER_BYTES));
+  c->xa_cap_ec = cap_records;
+  c->xa_cap_rows = cap_rows;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are documented as 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->xa_base));
+    memcpy(ipc_handle_out, &h, sizeof h);
+  }
+  *base_out = c->xa_base;
+  return ECB_OK;
+}
+
+int ecb_arena_open_peer(ecb_ctx* c, const void* ipc_handle, void** base_out) {
+  if (!c || !ipc_handle || !base_out) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof h);
+  void* p = nullptr;
+  CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->xa_opened.push_back(p);
+  *base_out = p;
+  return ECB_OK;
+}
+
+int ecb_arena_reset(ecb_ctx* c) {
+  if (!c || !c->xa_base) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->xa_base, 0, ECB_ARENA_HEADER_BYTES, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ECB_OK;
+}
+
+int ecb_export_to_arenas(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
+                         int64_t* min_base, int64_t* max_end) {
+  if (!c || !arena_bases || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;
+  if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
+  if (c->with_cells) return fail(c, ECB_ERR_INVALID, "the multi-GPU exchange covers the single-sample path only");
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots) CKR(init_table(c));
+  if (min_base) *min_base = c->n_ec ? (int64_t)c->min_base : 0;
+  if (max_end) *max_end = c->n_ec ? (int64_t)c->max_end : 0;
+  if (c->n_ec == 0) return ECB_OK;
+  ExportParams P{};
+  P.table = (const EcbEntry*)c->table.p;
+  P.ec_slot = (const u32*)c->ec_slot.p;
+  P.row_len = (const u32*)c->row_len.p;
+  P.row_off = (const u32*)c->row_off.p;
+  P.arena = (const uint2*)c->arena.p;
+  P.n_ec = c->n_ec;
+  P.world = (u32)world;
+  ArenaTargets A{};
+  for (int r = 0; r < world; ++r) {
+    if (!arena_bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
+    char* b = (char*)arena_bases[r];
+    A.hdr[r] = (unsigned long long*)b;
+    A.meta[r] = (long long*)(b + ECB_ARENA_HEADER_BYTES);
+    A.rows[r] = (int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_META_WORDS * 8);
+  }
+  A.cap_ec = (unsigned long long)cap_records;
+  A.cap_rows = (unsigned long long)cap_rows;
+  ecb_export_to_arenas_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
+  LAUNCH_CHECK("export_to_arenas");
+  CK(cudaStreamSynchronize(c->stream));   // remote stores are complete (and visible to the owner) when the kernel is
+  return ECB_OK;
+}
+
+int ecb_import_arena(ecb_ctx* c) {
+  if (!c || !c->xa_base) return ECB_ERR_INVALID;
+  CK(cudaSetDevice(c->device));
+  unsigned long long hdr[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(hdr, c->xa_base, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (hdr[2] || hdr[0] > (unsigned long long)c->xa_cap_ec || hdr[1] > (unsigned long long)c->xa_cap_rows)
+    return fail(c, ECB_ERR_LIMIT, "exchange arena too small: %llu records / %llu rows arrived, capacity %lld / %lld",
+                hdr[0], hdr[1], (long long)c->xa_cap_ec, (long long)c->xa_cap_rows);
+  const int64_t n_rec = (int64_t)hdr[0], n_rows = (int64_t)hdr[1];
+  const char* b = (const char*)c->xa_base;
+  return ecb_import_entries(c, (const int64_t*)(b + ECB_ARENA_HEADER_BYTES),
+                            (const int32_t*)(b + ECB_ARENA_HEADER_BYTES + (size_t)c->xa_cap_ec * ECB_META_WORDS * 8),
+                            &n_rec, &n_rows, 1);
+}
+
 static FinalizeParams global_params(ecb_ctx* c) {
   FinalizeParams F{};
   F.table = (const EcbEntry*)c->table.p;
@@ -1078,9 +1173,13 @@ int ecb_global_lens(ecb_ctx* c, int32_t* lens_device, int32_t* counts_device) {
   F.n_data = counts_device;
   CKR(ensure(c, c->r_n_indices, (size_t)c->g_n_ec_total * 4));
   F.n_indices = (int32_t*)c->r_n_indices.p;
+  F.wide_count = &c->d_ctr->scratch[2];        // rows with more than 8 entries are listed for ecb_global_rows
+  F.wide_list = (u32*)c->long_list.p;
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[2], 0, sizeof(u32), c->stream));
   ecb_fin_rank_kernel<true><<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rank");
-  CK(cudaStreamSynchronize(c->stream));
+  CKR(sync_counters(c));
+  c->g_n_wide = c->h_ctr->scratch[2];
   return ECB_OK;
 }
 
@@ -1104,8 +1203,11 @@ int ecb_global_rows(ecb_ctx* c, const int32_t* indptr_device, int32_t* indices_d
   F.a_data = data_device;
   ecb_fin_rows_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rows");
-  ecb_fin_rows_long_kernel<<<grid_for((u64)c->n_ec * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(F, nullptr, 0u);
-  LAUNCH_CHECK("fin_rows_long");
+  if (c->g_n_wide) {
+    ecb_fin_rows_long_kernel<<<grid_for((u64)c->g_n_wide * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+        F, (const u32*)c->long_list.p, c->g_n_wide);
+    LAUNCH_CHECK("fin_rows_long");
+  }
   CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;
 }
@@ -1122,6 +1224,8 @@ int ecb_destroy(ecb_ctx* c) {
   for (DevBuf* b : bufs) release(c, *b);
   cells_release(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (void* p : c->xa_opened) cudaIpcCloseMemHandle(p);
+  if (c->xa_base) cudaFree(c->xa_base);
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
   if (c->h_res) {

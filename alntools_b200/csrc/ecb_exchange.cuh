@@ -90,6 +90,113 @@ __global__ void __launch_bounds__(256) ecb_export_fill_kernel(const ExportParams
   }
 }
 
+// ---- fused partition + dispatch over peer memory ------------------------------------------------------
+// Every rank owns an ARENA (plain cudaMalloc, mapped into its peers through CUDA IPC): a small header
+// {records, rows, overflow} followed by a record area and a row area.  The kernel below does what
+// ecb_export_* + an all-to-all did, in one pass: it finds the owner of every local EC and stores the
+// record and its row straight into the owner's arena over NVLink (or into its own).  Space in the remote
+// arena is reserved with ONE remote atomicAdd per CTA tile and owner; all other traffic is plain stores.
+#define ECB_ARENA_HEADER_BYTES 256
+
+struct ArenaTargets {
+  unsigned long long* hdr[ECB_MAX_WORLD];   // [0] records, [1] rows, [2] overflow flag
+  long long* meta[ECB_MAX_WORLD];
+  int2* rows[ECB_MAX_WORLD];
+  unsigned long long cap_ec, cap_rows;
+};
+
+#define ECB_XT_ROWS 2048   // rows of one tile staged in shared memory (more: stored one by one)
+
+// One tile = 256 local ECs.  The tile's records (and rows) are first laid out in shared memory grouped
+// by owner, then each owner's segment goes out with fully coalesced 8-byte stores - NVLink wants long
+// contiguous writes, not one 8-byte word per lane every 40 bytes.
+__global__ void __launch_bounds__(256) ecb_export_to_arenas_kernel(const ExportParams P, const ArenaTargets A) {
+  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];                  // per tile: ECs / rows per owner
+  __shared__ u32 s_off[2 * ECB_MAX_WORLD];                  // ... their exclusive prefix over the owners
+  __shared__ unsigned long long s_base[2 * ECB_MAX_WORLD];  // where the tile's share starts in the owner's arena
+  __shared__ u32 s_drop[ECB_MAX_WORLD];
+  __shared__ u32 s_rows_total;
+  __shared__ __align__(16) long long s_meta[256 * ECB_META_WORDS];
+  __shared__ __align__(16) int2 s_rows[ECB_XT_ROWS];
+  const u32 W = P.world;
+  const u32 tiles = (P.n_ec + blockDim.x - 1) / blockDim.x;
+  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (u32 i = threadIdx.x; i < 2 * W; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+    const u32 e = tile * blockDim.x + threadIdx.x;
+    const bool live = e < P.n_ec;
+    EcbEntry en{};
+    u32 owner = 0, len = 0, idx = 0, roff = 0;
+    if (live) {
+      en = P.table[P.ec_slot[e]];
+      owner = ecb_owner_of(Key128{en.key_lo, en.key_hi}, W);
+      len = P.row_len[e];
+      idx = atomicAdd(&s_cnt[owner], 1u);
+      roff = atomicAdd(&s_cnt[W + owner], len);
+    }
+    __syncthreads();
+    if (threadIdx.x < W) {   // reserve space in the owners' arenas: one remote atomic per owner and area
+      const u32 o = threadIdx.x;
+      const u32 ce = s_cnt[o], cr = s_cnt[W + o];
+      s_drop[o] = 0u;
+      if (ce) {
+        const unsigned long long be = atomicAdd(A.hdr[o] + 0, (unsigned long long)ce);
+        const unsigned long long br = atomicAdd(A.hdr[o] + 1, (unsigned long long)cr);
+        s_base[o] = be;
+        s_base[W + o] = br;
+        if (be + ce > A.cap_ec || br + cr > A.cap_rows) {
+          atomicExch(A.hdr[o] + 2, 1ull);
+          s_drop[o] = 1u;
+        }
+      }
+    }
+    if (threadIdx.x == 32) {   // meanwhile: tile-local offsets of the owners' segments
+      u32 ae = 0, ar = 0;
+      for (u32 o = 0; o < W; ++o) {
+        s_off[o] = ae;
+        s_off[W + o] = ar;
+        ae += s_cnt[o];
+        ar += s_cnt[W + o];
+      }
+      s_rows_total = ar;
+    }
+    __syncthreads();
+    const bool stage_rows = s_rows_total <= ECB_XT_ROWS;
+    if (live && !s_drop[owner]) {
+      const unsigned long long rat = s_base[W + owner] + roff;
+      long long* m = s_meta + (size_t)(s_off[owner] + idx) * ECB_META_WORDS;
+      m[0] = (long long)en.key_lo;
+      m[1] = (long long)en.key_hi;
+      m[2] = (long long)en.first;
+      m[3] = (long long)(((u64)(en.countm1 + 1u) << 32) | len);
+      m[4] = (long long)rat;
+      const uint2* src = P.arena + P.row_off[e];
+      if (stage_rows) {
+        int2* dst = s_rows + s_off[W + owner] + roff;
+        for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+      } else {
+        int2* dst = A.rows[owner] + rat;
+        for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+      }
+    }
+    __syncthreads();
+    for (u32 o = 0; o < W; ++o) {
+      if (s_cnt[o] == 0u || s_drop[o]) continue;
+      const u32 n_words = s_cnt[o] * ECB_META_WORDS;
+      const long long* src = s_meta + (size_t)s_off[o] * ECB_META_WORDS;
+      long long* dst = A.meta[o] + s_base[o] * ECB_META_WORDS;
+      for (u32 w = threadIdx.x; w < n_words; w += blockDim.x) dst[w] = src[w];
+      if (stage_rows) {
+        const u32 n_rows = s_cnt[W + o];
+        const long long* rsrc = reinterpret_cast<const long long*>(s_rows + s_off[W + o]);
+        long long* rdst = reinterpret_cast<long long*>(A.rows[o] + s_base[W + o]);
+        for (u32 w = threadIdx.x; w < n_rows; w += blockDim.x) rdst[w] = rsrc[w];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 struct ImportParams {
   const long long* meta;
   u32 n_rec;

@@ -70,32 +70,68 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     if cur is not None:
         local.set_stream(cur)
     ph = _Phases(device)
-    meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
-    ph.mark("export")
-
-    # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
-    # one all-gather carries every rank's partition sizes and its pushed position range
-    info = torch.tensor(list(ec_counts) + list(row_counts) + [min_base if max_end > min_base else (1 << 62), max_end],
-                        dtype=torch.int64, device=device)
-    gathered = [torch.empty_like(info) for _ in range(world)]
-    dist.all_gather(gathered, info, group=group)
-    g = torch.stack(gathered).tolist()
     me = dist.get_rank(group)
-    recv_ec = [g[src][me] for src in range(world)]
-    recv_rows = [g[src][world + me] for src in range(world)]
-    g_min = min(row[2 * world] for row in g)
-    g_max = max(row[2 * world + 1] for row in g)
-    meta_in = torch.empty((sum(recv_ec), 5), dtype=torch.int64, device=device)
-    rows_in = torch.empty((sum(recv_rows), 2), dtype=torch.int32, device=device)
-    dist.all_to_all_single(meta_in, meta, output_split_sizes=recv_ec, input_split_sizes=ec_counts, group=group)
-    dist.all_to_all_single(rows_in, rows, output_split_sizes=recv_rows, input_split_sizes=row_counts, group=group)
-
-    ph.mark("all_to_all")
-    owner = make_owner()
-    if cur is not None:
+    p2p = (device.type == "cuda" and world > 1 and hasattr(local, "export_to_arenas")
+           and os.environ.get("ECB_EXCHANGE", "p2p") != "nccl")
+    if p2p:
+        # ---- fused partition + dispatch: every local EC is stored straight into its owner's arena
+        # over NVLink by ONE kernel (peer memory mapped through CUDA IPC); no staging, no all-to-all
+        owner = make_owner()
         owner.set_stream(cur)
-    owner.import_entries(meta_in, rows_in, recv_ec, recv_rows)
-    ph.mark("import")
+        st = local.stats()
+        arena = getattr(owner, "_exchange_arena", None)
+        if arena is not None:
+            owner.arena_reset()
+        info = torch.tensor([st["table_used"], st["row_entries"], 0 if arena is None else arena["cap_ec"],
+                             0 if arena is None else arena["cap_rows"]], dtype=torch.int64, device=device)
+        gathered = [torch.empty_like(info) for _ in range(world)]
+        dist.all_gather(gathered, info, group=group)     # also the barrier between "reset" and "store"
+        g = torch.stack(gathered).tolist()
+        need_ec = 2 * max(r[0] for r in g) + 1024
+        need_rows = 2 * max(r[1] for r in g) + 1024
+        if any(r[2] < need_ec // 2 + 512 or r[3] < need_rows // 2 + 512 for r in g) or arena is None:
+            if arena is not None:
+                raise RuntimeError("exchange arena too small for this input; create the owner context per job")
+            handle, base = owner.arena_create(need_ec, need_rows)
+            hs = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+            dist.all_gather(hs, torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device), group=group)
+            bases = [base if r == me else owner.arena_open_peer(bytes(hs[r].cpu().tolist())) for r in range(world)]
+            arena = {"bases": bases, "cap_ec": need_ec, "cap_rows": need_rows}
+            owner._exchange_arena = arena
+            dist.barrier(group=group)                     # every arena exists and is zeroed
+        ph.mark("setup")
+        min_base, max_end = local.export_to_arenas(arena["bases"], arena["cap_ec"], arena["cap_rows"])
+        ph.mark("export+store")
+        span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
+        dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)   # the barrier between "store" and "merge"
+        g_min, g_max = -int(span[0].item()), int(span[1].item())
+        owner.import_arena()
+        ph.mark("import")
+    else:
+        meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
+        ph.mark("export")
+
+        # ---- all-to-all of the hash-partitioned local ECs -------------------------------------------
+        # one all-gather carries every rank's partition sizes and its pushed position range
+        info = torch.tensor(list(ec_counts) + list(row_counts) + [min_base if max_end > min_base else (1 << 62), max_end],
+                            dtype=torch.int64, device=device)
+        gathered = [torch.empty_like(info) for _ in range(world)]
+        dist.all_gather(gathered, info, group=group)
+        g = torch.stack(gathered).tolist()
+        recv_ec = [g[src][me] for src in range(world)]
+        recv_rows = [g[src][world + me] for src in range(world)]
+        g_min = min(row[2 * world] for row in g)
+        g_max = max(row[2 * world + 1] for row in g)
+        meta_in = torch.empty((sum(recv_ec), 5), dtype=torch.int64, device=device)
+        rows_in = torch.empty((sum(recv_rows), 2), dtype=torch.int32, device=device)
+        dist.all_to_all_single(meta_in, meta, output_split_sizes=recv_ec, input_split_sizes=ec_counts, group=group)
+        dist.all_to_all_single(rows_in, rows, output_split_sizes=recv_rows, input_split_sizes=row_counts, group=group)
+        ph.mark("all_to_all")
+        owner = make_owner()
+        if cur is not None:
+            owner.set_stream(cur)
+        owner.import_entries(meta_in, rows_in, recv_ec, recv_rows)
+        ph.mark("import")
 
     # ---- global EC ids from the OR-ed first-occurrence bitmap ------------------------------------
     if g_max <= g_min:

@@ -94,6 +94,7 @@ typedef struct ecb_stats {
   int64_t overflow_reads; /* reads that had to be replayed after a table growth                   */
   int64_t h2d_bytes;      /* bytes copied host->device since create/reset                         */
   int64_t d2h_bytes;      /* bytes copied device->host since create/reset                         */
+  int64_t row_entries;    /* (target, mask) pairs reserved in the row arena (upper bound of nnz)   */
 } ecb_stats;
 
 /* Library/ABI version (major*1000 + minor). */
@@ -181,6 +182,23 @@ int ecb_export_partition(ecb_ctx* ctx, int world, ecb_export* out);
 /* Merge n_parts received partitions (concatenated, in source-rank order) into this OWNER context. */
 int ecb_import_entries(ecb_ctx* ctx, const int64_t* meta_device, const int32_t* rows_device,
                        const int64_t* part_ec_counts, const int64_t* part_row_counts, int n_parts);
+
+/* ---- fused partition + dispatch over peer memory (replaces steps 1-3 when the ranks can map each
+ * other's memory: one process per GPU on an NVLink / NVSwitch box) ------------------------------------
+ * Each rank creates an ARENA on its OWNER context (device memory from cudaMalloc, exportable through
+ * CUDA IPC), hands the 64-byte IPC handle to its peers and maps theirs.  ecb_export_to_arenas on the
+ * LOCAL context then finds the owner of every local EC and stores record and row directly into the
+ * owner's arena over NVLink (one remote atomicAdd per CTA tile and owner reserves the space), and
+ * ecb_import_arena on the owner merges what arrived.  The caller brackets the stores with barriers:
+ *     ecb_arena_reset (every rank) - barrier - ecb_export_to_arenas - barrier - ecb_import_arena.
+ * arena_bases[r] = base address of rank r's arena as seen from THIS process (own base for r == rank). */
+int ecb_arena_create(ecb_ctx* owner_ctx, int64_t cap_records, int64_t cap_rows, void* ipc_handle_out /* 64 bytes */,
+                     void** base_out);
+int ecb_arena_open_peer(ecb_ctx* owner_ctx, const void* ipc_handle /* 64 bytes */, void** base_out);
+int ecb_arena_reset(ecb_ctx* owner_ctx);
+int ecb_export_to_arenas(ecb_ctx* local_ctx, int world, void* const* arena_bases, int64_t cap_records,
+                         int64_t cap_rows, int64_t* min_base, int64_t* max_end);
+int ecb_import_arena(ecb_ctx* owner_ctx);
 
 /* Set the first-occurrence bits of the ECs this context owns in bitmap[n_words] (bit i = order key
  * min_base + i).  The caller zero-fills the bitmap and all-reduces it afterwards. */

@@ -325,7 +325,7 @@ def test_exchange_primitives_single_gpu(native):
     want = _oracle(cols)
     dev = torch.device("cuda", 0)
     from alntools_b200 import multi_gpu
-    for world in (1, 2, 3):
+    for world, arenas in ((1, False), (2, False), (3, False), (2, True), (3, True)):
         cuts = multi_gpu.shard_bounds(rg, world)
         exports = []
         locals_ = []
@@ -334,9 +334,18 @@ def test_exchange_primitives_single_gpu(native):
             lb = native.EcBuilder(4000, 2, alignments_hint=b - a)
             lb.push(np.ascontiguousarray(rg[a:b]), np.ascontiguousarray(tg[a:b]), np.ascontiguousarray(hp[a:b]), order_base=a)
             locals_.append(lb)
-            exports.append(lb.export_partition(world))
+            if not arenas:
+                exports.append(lb.export_partition(world))
         owners = []
-        for o in range(world):   # what all_to_all would deliver to owner o
+        if arenas:   # fused partition + store into the owners' arenas (here all in one process, no IPC)
+            cap_ec, cap_rows = 2 * len(want[3]) + 64, 2 * len(want[1]) + 64
+            owners = [native.EcBuilder(4000, 2, alignments_hint=len(rg)) for _ in range(world)]
+            bases = [ob.arena_create(cap_ec, cap_rows)[1] for ob in owners]
+            for lb in locals_:
+                lb.export_to_arenas(bases, cap_ec, cap_rows)
+            for ob in owners:
+                ob.import_arena()
+        for o in range(world if not arenas else 0):   # what all_to_all would deliver to owner o
             metas, rows, ecn, rown = [], [], [], []
             for src in range(world):
                 meta, row, ec_counts, row_counts, _, _ = exports[src]
