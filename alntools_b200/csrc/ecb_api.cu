@@ -59,6 +59,9 @@ struct ecb_ctx {
   u32 n_ec = 0;                  // host copy after the last sync
   // staging
   DevBuf st_rg, st_tg, st_hp, st_cell;
+  DevBuf st2_rg, st2_tg, st2_hp, st2_cell;   // second staging set of pipelined host pushes
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr};
   DevBuf overflow_bits;
   DevBuf scan_partials;  // u64 block sums + 1 total
   // push bookkeeping
@@ -618,19 +621,11 @@ int ecb_set_stream(ecb_ctx* c, void* cuda_stream) {
   return ECB_OK;
 }
 
-int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, const int32_t* hap_idx,
-             const int32_t* cell_idx, int64_t n, int64_t order_base, int drop_last_group, int on_device) {
-  if (!c) return ECB_ERR_INVALID;
-  if (n < 0 || order_base < 0) return fail(c, ECB_ERR_INVALID, "negative n or order_base");
-  if (n > 0x7FFFFFFFll - 8192) return fail(c, ECB_ERR_LIMIT, "a push is limited to 2^31-8192 alignments; split it");
-  if (n > 0 && (!read_group || !target_idx || !hap_idx)) return fail(c, ECB_ERR_INVALID, "NULL column");
-  if (c->with_cells && n > 0 && !cell_idx) return fail(c, ECB_ERR_INVALID, "context has cells but cell_idx is NULL");
-  if (!c->with_cells && cell_idx) return fail(c, ECB_ERR_INVALID, "cell_idx given but context was created without cells");
-  CK(cudaSetDevice(c->device));
-  if (!c->table_slots) CKR(init_table(c, n));
-  const u32 push_id = c->push_count++;
-  if (n == 0) return ECB_OK;
-
+// One launch sequence over one contiguous piece of columns (the whole push, or one piece of a
+// pipelined host push).
+static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, const int32_t* hap_idx,
+                    const int32_t* cell_idx, int64_t n, int64_t order_base, int drop_last_group, int on_device,
+                    u32 push_id) {
   CK(cudaEventRecord(c->ev[0], c->stream));
   const int32_t *rg = read_group, *tg = target_idx, *hp = hap_idx, *cell = cell_idx;
   const size_t col_bytes = (size_t)n * 4;
@@ -729,6 +724,73 @@ int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, c
   c->stats.table_slots = c->table_slots;
   c->stats.table_used = c->n_ec;
   return ECB_OK;
+}
+
+// Host columns of a large push are sent in read-aligned pieces on a second stream, two staging sets
+// deep, so that the copy of piece i+1 runs while piece i is grouped and harvested.  The pieces share
+// the push id (the "file" of the per-cell path) and only the last one drops the last read.
+#define ECB_PIPE_PIECE (8ll << 20)   // alignments per piece (96 MB of columns)
+
+static int push_pipelined(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int32_t* hp, const int32_t* cell,
+                          int64_t n, int64_t order_base, int drop_last_group, u32 push_id) {
+  std::vector<int64_t> cut{0};
+  while (cut.back() < n) {
+    int64_t b = std::min<int64_t>(n, cut.back() + ECB_PIPE_PIECE);
+    while (b < n && rg[b] == rg[b - 1]) ++b;   // never split a read
+    cut.push_back(b);
+  }
+  const int pieces = (int)cut.size() - 1;
+  int64_t longest = 0;
+  for (int i = 0; i < pieces; ++i) longest = std::max(longest, cut[i + 1] - cut[i]);
+  if (!c->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->copy_done[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->copy_done[1], cudaEventDisableTiming));
+  }
+  DevBuf* set[2][4] = {{&c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell}, {&c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell}};
+  const int ncols = cell ? 4 : 3;
+  for (int k = 0; k < 2; ++k)
+    for (int j = 0; j < ncols; ++j) CKR(ensure(c, *set[k][j], (size_t)longest * 4));
+  CK(cudaStreamSynchronize(c->stream));   // the staging sets exist before the copy stream touches them
+  const int32_t* src[4] = {rg, tg, hp, cell};
+  auto send = [&](int i) -> int {
+    const size_t bytes = (size_t)(cut[i + 1] - cut[i]) * 4;
+    for (int j = 0; j < ncols; ++j)
+      CK(cudaMemcpyAsync(set[i & 1][j]->p, src[j] + cut[i], bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    CK(cudaEventRecord(c->copy_done[i & 1], c->copy_stream));
+    c->stats.h2d_bytes += (int64_t)bytes * ncols;
+    return ECB_OK;
+  };
+  CKR(send(0));
+  for (int i = 0; i < pieces; ++i) {
+    if (i + 1 < pieces) CKR(send(i + 1));   // its staging set was last read by piece i-1, which has completed
+    CK(cudaStreamWaitEvent(c->stream, c->copy_done[i & 1], 0));
+    const int rc = push_one(c, (const int32_t*)set[i & 1][0]->p, (const int32_t*)set[i & 1][1]->p,
+                            (const int32_t*)set[i & 1][2]->p, cell ? (const int32_t*)set[i & 1][3]->p : nullptr,
+                            cut[i + 1] - cut[i], order_base + cut[i], drop_last_group && i + 1 == pieces, 1, push_id);
+    if (rc != ECB_OK) {
+      cudaStreamSynchronize(c->copy_stream);
+      return rc;
+    }
+  }
+  return ECB_OK;
+}
+
+int ecb_push(ecb_ctx* c, const int32_t* read_group, const int32_t* target_idx, const int32_t* hap_idx,
+             const int32_t* cell_idx, int64_t n, int64_t order_base, int drop_last_group, int on_device) {
+  if (!c) return ECB_ERR_INVALID;
+  if (n < 0 || order_base < 0) return fail(c, ECB_ERR_INVALID, "negative n or order_base");
+  if (n > 0x7FFFFFFFll - 8192) return fail(c, ECB_ERR_LIMIT, "a push is limited to 2^31-8192 alignments; split it");
+  if (n > 0 && (!read_group || !target_idx || !hap_idx)) return fail(c, ECB_ERR_INVALID, "NULL column");
+  if (c->with_cells && n > 0 && !cell_idx) return fail(c, ECB_ERR_INVALID, "context has cells but cell_idx is NULL");
+  if (!c->with_cells && cell_idx) return fail(c, ECB_ERR_INVALID, "cell_idx given but context was created without cells");
+  CK(cudaSetDevice(c->device));
+  if (!c->table_slots) CKR(init_table(c, n));
+  const u32 push_id = c->push_count++;
+  if (n == 0) return ECB_OK;
+  if (!on_device && n >= 2 * ECB_PIPE_PIECE)
+    return push_pipelined(c, read_group, target_idx, hap_idx, cell_idx, n, order_base, drop_last_group, push_id);
+  return push_one(c, read_group, target_idx, hap_idx, cell_idx, n, order_base, drop_last_group, on_device, push_id);
 }
 
 int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
@@ -1217,13 +1279,20 @@ int ecb_destroy(ecb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->big_list, &c->count_of,
-                    &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->overflow_bits,
+                    &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell,
+                    &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,
                     &c->r_n_data, &c->r_cell_order, &c->x_meta, &c->x_rows, &c->x_counts, &c->x_base};
   for (DevBuf* b : bufs) release(c, *b);
   cells_release(c);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->copy_done[0]);
+    cudaEventDestroy(c->copy_done[1]);
+  }
   for (void* p : c->xa_opened) cudaIpcCloseMemHandle(p);
   if (c->xa_base) cudaFree(c->xa_base);
   if (c->d_ctr) cudaFree(c->d_ctr);

@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--table-slots", type=int, default=0)
     ap.add_argument("--grid-ctas", type=int, default=0)
     ap.add_argument("--hot-cache", type=int, default=1)
+    ap.add_argument("--chunk-len", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -297,6 +298,8 @@ def main():
     if args.grid_ctas:
         opts["grid_ctas"] = args.grid_ctas
     opts["hot_cache"] = args.hot_cache
+    if args.chunk_len:
+        opts["chunk_len"] = args.chunk_len
     stream = torch.cuda.current_stream()
 
     def barrier():
