@@ -5,27 +5,28 @@
 // by read, collapse duplicate tids, ec[key] += 1) and the ordering half of :680-698 (EC id = rank of
 // the key's first occurrence), on int32 columns.
 //
-// Shape of the kernel (HBM-bound integer work, no tensor cores; the binding resource after the
-// column stream is instruction issue, so the design minimises warp instructions per alignment):
-//   * one persistent CTA per SM (grid = 148), 32 warps; every WARP owns one contiguous chunk of the
-//     alignment stream and walks it on its own — no CTA-wide barrier, no cross-warp carry;
+// Shape of the kernel (HBM-bound integer work, no tensor cores; after the column stream the binding
+// resources are the latency of the random table sectors and the dependent chains inside a window):
+//   * one persistent CTA per SM (grid = 148), 32 warps; every WARP walks chunks of the alignment
+//     stream on its own — no CTA-wide barrier, no cross-warp carry;
 //   * a warp looks at a WINDOW of 32 consecutive alignments (lane = alignment) that always starts at
-//     a read start.  One ballot of the "last alignment of its read" flags gives every lane its read
-//     start, one __match_any_sync on the element code finds duplicate (target, haplotype) pairs
-//     inside a read, a segmented shuffle scan with only ceil(log2(longest read in the window))
-//     steps adds the 128-bit element mixes of a read (commutative set hash -> no per-read sort).
-//     The window then advances to the first alignment after its last COMPLETE read, so no read ever
-//     straddles two windows; the columns of the next window are requested before the current one
-//     is processed and the lines further ahead are pulled into L2 by prefetches, so the dependent
-//     window address never waits for HBM.  Reads longer than a window take a warp-cooperative path;
-//   * a read is owned by the warp in whose chunk it STARTS; the owner runs past its chunk end until
-//     the read closes, the next warp starts at the first read start inside its chunk;
-//   * closed reads first try the per-CTA shared-memory cache of hot ECs (4096 entries; the top few
-//     thousand ECs carry more than half of the reads).  Misses are parked in a per-warp
-//     shared-memory queue — with an L2 prefetch of their table sector — and inserted into the HBM
-//     table 32 at a time with a full warp: one 256-bit sector load per probe, a 128-bit atomicCAS
-//     only when the slot looks empty, RED.ADD on the count and atomicMin on the first-occurrence key
-//     only when it can lower it.  The cache is flushed when the CTA has finished its chunks.
+//     a read start.  One ballot of the read_group changes gives every lane its read start (positions
+//     beyond the push hold a sentinel), duplicate (target, haplotype) pairs inside a read are found
+//     with shuffled compares (match_any only for windows with reads longer than 8), a segmented
+//     shuffle scan with only ceil(log2(longest read in the window)) steps adds the 128-bit element
+//     mixes of a read (commutative set hash -> no per-read sort).  The window then advances to its
+//     last read start, so no read ever straddles two windows; the columns of the next window are
+//     requested before the current one is inserted and the lines further ahead are pulled into L2 by
+//     prefetches.  Reads that fill a whole window take a warp-cooperative path;
+//   * a read is owned by the chunk it STARTS in (chunks are handed out by a global counter); the
+//     owner runs past the chunk end until the read closes;
+//   * closed reads first try the per-CTA shared-memory cache of hot ECs (4096 entries, lock-free hit
+//     path, keys admitted on their second miss).  Misses are parked in a per-warp shared-memory queue
+//     - with an L2 prefetch of their table sector - and inserted into the HBM table 64 at a time, two
+//     per lane: one 256-bit sector load per probe, a 128-bit atomicCAS only when the slot looks empty,
+//     RED.ADD on the count and atomicMin on the first-occurrence key only when it can lower it.  The
+//     first load and the first CAS of both reads of a lane are in flight together: a warp pays for the
+//     slowest lane's chain of round trips once per batch.  The cache is flushed when the CTA is done.
 #pragma once
 #include "ecb_common.cuh"
 
