@@ -226,7 +226,7 @@ int init_table(ecb_ctx* c, int64_t first_n = 0) {
   CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
   CKR(alloc_ec_arrays(c, c->table_slots, false));
   if (c->with_cells) {
-    u64 tw = c->opt_pair_slots > 0 ? (u64)c->opt_pair_slots : std::max<u64>(1u << 16, (u64)c->hint / 2);
+    u64 tw = c->opt_pair_slots > 0 ? (u64)c->opt_pair_slots : std::max<u64>(1u << 16, (u64)c->hint / 8);
     c->ttable_slots = std::max<u32>(1u << 10, pow2_ceil(tw));
     CKR(ensure(c, c->ttable, (size_t)c->ttable_slots * sizeof(EcbEntry)));
     CK(cudaMemsetAsync(c->ttable.p, 0xFF, (size_t)c->ttable_slots * sizeof(EcbEntry), c->stream));
@@ -657,8 +657,14 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     if (projected * 5 > (u64)c->table_slots * 3 && c->table_slots < (1u << 31)) CKR(grow_table(c, pow2_ceil(projected * 2)));
   }
   if (c->with_cells) {
-    // the triple table must be able to absorb one new entry per alignment without filling up
-    u64 need = ((u64)c->n_triples + (u64)n) * 2;
+    // the triple table must be able to absorb one new entry per READ of this push without filling up
+    // (it has no replay path): count the reads first - one pass over read_group, 4 bytes per alignment
+    CK(cudaMemsetAsync(&c->d_ctr->scratch[4], 0, sizeof(u32), c->stream));
+    ecb_count_reads_kernel<<<grid_for((u64)n, 1024, c->sm_count * 4), 256, 0, c->stream>>>(rg, (int)n, &c->d_ctr->scratch[4]);
+    LAUNCH_CHECK("count_reads");
+    CKR(sync_counters(c));
+    const u64 reads = c->h_ctr->scratch[4];
+    u64 need = ((u64)c->n_triples + reads) * 2;
     if (need > c->ttable_slots) CKR(rebuild_triple_table(c, pow2_ceil(need), nullptr));
   }
   const size_t ov_words = ((size_t)n + 31) / 32;

@@ -677,6 +677,15 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
 }
 
+// Number of reads (runs of equal read_group) in a push.
+__global__ void __launch_bounds__(256) ecb_count_reads_kernel(const int32_t* __restrict__ rg, int n, u32* out) {
+  u32 cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    cnt += (i == 0 || rg[i] != rg[i - 1]) ? 1u : 0u;
+  cnt = __reduce_add_sync(ECB_FULL, cnt);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, cnt);
+}
+
 // Key of the read that starts at offset s, computed serially (replay / verification path).
 __device__ inline Key128 ecb_serial_read_key(const int32_t* rg, const int32_t* tg, const int32_t* hp, int n,
                                              int s, int* len_out) {
