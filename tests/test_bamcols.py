@@ -233,3 +233,23 @@ def test_range_file_matches_the_reference(case, tmp_path):
     utils.write_range_file(out, list(tables.main_targets.keys()), tables.haplotypes, refs, lo, hi)
     with open(out) as a, open(os.path.join(GOLDEN, case["range"])) as b:
         assert a.read() == b.read()
+
+
+def test_randomised_small_bams(tmp_path, monkeypatch):
+    """Random small BAMs (names with blanks, every filter combination, tiny BGZF blocks, forced thread
+    splits) through the native emitter and the record-level Python emitter."""
+    rng = np.random.default_rng(77)
+    flags = [0, 16, 4, 20, 1 | 2 | 64, 1 | 2 | 128, 1 | 64, 1 | 2 | 64 | 16, 1 | 2 | 64 | 4, 256, 2048]
+    for case in range(25):
+        n = int(rng.integers(1, 600))
+        alns, read = [], 0
+        for _ in range(n):
+            if rng.random() < 0.4:
+                read += 1
+            name = ("r%d" % read) if read % 4 else ("r%d tail %d" % (read, int(rng.integers(0, 3))))
+            tid = int(rng.integers(0, len(REFS)))
+            alns.append((name, int(rng.choice(flags)), tid, int(rng.integers(0, 500)),
+                         tid if rng.random() < 0.8 else int(rng.integers(0, len(REFS))), int(rng.choice([-1, 0, 77]))))
+        monkeypatch.setenv("BAMCOLS_GRAIN", str(int(rng.choice([1, 5, 4096]))))
+        path = _write(tmp_path, alns, "rand%d.bam" % case, block_payload=int(rng.choice([64, 200, 5000])))
+        _same_single(path, n_threads=int(rng.choice([1, 2, 5])))

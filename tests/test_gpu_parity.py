@@ -387,3 +387,35 @@ def test_exchange_primitives_single_gpu(native):
         assert np.array_equal(counts.cpu().numpy(), want[3])
         for b in locals_ + owners:
             b.close()
+
+
+def test_randomised_read_shapes_and_launch_geometry(native):
+    """Many small random inputs against the oracle: read lengths around the 32-alignment window and the
+    8-alignment shuffle-de-dup limit, heavy duplication, tiny target spaces (hot keys), and random work
+    chunk lengths / grids / cache settings, so that chunk, window and batch boundaries fall everywhere."""
+    rng = np.random.default_rng(2024)
+    length_pools = [
+        [1], [1, 2], [1, 2, 3, 4], [7, 8, 9], [1, 8, 9, 16, 17], [30, 31, 32, 33, 34], [1, 31, 32, 33, 63, 64, 65],
+        [1, 2, 3, 100, 200], [1, 1, 1, 1, 1500],
+    ]
+    for case in range(48):
+        pool = length_pools[case % len(length_pools)]
+        n_reads = int(rng.integers(1, 4000))
+        lens = rng.choice(pool, n_reads)
+        n_targets = int(rng.choice([1, 3, 50, 5000]))
+        n_haps = int(rng.choice([1, 2, 8]))
+        rg = np.repeat(np.arange(n_reads, dtype=np.int32) * 3 + 5, lens)      # any increasing labels
+        n = len(rg)
+        tg = rng.integers(0, n_targets, n).astype(np.int32)
+        hp = rng.integers(0, n_haps, n).astype(np.int32)
+        if case % 3 == 0:                                                     # runs of verbatim duplicates
+            rep = rng.integers(0, 4, n) == 0
+            tg[1:][rep[1:]] = tg[:-1][rep[1:]]
+            hp[1:][rep[1:]] = hp[:-1][rep[1:]]
+        cols = {"read_group": rg, "target_idx": tg, "hap_idx": hp}
+        opts = {"chunk_len": int(rng.choice([0, 32, 64, 160, 1024])), "grid_ctas": int(rng.choice([0, 1, 2, 7])),
+                "hot_cache": int(rng.integers(0, 2))}
+        if case % 5 == 0:
+            opts["table_slots"] = 1024                                        # growth + replay
+        got, _ = _run(native, cols, n_targets, n_haps, **opts)
+        _assert_same(got, _oracle(cols))
