@@ -718,6 +718,20 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   CK(cudaEventRecord(c->ev[3], c->stream));
   CKR(harvest_new_rows(c, rg, tg, hp, n, e_before, c->n_ec));
   CK(cudaEventRecord(c->ev[4], c->stream));
+  if (c->verify_keys) {
+    VerifyParams V{};
+    V.rg = rg; V.tg = tg; V.hp = hp; V.n = (int)n; V.drop_last = drop_last_group;
+    V.table = (const EcbEntry*)c->table.p;
+    V.mask = c->table_slots - 1;
+    V.row_len = (const u32*)c->row_len.p;
+    V.row_off = (const u32*)c->row_off.p;
+    V.arena = (const uint2*)c->arena.p;
+    V.ctr = c->d_ctr;
+    ecb_verify_kernel<<<grid_for((u64)n, 256, c->sm_count * 16), 256, 0, c->stream>>>(V);
+    LAUNCH_CHECK("verify");
+    CKR(sync_counters(c));
+    CKR(check_device_error(c));
+  }
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.group_ms = ms;

@@ -7,10 +7,6 @@ typedef unsigned int u32;
 typedef unsigned long long u64;
 
 #define ECB_FULL 0xFFFFFFFFu
-#define ECB_TILE_THREADS 256
-#define ECB_ITEMS 4
-#define ECB_TILE (ECB_TILE_THREADS * ECB_ITEMS)
-#define ECB_WARPS (ECB_TILE_THREADS / 32)
 #define ECB_MAX_PROBE 192
 #define ECB_NONE 0xFFFFFFFFu
 
@@ -65,15 +61,6 @@ __device__ __forceinline__ void load_entry_cg(const EcbEntry* e, Key128& key, u6
                : "l"(e));
   countm1 = (u32)w3;
   aux = (u32)(w3 >> 32);
-}
-
-// Streaming (read-once) 128-bit column load: do not keep the line in L1.
-__device__ __forceinline__ int4 ld_stream_int4(const int32_t* p) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
 }
 
 __device__ __forceinline__ u32 fmix32(u32 h) {

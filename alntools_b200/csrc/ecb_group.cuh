@@ -57,7 +57,7 @@ struct GroupParams {
   const int32_t* hp;
   const int32_t* cell;
   int n;           // alignments in this push
-  int chunk_len;   // alignments per CTA, multiple of ECB_TILE
+  int chunk_len;   // alignments per work chunk, multiple of 32
   u64 order_base;
   int drop_last;
   int use_cache;
@@ -704,6 +704,65 @@ __device__ inline Key128 ecb_serial_read_key(const int32_t* rg, const int32_t* t
   }
   if (len_out) *len_out = j - s;
   return mix_to_key(sum);
+}
+
+// ECB_OPT_VERIFY_KEYS: prove that no two different reads of this push were merged by the 128-bit key.
+// One thread per read: its key is recomputed serially, its EC looked up, and the read's set of
+// (target, haplotype) pairs compared with the EC's row: every pair must be in the row and the number of
+// distinct pairs must equal the number of bits set in the row's masks.  O(k * row) per read - a
+// debugging aid, not part of the streaming path.
+struct VerifyParams {
+  const int32_t* rg;
+  const int32_t* tg;
+  const int32_t* hp;
+  int n;
+  int drop_last;
+  const EcbEntry* table;
+  u32 mask;
+  const u32* row_len;
+  const u32* row_off;
+  const uint2* arena;
+  EcbCounters* ctr;
+};
+
+__global__ void __launch_bounds__(256) ecb_verify_kernel(const VerifyParams P) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < P.n; s += gridDim.x * blockDim.x) {
+    if (s > 0 && P.rg[s] == P.rg[s - 1]) continue;   // not a read start
+    int len = 0;
+    const Key128 key = ecb_serial_read_key(P.rg, P.tg, P.hp, P.n, s, &len);
+    if (P.drop_last && s + len == P.n) continue;
+    u32 slot = ec_slot_hash(key) & P.mask;
+    bool found = false;
+    for (u32 p = 0; p <= P.mask; ++p) {
+      Key128 k;
+      u64 first;
+      u32 cm1, aux;
+      load_entry_cg(P.table + slot, k, first, cm1, aux);
+      if (key_eq(k, key)) {
+        found = true;
+        const uint2* row = P.arena + P.row_off[aux];
+        const u32 rl = P.row_len[aux];
+        u32 bits = 0, distinct = 0;
+        for (u32 j = 0; j < rl; ++j) bits += __popc(row[j].y);
+        bool ok = true;
+        for (int i = s; i < s + len && ok; ++i) {
+          const u32 t = (u32)P.tg[i], h = (u32)P.hp[i];
+          bool seen_before = false;
+          for (int m = s; m < i; ++m) seen_before |= (u32)P.tg[m] == t && (u32)P.hp[m] == h;
+          if (seen_before) continue;
+          ++distinct;
+          bool in_row = false;
+          for (u32 j = 0; j < rl; ++j) in_row |= row[j].x == t && ((row[j].y >> h) & 1u);
+          ok = in_row;
+        }
+        if (!ok || distinct != bits) atomicOr(&P.ctr->error, ECB_DEVERR_VERIFY);
+        break;
+      }
+      if (key_empty(k)) break;
+      slot = (slot + 1) & P.mask;
+    }
+    if (!found) atomicOr(&P.ctr->error, ECB_DEVERR_VERIFY);
+  }
 }
 
 // Replay the reads flagged in overflow_bits after the table has been grown.  One thread per flagged

@@ -59,8 +59,9 @@ enum ecb_option {
   ECB_OPT_PAIR_SLOTS = 3,       /* initial (file, EC, cell) table capacity */
   ECB_OPT_GRID_CTAS = 4,        /* CTAs of the grouping kernel (0 = one persistent CTA per SM) */
   ECB_OPT_HOT_CACHE = 5,        /* 1 (default): per-CTA shared-memory cache of hot ECs in front of the HBM table */
-  ECB_OPT_VERIFY_KEYS = 6,      /* 1: finalize re-derives every read's row and compares it with its
-                                   EC's row, turning a 128-bit hash collision into an error */
+  ECB_OPT_VERIFY_KEYS = 6,      /* 1: every push re-derives each read's set of (target, haplotype) pairs and
+                                   compares it with the row of the EC the read was counted in, turning
+                                   a 128-bit key collision into ECB_ERR_LIMIT (slow; a debugging aid) */
   ECB_OPT_CHUNK_LEN = 7,        /* alignments per work chunk of the grouping kernel (0 = automatic) */
   ECB_OPT_PAGEABLE_RESULTS = 8  /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
                                    cheaper for a context that finalizes once, slower when reused */

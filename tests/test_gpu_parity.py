@@ -419,3 +419,13 @@ def test_randomised_read_shapes_and_launch_geometry(native):
             opts["table_slots"] = 1024                                        # growth + replay
         got, _ = _run(native, cols, n_targets, n_haps, **opts)
         _assert_same(got, _oracle(cols))
+
+
+def test_key_verification_option_finds_no_collision(native):
+    """ECB_OPT_VERIFY_KEYS re-derives every read's element set and compares it with its EC's row: on
+    real-shaped inputs it must pass (no 128-bit key collision) and leave the result unchanged."""
+    from alntools_b200 import synth
+    for n_reads, n_targets, n_haps, mode, dup in ((60000, 3000, 2, "diploid", 0.05), (4000, 500, 8, "heavy", 0.02)):
+        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=9, mode=mode, dup_rate=dup)
+        got, _ = _run(native, cols, n_targets, n_haps, verify_keys=1)
+        _assert_same(got, _oracle(cols))
