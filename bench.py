@@ -213,7 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_diploid_30M", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample-reads", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--bam-sample-reads", type=int, default=8_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table-slots", type=int, default=0)
@@ -222,6 +222,16 @@ def main():
     ap.add_argument("--chunk-len", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly one JSON line: anything libraries print on fd 1 meanwhile (NCCL announces its
+    # version there) is sent to stderr; the real stdout comes back for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -243,7 +253,7 @@ def main():
                 "e2e": {"value": cpu["value"], "unit": "alignments/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -256,8 +266,6 @@ def main():
         raise SystemExit("bench.py needs a B200: there is no CPU path for the EC build")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic shard of this rank (weak scaling: fixed reads per GPU) --------------------------
@@ -456,7 +464,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line["bam_e2e"] = run_bam_e2e(args.workload, args.bam_sample_reads, local_rank)
         line["cpu_baseline"] = run_cpu_arm(args.workload, 2, 0, args.cpu_sample_reads, max_seconds=60.0)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
