@@ -98,6 +98,9 @@ struct bamcols {
   size_t grain = 4096;           // records per worker thread below which no further thread is used
   double phase_s[6] = {0, 0, 0, 0, 0, 0};  // inflate, record hop, validity, read starts, rows, copy-out
   // --rangefile (bam_utils.py:282-286): smallest / largest reference_start of the valid alignments per tid
+  // the first batch of blocks is inflated in the background while the caller builds its header tables
+  std::thread prefetch;
+  int prefetch_rc = 0;
   bool track_ranges = false;
   std::vector<int32_t> range_min, range_max;
   std::string err;
@@ -549,12 +552,14 @@ int bamcols_open(bamcols** out, const char* path, int n_threads) {
   const int rc = read_header(r);
   r->batch_blocks = full_batch;
   if (rc < 0) return bail(rc);
+  r->prefetch = std::thread([r]() { r->prefetch_rc = refill(r); });
   *out = r;
   return BAMCOLS_OK;
 }
 
 void bamcols_close(bamcols* r) {
   if (!r) return;
+  if (r->prefetch.joinable()) r->prefetch.join();
   if (r->file) munmap(const_cast<uint8_t*>(r->file), r->file_size);
   if (r->fd >= 0) close(r->fd);
   delete r;
@@ -634,6 +639,10 @@ int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int3
   if (cells && !cell_idx) return fail(r, BAMCOLS_ERR_INVALID, "per-cell mode needs a cell_idx buffer");
   if (r->tid_target.empty() && !r->ref_names.empty()) return fail(r, BAMCOLS_ERR_INVALID, "bamcols_set_tables was not called");
   *done = 0;
+  if (r->prefetch.joinable()) {
+    r->prefetch.join();
+    if (r->prefetch_rc < 0) return r->prefetch_rc;
+  }
   const int want_mode = cells ? 2 : 1;
   if (r->mode == 0) r->mode = want_mode;
   if (r->mode != want_mode) return fail(r, BAMCOLS_ERR_INVALID, "a reader cannot switch between single-sample and per-cell rules");
