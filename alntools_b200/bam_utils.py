@@ -69,8 +69,7 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
         # native emitter: inflate threads + one record pass, streamed to the GPU in read-aligned chunks
         import torch
         with bamcols.BamColumnReader(bam_filename, n_threads=num_processes) as reader:
-            tables = TargetTables(reader.references, reader.lengths, target_filename)
-            reader.set_tables(tables)
+            tables = reader.build_tables(target_filename)   # native statement of header.TargetTables
             if range_filename is not None:
                 reader.track_ranges(True)
             LOG.info("File parsed in {}, total time: {}".format(utils.format_time(temp_time, time.time()),

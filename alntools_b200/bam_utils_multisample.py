@@ -42,9 +42,10 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
         for bam_file in bam_files:
             with bamcols.BamColumnReader(bam_file) as reader:
                 if tables is None:                            # tables from the first file only (:399)
-                    tables = TargetTables(reader.references, reader.lengths, target_filename)
+                    tables = reader.build_tables(target_filename)
                     references = reader.references
-                reader.set_tables(tables)
+                else:
+                    reader.set_tables(tables)
                 if range_filename is not None:
                     reader.track_ranges(True)
                 c = reader.read_all(cells=cells)

@@ -24,6 +24,12 @@ SIGNATURES = {
     "bamcols_reference_blob": (ctypes.c_int64, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
                                                 ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_set_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "bamcols_build_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
+    "bamcols_tables": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int64),
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                      ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_cells_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_cells_destroy": (None, [ctypes.c_void_p]),
     "bamcols_cells_count": (ctypes.c_int64, [ctypes.c_void_p]),
@@ -113,6 +119,41 @@ class BamColumnReader(object):
         rc = self._lib.bamcols_set_tables(self._h, tt.ctypes.data, th.ctypes.data, len(tt))
         if rc != 0:
             _raise(rc, self._lib.bamcols_last_error(self._h).decode())
+
+    def build_tables(self, target_filename=None):
+        """Header -> TargetTables-compatible object, built natively and installed in this reader."""
+        from collections import OrderedDict
+        from . import utils
+        first = b""
+        if target_filename:
+            ids = utils.parse_targets(target_filename)
+            if len(ids) == 0:                                   # bam_utils.py:577-579
+                utils.get_logger().error("Unable to parse target file")
+                raise SystemExit(-1)
+            first = b"".join(t.encode() + b"\0" for t in ids)
+        rc = self._lib.bamcols_build_tables(self._h, first, len(first))
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(self._h).decode())
+        nt, nh = ctypes.c_int32(), ctypes.c_int32()
+        tp, hp_, a, b, c = (ctypes.c_void_p() for _ in range(5))
+        tl, hl = ctypes.c_int64(), ctypes.c_int64()
+        self._lib.bamcols_tables(self._h, ctypes.byref(nt), ctypes.byref(nh), ctypes.byref(tp), ctypes.byref(tl),
+                                 ctypes.byref(hp_), ctypes.byref(hl), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        n_ref = len(self.references)
+
+        class _Tables(object):
+            pass
+        t = _Tables()
+        names = ctypes.string_at(tp, tl.value).decode().split("\0")[:nt.value] if nt.value else []
+        t.main_targets = OrderedDict(zip(names, range(len(names))))
+        t.haplotypes = ctypes.string_at(hp_, hl.value).decode().split("\0")[:nh.value] if nh.value else []
+        t.tid_target = np.array((ctypes.c_int32 * n_ref).from_address(a.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)
+        t.tid_hap = np.array((ctypes.c_int32 * n_ref).from_address(b.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)
+        cells_ = nt.value * nh.value
+        t.lengths = (np.array((ctypes.c_int32 * cells_).from_address(c.value), dtype=np.int32).reshape(nt.value, nh.value)
+                     if cells_ else np.zeros((nt.value, nh.value), np.int32))
+        t.num_targets, t.num_haplotypes = nt.value, nh.value
+        return t
 
     def emit(self, read_group, target_idx, hap_idx, cell_idx=None, cells=None):
         """Fill the given int32 arrays (numpy or pinned torch tensors) with the next whole reads.

@@ -7,6 +7,7 @@
 // deflate streams, SAM spec 4.1), and one pass over the fixed-offset record fields produces the rows.
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <climits>
@@ -98,6 +99,11 @@ struct bamcols {
   size_t grain = 4096;           // records per worker thread below which no further thread is used
   double phase_s[6] = {0, 0, 0, 0, 0, 0};  // inflate, record hop, validity, read starts, rows, copy-out
   // --rangefile (bam_utils.py:282-286): smallest / largest reference_start of the valid alignments per tid
+  // header tables built natively (bamcols_build_tables)
+  std::string tb_targets;        // main target names, each followed by a NUL, in main-target order
+  std::string tb_haps;           // sorted haplotype names, each followed by a NUL
+  std::vector<int32_t> tb_lengths;  // [n_targets x n_haps]
+  int32_t tb_n_targets = 0, tb_n_haps = 0;
   // the first batch of blocks is inflated in the background while the caller builds its header tables
   std::thread prefetch;
   int prefetch_rc = 0;
@@ -591,6 +597,94 @@ int bamcols_set_tables(bamcols* r, const int32_t* tid_target, const int32_t* tid
                 r->ref_names.size());
   r->tid_target.assign(tid_target, tid_target + n_references);
   r->tid_hap.assign(tid_hap, tid_hap + n_references);
+  return BAMCOLS_OK;
+}
+
+// Header -> tables (alntools/bam_utils.py:561-633; alntools_b200/header.py is the readable statement):
+// every @SQ name is split at its LAST '_' (unless that is its first character) into main target and
+// haplotype; main targets are numbered target-file ids first, then in header order; haplotypes are
+// sorted; lengths[target][haplotype] = reference length.  first_targets: the target file's ids, each
+// followed by a NUL (may be empty).
+int bamcols_build_tables(bamcols* r, const char* first_targets, int64_t first_len) {
+  if (!r || first_len < 0 || (first_len > 0 && !first_targets)) return BAMCOLS_ERR_INVALID;
+  const size_t n = r->ref_names.size();
+  std::unordered_map<std::string, int32_t> target_id;
+  std::vector<const std::string*> target_names;
+  target_id.reserve(n);
+  auto add_target = [&](const std::string& t) -> int32_t {
+    auto it = target_id.find(t);
+    if (it != target_id.end()) return it->second;
+    const int32_t id = (int32_t)target_names.size();
+    auto ins = target_id.emplace(t, id);
+    target_names.push_back(&ins.first->first);
+    return id;
+  };
+  for (int64_t p = 0; p < first_len;) {
+    const size_t l = strnlen(first_targets + p, (size_t)(first_len - p));
+    add_target(std::string(first_targets + p, l));
+    p += (int64_t)l + 1;
+  }
+  std::vector<std::string> haps(n);
+  std::vector<int32_t> tt(n);
+  for (size_t i = 0; i < n; ++i) {
+    const std::string& name = r->ref_names[i];
+    const size_t cut = name.rfind('_');
+    if (cut != std::string::npos && cut > 0) {
+      tt[i] = add_target(name.substr(0, cut));
+      haps[i] = name.substr(cut + 1);
+    } else {
+      tt[i] = add_target(name);
+    }
+  }
+  std::vector<std::string> sorted_haps(haps);
+  std::sort(sorted_haps.begin(), sorted_haps.end());
+  sorted_haps.erase(std::unique(sorted_haps.begin(), sorted_haps.end()), sorted_haps.end());
+  std::unordered_map<std::string, int32_t> hap_id;
+  for (size_t h = 0; h < sorted_haps.size(); ++h) hap_id.emplace(sorted_haps[h], (int32_t)h);
+  const size_t T = target_names.size(), H = sorted_haps.size();
+  std::vector<int32_t> th(n);
+  std::vector<int32_t> owner(T * H, -1);
+  r->tb_lengths.assign(T * H, 0);
+  for (size_t i = 0; i < n; ++i) {
+    th[i] = hap_id[haps[i]];
+    int32_t& o = owner[(size_t)tt[i] * H + (size_t)th[i]];
+    if (o >= 0)
+      return fail(r, BAMCOLS_ERR_INVALID, "@SQ names '%s' and '%s' map to the same (target, haplotype)",
+                  r->ref_names[(size_t)o].c_str(), r->ref_names[i].c_str());
+    o = (int32_t)i;
+    r->tb_lengths[(size_t)tt[i] * H + (size_t)th[i]] = r->ref_lengths[i];
+  }
+  r->tb_targets.clear();
+  for (const std::string* t : target_names) {
+    r->tb_targets.append(*t);
+    r->tb_targets.push_back('\0');
+  }
+  r->tb_haps.clear();
+  for (const std::string& h : sorted_haps) {
+    r->tb_haps.append(h);
+    r->tb_haps.push_back('\0');
+  }
+  r->tb_n_targets = (int32_t)T;
+  r->tb_n_haps = (int32_t)H;
+  r->tid_target = std::move(tt);
+  r->tid_hap = std::move(th);
+  return BAMCOLS_OK;
+}
+
+int bamcols_tables(const bamcols* r, int32_t* n_targets, int32_t* n_haps, const char** targets, int64_t* targets_len,
+                   const char** haps, int64_t* haps_len, const int32_t** tid_target, const int32_t** tid_hap,
+                   const int32_t** lengths) {
+  if (!r || !n_targets || !n_haps || !targets || !targets_len || !haps || !haps_len || !tid_target || !tid_hap || !lengths)
+    return BAMCOLS_ERR_INVALID;
+  *n_targets = r->tb_n_targets;
+  *n_haps = r->tb_n_haps;
+  *targets = r->tb_targets.data();
+  *targets_len = (int64_t)r->tb_targets.size();
+  *haps = r->tb_haps.data();
+  *haps_len = (int64_t)r->tb_haps.size();
+  *tid_target = r->tid_target.data();
+  *tid_hap = r->tid_hap.data();
+  *lengths = r->tb_lengths.data();
   return BAMCOLS_OK;
 }
 

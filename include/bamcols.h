@@ -59,6 +59,16 @@ int64_t bamcols_reference_blob(const bamcols* r, const char** names, const int32
  * (alntools/bam_utils.py:561-633).  Copied. */
 int bamcols_set_tables(bamcols* r, const int32_t* tid_target, const int32_t* tid_hap, int n_references);
 
+/* The same tables built natively (alntools/bam_utils.py:561-633): main targets = target-file ids first
+ * (first_targets: each id followed by a NUL; may be empty), then unseen targets in header order; a name is
+ * split at its LAST '_' unless that is its first character; haplotypes sorted; lengths[target][hap].
+ * Installs the tid lookups (no bamcols_set_tables needed).  Two @SQ names that collapse to the same
+ * (target, haplotype) are refused.  bamcols_tables hands the results out (names as NUL-separated blobs). */
+int bamcols_build_tables(bamcols* r, const char* first_targets, int64_t first_len);
+int bamcols_tables(const bamcols* r, int32_t* n_targets, int32_t* n_haps, const char** targets, int64_t* targets_len,
+                   const char** haps, int64_t* haps_len, const int32_t** tid_target, const int32_t** tid_hap,
+                   const int32_t** lengths);
+
 /* Cell-name dictionary of one per-cell job: names get dense ids in order of first appearance. */
 int bamcols_cells_create(bamcols_cells** out);
 void bamcols_cells_destroy(bamcols_cells* c);

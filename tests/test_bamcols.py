@@ -253,3 +253,42 @@ def test_randomised_small_bams(tmp_path, monkeypatch):
         monkeypatch.setenv("BAMCOLS_GRAIN", str(int(rng.choice([1, 5, 4096]))))
         path = _write(tmp_path, alns, "rand%d.bam" % case, block_payload=int(rng.choice([64, 200, 5000])))
         _same_single(path, n_threads=int(rng.choice([1, 2, 5])))
+
+
+def _tables_equal(a, b):
+    assert list(a.main_targets.items()) == list(b.main_targets.items())
+    assert a.haplotypes == b.haplotypes
+    assert np.array_equal(a.tid_target, b.tid_target) and np.array_equal(a.tid_hap, b.tid_hap)
+    assert np.array_equal(a.lengths, b.lengths) and a.lengths.dtype == b.lengths.dtype
+    assert (a.num_targets, a.num_haplotypes) == (b.num_targets, b.num_haplotypes)
+
+
+def test_native_header_tables_equal_the_python_tables(tmp_path):
+    """bamcols_build_tables against alntools_b200/header.py (the statement of bam_utils.py:561-633) on the
+    golden headers, with target files, and on names that exercise the '_' rules."""
+    for case in golden_cases("single"):
+        path = os.path.join(GOLDEN, case["bam"])
+        tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+        with bamcols.BamColumnReader(path) as r:
+            _tables_equal(r.build_tables(tfile), TargetTables(r.references, r.lengths, tfile))
+    refs = [("G1_A", 1), ("G1_B", 2), ("G2", 3), ("_G3", 4), ("G5_x_A", 5), ("G6_", 6), ("Z_A", 7), ("G2_B", 8)]
+    p = str(tmp_path / "quirks.bam")
+    bam_io.write_bam(p, refs, [("r", 0, 0)])
+    tf = str(tmp_path / "t.txt")
+    with open(tf, "w") as fh:
+        fh.write("# comment\nZ\nG9 second token ignored\nG1\n")
+    with bamcols.BamColumnReader(p) as r:
+        _tables_equal(r.build_tables(None), TargetTables(r.references, r.lengths, None))
+    with bamcols.BamColumnReader(p) as r:
+        got = r.build_tables(tf)
+        _tables_equal(got, TargetTables(r.references, r.lengths, tf))
+        assert list(got.main_targets)[:3] == ["Z", "G9", "G1"]
+        cols = r.read_all()                                   # the lookups are installed
+        assert cols["target_idx"].tolist() == [2] and cols["hap_idx"].tolist() == [1]
+    clash = str(tmp_path / "clash.bam")
+    bam_io.write_bam(clash, [("a", 1), ("a_", 2)], [("r", 0, 0)])
+    with bamcols.BamColumnReader(clash) as r:
+        with pytest.raises(ValueError):
+            TargetTables(r.references, r.lengths, None)
+        with pytest.raises(ValueError):
+            r.build_tables(None)
