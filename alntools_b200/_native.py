@@ -210,9 +210,10 @@ class EcBuilder(object):
         self._check(self._lib.ecb_finalize(self._ctx, int(min_cell_count), ctypes.byref(res)))
         return res
 
-    def finalize(self, min_cell_count=0):
+    def finalize(self, min_cell_count=0, copy=True):
         """Returns dict(a_indptr, a_indices, a_data, n_indptr, n_indices, n_data[, cell_order]) as
-        numpy int32 COPIES plus scalar sizes."""
+        numpy int32 arrays plus scalar sizes.  copy=False returns VIEWS of the library's result buffers
+        (valid until the next finalize / reset / close): the EC file can be written straight from them."""
         if self._result_on_device:
             raise RuntimeError("finalize() needs host results; use finalize_raw() with result_on_device")
         res = self.finalize_raw(min_cell_count)
@@ -220,7 +221,8 @@ class EcBuilder(object):
         def arr(ptr, n):
             if n == 0:
                 return np.zeros(0, dtype=np.int32)
-            return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+            view = np.ctypeslib.as_array(ptr, shape=(n,))
+            return view.copy() if copy else view
 
         out = {
             "n_ec": res.n_ec, "nnz_a": res.nnz_a, "n_samples": res.n_samples, "nnz_n": res.nnz_n,

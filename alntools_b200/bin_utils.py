@@ -14,7 +14,10 @@ import numpy as np
 
 
 def _i32(arr):
-    return np.ascontiguousarray(arr, dtype="<i4").tobytes()
+    """Little-endian int32 bytes of `arr` without a copy when it already is a contiguous int32 array
+    (the library's result buffers are written to the file directly)."""
+    a = np.ascontiguousarray(arr, dtype="<i4")
+    return a.data if a.size else b""
 
 
 def _target_section(target_names, lengths, n_haps):
