@@ -60,6 +60,12 @@ class EcbStats(ctypes.Structure):
         return {name: getattr(self, name) for name, _ in self._fields_}
 
 
+class EcbSlice(ctypes.Structure):
+    _i32p = ctypes.POINTER(ctypes.c_int32)
+    _fields_ = [("id_base", ctypes.c_int64), ("n_ec", ctypes.c_int64), ("nnz", ctypes.c_int64),
+                ("a_indptr", _i32p), ("a_indices", _i32p), ("a_data", _i32p), ("n_data", _i32p)]
+
+
 # every symbol include/ecb200.h declares, with its ctypes signature
 SIGNATURES = {
     "ecb_version": (ctypes.c_int, []),
@@ -75,6 +81,9 @@ SIGNATURES = {
                                             ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
                                             ctypes.POINTER(ctypes.c_int64)]),
     "ecb_import_arena": (ctypes.c_int, [ctypes.c_void_p]),
+    "ecb_slice_dispatch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                          ctypes.c_int64, ctypes.c_int64]),
+    "ecb_slice_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(EcbSlice)]),
     "ecb_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "ecb_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(EcbResult)]),
@@ -290,6 +299,23 @@ class EcBuilder(object):
 
     def import_arena(self):
         self._check(self._lib.ecb_import_arena(self._ctx))
+
+    def slice_dispatch(self, bases, cap_records, cap_rows):
+        """After global_count: send every owned EC (id, count, row) to the rank that assembles its id range."""
+        arr = (ctypes.c_void_p * len(bases))(*bases)
+        self._check(self._lib.ecb_slice_dispatch(self._ctx, len(bases), arr, int(cap_records), int(cap_rows)))
+
+    def slice_build(self, rank, world):
+        """-> dict(id_base, n_ec, nnz, a_indptr, a_indices, a_data, n_data): this rank's EC-id range of the
+        final matrices as torch views of library memory (valid until the next call on this context)."""
+        import torch
+        sl = EcbSlice()
+        self._check(self._lib.ecb_slice_build(self._ctx, int(rank), int(world), ctypes.byref(sl)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        view = lambda p, n: _device_view(ctypes.cast(p, ctypes.c_void_p).value, (n,), "<i4", torch.int32, dev)
+        return {"id_base": int(sl.id_base), "n_ec": int(sl.n_ec), "nnz": int(sl.nnz),
+                "a_indptr": view(sl.a_indptr, sl.n_ec + 1), "a_indices": view(sl.a_indices, sl.nnz),
+                "a_data": view(sl.a_data, sl.nnz), "n_data": view(sl.n_data, sl.n_ec)}
 
     def global_mark(self, min_base, bitmap):
         self._check(self._lib.ecb_global_mark(self._ctx, int(min_base), bitmap.data_ptr(), bitmap.numel()))

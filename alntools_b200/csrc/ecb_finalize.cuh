@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) ecb_fin_rank_kernel(const FinalizeParams 
     const u32 id = P.word_rank[w] + __popc(P.bitmap[w] & ((1u << b) - 1u));
     P.ecid_of[e] = id;
     const u32 len = P.row_len[e];
+    if (P.a_indptr == nullptr) continue;   // ids only (slice assembly)
     P.a_indptr[id] = (int32_t)len;
     if (SINGLE_SAMPLE) {
       P.n_indices[id] = (int32_t)id;

@@ -62,7 +62,10 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     """local: builder holding this rank's shard; make_owner(): fresh builder for the owner role.
     Returns dict(a_indptr, a_indices, a_data, n_data, n_ec, nnz_a) of int32 tensors on `device`,
     identical on every rank (result_on="all") or complete on rank 0 only (result_on="rank0": the rank
-    that writes the EC file; the other ranks then hold partial a_indices / a_data / n_data)."""
+    that writes the EC file; the other ranks then hold partial a_indices / a_data / n_data).
+    result_on="slices" (peer-memory exchange only): the final matrices stay partitioned by EC-id range,
+    rank j holding ids [id_base, id_base + n_ec_local) with a_indptr local to its slice; the dict then
+    also carries id_base, n_ec_local, nnz_local.  Nothing is padded to the global size on any rank."""
     world = dist.get_world_size(group)
     # library kernels and torch's collectives must be ordered against each other: both builders work
     # on torch's current stream from here on (NCCL orders itself against that stream)
@@ -106,7 +109,9 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
         dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)   # the barrier between "store" and "merge"
         g_min, g_max = -int(span[0].item()), int(span[1].item())
         owner.import_arena()
-        ph.mark("import")
+        if result_on == "slices":
+            owner.arena_reset()          # the arena is reused by the slice dispatch; the bitmap all-reduce
+        ph.mark("import")                # below orders this reset before any peer's second store
     else:
         meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
         ph.mark("export")
@@ -143,6 +148,18 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     ph.mark("bitmap")
     n_ec = owner.global_count(bitmap)
     ph.mark("count")
+    if result_on == "slices":
+        if not p2p:
+            raise RuntimeError('result_on="slices" needs the peer-memory exchange')
+        owner.slice_dispatch(arena["bases"], arena["cap_ec"], arena["cap_rows"])
+        dist.barrier(group=group)        # every rank's rows have landed
+        ph.mark("slice dispatch")
+        sl = owner.slice_build(me, world)
+        ph.mark("slice build")
+        ph.report()
+        return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
+                "n_data": sl["n_data"], "n_ec": n_ec, "id_base": sl["id_base"], "n_ec_local": sl["n_ec"],
+                "nnz_local": sl["nnz"], "nnz_a": None}
 
     lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=device)
     counts = torch.zeros(n_ec, dtype=torch.int32, device=device)

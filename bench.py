@@ -238,8 +238,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     config = {"workload": args.workload, "reads_per_gpu": wl["n_reads"], "n_targets": wl["n_targets"],
-              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU; N > 1: + all-to-all of hash-partitioned local ECs, owner merge, "
-                                                              "global ids and CSR on every rank",
+              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU; N > 1: + dispatch of hash-partitioned local ECs over peer "
+                                                              "memory, owner merge, global ids, final CSR partitioned by "
+                                                              "EC-id range across the ranks (e2e: every rank copies its "
+                                                              "range to its host)",
               "l2": "inputs (>= 700 MB per GPU) exceed the 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
@@ -371,27 +373,32 @@ def main():
 
     class _Res(object):
         def __init__(self, d):
-            self.n_ec, self.nnz_a = d["n_ec"], d["nnz_a"]
+            self.n_ec = d["n_ec"]
+            self.nnz_a = d["nnz_a"] if d.get("nnz_a") is not None else d["nnz_local"]
 
     def fin_device(b):
         if world == 1:
             return b.finalize_raw(min_count)
         owner.reset()
-        return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0"))
+        return _Res(multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="slices"))
 
     def fin_host(b):
         if world == 1:
             return b.finalize_raw(min_count)
         owner.reset()
-        out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="rank0")
-        if rank == 0:   # the job's result leaves the device once, on rank 0, into pinned memory
-            for k in ("a_indptr", "a_indices", "a_data", "n_data"):
-                t = out[k]
-                if k not in pinned_out or pinned_out[k].numel() < t.numel():
-                    pinned_out[k] = torch.empty(int(t.numel() * 1.25) + 1, dtype=t.dtype, pin_memory=True)
-                pinned_out[k][:t.numel()].copy_(t, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        out = multi_gpu.distributed_finalize(b, lambda: owner, dev_t, result_on="slices")
+        # every rank brings its EC-id range of the matrices to its own pinned host memory (the ranks
+        # write disjoint byte ranges of the EC file)
+        for k in ("a_indptr", "a_indices", "a_data", "n_data"):
+            t = out[k]
+            if k not in pinned_out or pinned_out[k].numel() < t.numel():
+                pinned_out[k] = torch.empty(int(t.numel() * 1.25) + 1, dtype=t.dtype, pin_memory=True)
+            pinned_out[k][:t.numel()].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        d2h_slices[0] = 4 * (int(out["n_ec_local"]) + 1) + 8 * int(out["nnz_local"]) + 4 * int(out["n_ec_local"])
         return _Res(out)
+
+    d2h_slices = [0]
 
     # ---- device-resident arm ("value") --------------------------------------------------------------
     b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], with_cells=bool(n_cells), alignments_hint=n_aln,
@@ -405,6 +412,10 @@ def main():
     if owner is not None:
         launches_per_step += owner.stats()["kernel_launches"]
     n_ec, nnz_a = int(res_dev.n_ec), int(res_dev.nnz_a)
+    if world > 1:   # the slices' non-zeros add up to the matrix's
+        t = torch.tensor([nnz_a], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        nnz_a = int(t.item())
     b_dev.close()
 
     # ---- end-to-end arm: host columns in, host matrices out ----------------------------------------
@@ -417,7 +428,9 @@ def main():
     assert int(res_e2e.n_ec) == n_ec
     d2h_e2e = stats_e2e["d2h_bytes"]
     if world > 1:
-        d2h_e2e += 4 * (n_ec + 1) + 8 * nnz_a + 4 * n_ec   # rank 0's copy of the global result
+        t = torch.tensor([d2h_slices[0]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        d2h_e2e = d2h_e2e * world + int(t.item())            # all ranks: counters + their slice
     b_e2e.close()
     if owner is not None:
         owner.close()
@@ -448,7 +461,7 @@ def main():
         "config": dict(config, alignments_per_gpu=n_aln, n_ec=n_ec, nnz_a=nnz_a,
                        table_slots=stats_dev["table_slots"], table_grows=stats_dev["table_grows"]),
         "e2e": {"value": total_aln * args.steps / (ms_e2e * 1e-3), "unit": "alignments/s",
-                "h2d_bytes_per_step": stats_e2e["h2d_bytes"], "d2h_bytes_per_step": d2h_e2e,
+                "h2d_bytes_per_step": stats_e2e["h2d_bytes"] * world, "d2h_bytes_per_step": d2h_e2e,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "ecb_group_insert_kernel", "achieved": achieved, "peak": peak,

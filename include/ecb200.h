@@ -201,6 +201,21 @@ int ecb_export_to_arenas(ecb_ctx* local_ctx, int world, void* const* arena_bases
                          int64_t cap_rows, int64_t* min_base, int64_t* max_end);
 int ecb_import_arena(ecb_ctx* owner_ctx);
 
+/* ---- slice assembly (after ecb_global_count): instead of steps 5's zero-padded global arrays the final
+ * CSR is built in EC-id ranges, rank j holding ids [j * slice, (j + 1) * slice) with
+ * slice = ceil(n_ec_total / world).  ecb_slice_dispatch on the OWNER context sends every owned EC (id,
+ * count, row) straight into the arena of the rank that assembles its id (the arenas of the first
+ * dispatch are reused: reset them after ecb_import_arena); after a barrier ecb_slice_build turns what
+ * arrived into that rank's slice: a_indptr[n_ec + 1] (offsets local to the slice), a_indices, a_data
+ * and n_data (read counts), all device memory of the context, valid until the next call. */
+typedef struct ecb_slice {
+  int64_t id_base, n_ec, nnz;
+  const int32_t *a_indptr, *a_indices, *a_data, *n_data;
+} ecb_slice;
+int ecb_slice_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, int64_t cap_records,
+                       int64_t cap_rows);
+int ecb_slice_build(ecb_ctx* owner_ctx, int rank, int world, ecb_slice* out);
+
 /* Set the first-occurrence bits of the ECs this context owns in bitmap[n_words] (bit i = order key
  * min_base + i).  The caller zero-fills the bitmap and all-reduces it afterwards. */
 int ecb_global_mark(ecb_ctx* ctx, int64_t min_base, uint32_t* bitmap_device, int64_t n_words);

@@ -85,6 +85,24 @@ def main():
     if rank == 0:
         print("multigpu_check world=%d own-shards device-resident reuse: alignments=%d ECs=%d: %s"
               % (world, len(rg), len(counts), "OK" if flag.item() else "MISMATCH"), flush=True)
+    # the same job with the result left partitioned by EC-id range (peer-memory exchange only)
+    if os.environ.get("ECB_EXCHANGE", "p2p") != "nccl":
+        for _ in range(2):
+            local_b.reset()
+            owner_b.reset()
+            local_b.push(mine["read_group"], mine["target_idx"], mine["hap_idx"], order_base=base)
+            sl = multi_gpu.distributed_finalize(local_b, lambda: owner_b, dev, result_on="slices")
+        a, b = sl["id_base"], sl["id_base"] + sl["n_ec_local"]
+        ok = (sl["n_ec"] == len(counts)
+              and np.array_equal(sl["a_indptr"].cpu().numpy(), indptr[a:b + 1] - indptr[a])
+              and np.array_equal(sl["a_indices"].cpu().numpy(), indices[indptr[a]:indptr[b]])
+              and np.array_equal(sl["a_data"].cpu().numpy(), data[indptr[a]:indptr[b]])
+              and np.array_equal(sl["n_data"].cpu().numpy(), counts[a:b]))
+        flag2 = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag2, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print("multigpu_check world=%d slices: %s" % (world, "OK" if flag2.item() else "MISMATCH"), flush=True)
+        flag = torch.minimum(flag, flag2)
     local_b.close()
     owner_b.close()
     if not flag.item():

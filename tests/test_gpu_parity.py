@@ -312,7 +312,7 @@ def test_multigpu_exchange_matches_oracle(native):
                           os.path.join(ROOT, "tests", "multigpu_check.py"), "300000"],
                          capture_output=True, text=True, timeout=400)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("OK") == 3
+    assert out.stdout.count("OK") == 4
 
 
 def test_exchange_primitives_single_gpu(native):
@@ -345,6 +345,9 @@ def test_exchange_primitives_single_gpu(native):
                 lb.export_to_arenas(bases, cap_ec, cap_rows)
             for ob in owners:
                 ob.import_arena()
+        if arenas:
+            for ob in owners:
+                ob.arena_reset()
         for o in range(world if not arenas else 0):   # what all_to_all would deliver to owner o
             metas, rows, ecn, rown = [], [], [], []
             for src in range(world):
@@ -385,6 +388,20 @@ def test_exchange_primitives_single_gpu(native):
         assert np.array_equal(indices.cpu().numpy(), want[1])
         assert np.array_equal(data.cpu().numpy(), want[2])
         assert np.array_equal(counts.cpu().numpy(), want[3])
+        if arenas:   # slice assembly: every owner sends its ECs to the rank of their id range
+            for ob in owners:
+                ob.slice_dispatch(bases, cap_ec, cap_rows)
+            at = 0
+            for r, ob in enumerate(owners):
+                sl = ob.slice_build(r, world)
+                assert sl["id_base"] == at
+                a, b = at, at + sl["n_ec"]
+                assert np.array_equal(sl["a_indptr"].cpu().numpy(), want[0][a:b + 1] - want[0][a])
+                assert np.array_equal(sl["a_indices"].cpu().numpy(), want[1][want[0][a]:want[0][b]])
+                assert np.array_equal(sl["a_data"].cpu().numpy(), want[2][want[0][a]:want[0][b]])
+                assert np.array_equal(sl["n_data"].cpu().numpy(), want[3][a:b])
+                at = b
+            assert at == n_ec
         for b in locals_ + owners:
             b.close()
 
