@@ -43,7 +43,9 @@
 #define ECB_CACHE 4096                 // per-CTA hot-EC cache entries
 #endif
 #define ECB_MQ 96                      // per-warp miss queue (entries); 64 are inserted at a time, two per lane
+#ifndef ECB_PF_DIST
 #define ECB_PF_DIST 256                // L2 prefetch distance of the column stream (alignments)
+#endif
 
 // A hot-cache entry that could not be flushed because the table was too full (replayed after growth).
 struct EcbSpill {
