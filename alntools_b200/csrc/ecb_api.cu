@@ -56,6 +56,7 @@ struct ecb_ctx {
   // counters
   EcbCounters* d_ctr = nullptr;
   EcbCounters* h_ctr = nullptr;  // pinned mirror
+  u64* h_total = nullptr;        // pinned landing place of a scan total
   u32 n_ec = 0;                  // host copy after the last sync
   // staging
   DevBuf st_rg, st_tg, st_hp, st_cell;
@@ -583,7 +584,8 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   c->stream = c->own_stream;
   for (auto& e : c->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaEventCreate failed"); return bail(ECB_ERR_CUDA); }
-  if (cudaMalloc(&c->d_ctr, sizeof(EcbCounters)) != cudaSuccess || cudaMallocHost(&c->h_ctr, sizeof(EcbCounters)) != cudaSuccess) {
+  if (cudaMalloc(&c->d_ctr, sizeof(EcbCounters)) != cudaSuccess || cudaMallocHost(&c->h_ctr, sizeof(EcbCounters)) != cudaSuccess ||
+      cudaMallocHost(&c->h_total, 64) != cudaSuccess) {
     fail(c, ECB_ERR_CUDA, "counter allocation failed");
     return bail(ECB_ERR_CUDA);
   }
@@ -819,8 +821,7 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   CK(cudaSetDevice(c->device));
   if (!c->table_slots || c->n_ec == 0) return fail(c, ECB_ERR_EMPTY, "no equivalence classes (nothing pushed)");
   CK(cudaEventRecord(c->ev[0], c->stream));
-  CKR(sync_counters(c));
-  const u32 n_prov = c->n_ec;
+  const u32 n_prov = c->n_ec;   // the host mirror of the counters is current: every push ends with a sync
   const u64 span = c->max_end - c->min_base;
   if (span > (1ull << 34)) return fail(c, ECB_ERR_LIMIT, "order_base range spans more than 2^34 positions");
   const size_t words = (size_t)((span + 31) / 32) + 1;
@@ -881,7 +882,14 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   else ecb_fin_rank_kernel<true><<<g_ec, 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rank");
   u64 Z = 0;
-  CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, E + 1, 0, &Z));
+  {  // row lengths -> indptr; its total and the counters (wide-row count) come back with ONE sync
+    CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, E + 1, 0, nullptr));
+    const u32 n_blocks = (u32)((E + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    CK(cudaMemcpyAsync(c->h_total, (const u64*)c->scan_partials.p + n_blocks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    CKR(sync_counters(c));
+    c->stats.d2h_bytes += sizeof(u64);
+    Z = *c->h_total;
+  }
   if (Z > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix has more than 2^31-1 non-zeros");
   CKR(ensure(c, c->r_a_indices, std::max<u64>(Z, 1) * 4));
   CKR(ensure(c, c->r_a_data, std::max<u64>(Z, 1) * 4));
@@ -889,7 +897,6 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   F.a_data = (int32_t*)c->r_a_data.p;
   ecb_fin_rows_kernel<<<grid_for(n_prov, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rows");
-  CKR(sync_counters(c));
   if (c->h_ctr->scratch[2]) {
     const u32 n_wide = c->h_ctr->scratch[2];
     ecb_fin_rows_long_kernel<<<grid_for((u64)n_wide * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
@@ -970,8 +977,7 @@ int ecb_reset(ecb_ctx* c) {
   if (c->table_slots) {
     CK(cudaMemsetAsync(c->table.p, 0xFF, (size_t)c->table_slots * sizeof(EcbEntry), c->stream));
     if (c->ttable_slots) CK(cudaMemsetAsync(c->ttable.p, 0xFF, (size_t)c->ttable_slots * sizeof(EcbEntry), c->stream));
-    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(EcbCounters), c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(EcbCounters), c->stream));   // stream-ordered: no host sync needed
   }
   memset(c->h_ctr, 0, sizeof(EcbCounters));
   c->n_ec = 0;
@@ -1415,6 +1421,7 @@ int ecb_destroy(ecb_ctx* c) {
   if (c->xa_base) cudaFree(c->xa_base);
   if (c->d_ctr) cudaFree(c->d_ctr);
   if (c->h_ctr) cudaFreeHost(c->h_ctr);
+  if (c->h_total) cudaFreeHost(c->h_total);
   if (c->h_res) {
     if (c->pageable_results) free(c->h_res); else cudaFreeHost(c->h_res);
   }
