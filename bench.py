@@ -404,8 +404,10 @@ def main():
     b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], with_cells=bool(n_cells), alignments_hint=n_aln,
                       device=local_rank, result_on_device=1, **opts)
     b_dev.set_stream(stream.cuda_stream)
-    timed_once(b_dev, dev, args.warmup, fin_device)
+    # clocks / throttle reasons are sampled from the warm-up on (same work, same load): the timed region
+    # itself lasts a few milliseconds, less than one nvidia-smi call
     with ClockSampler(local_rank) as clocks:
+        timed_once(b_dev, dev, args.warmup, fin_device)
         ms_dev, res_dev, group_ms, note_dev = timed(b_dev, dev, args.steps, fin_device)
     stats_dev = b_dev.stats()
     launches_per_step = stats_dev["kernel_launches"]  # stats are zeroed by reset(): this is the last step
