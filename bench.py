@@ -57,23 +57,55 @@ def measured_peak_gbs():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in-process (a query costs
+    microseconds, so a few-millisecond region still gets many samples and is not disturbed); falls back
+    to spawning nvidia-smi, whose queries can stall kernel launches for milliseconds."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]   # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []          # [sm_mhz, sm_max_mhz, flag, flag, flag, flag]
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
-        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
 
-    def _run(self):
+    def _run_nvml(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle))
+                except Exception:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+                self.samples.append([mhz, self._max] + [bool(reasons & b) for b in self.BITS])
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 if out.returncode == 0 and out.stdout.strip():
-                    self.samples.append([x.strip() for x in out.stdout.strip().split(",")])
+                    f = [x.strip() for x in out.stdout.strip().split(",")]
+                    if f[0].isdigit():
+                        self.samples.append([int(f[0]), int(f[1]) if f[1].isdigit() else None]
+                                            + [x.lower().startswith("active") for x in f[2:6]])
             except Exception:
                 pass
             self._stop.wait(0.2)
@@ -86,15 +118,18 @@ class ClockSampler(object):
         self._stop.set()
         self._thread.join(timeout=6)
 
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self._first = len(self.samples)
+
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        samples = self.samples[getattr(self, "_first", 0):] or self.samples
+        if not samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sample"], "source": self.source}
+        mhz = sorted(s[0] for s in samples)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i] for s in samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": samples[0][1], "reasons": reasons,
+                "samples": len(samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -404,10 +439,10 @@ def main():
     b_dev = EcBuilder(wl["n_targets"], wl["n_haps"], with_cells=bool(n_cells), alignments_hint=n_aln,
                       device=local_rank, result_on_device=1, **opts)
     b_dev.set_stream(stream.cuda_stream)
-    # clocks / throttle reasons are sampled from the warm-up on (same work, same load): the timed region
-    # itself lasts a few milliseconds, less than one nvidia-smi call
+    # the sampler starts with the warm-up; only the samples of the timed region are reported
     with ClockSampler(local_rank) as clocks:
         timed_once(b_dev, dev, args.warmup, fin_device)
+        clocks.mark()
         ms_dev, res_dev, group_ms, note_dev = timed(b_dev, dev, args.steps, fin_device)
     stats_dev = b_dev.stats()
     launches_per_step = stats_dev["kernel_launches"]  # stats are zeroed by reset(): this is the last step
