@@ -292,3 +292,37 @@ def test_native_header_tables_equal_the_python_tables(tmp_path):
             TargetTables(r.references, r.lengths, None)
         with pytest.raises(ValueError):
             r.build_tables(None)
+
+
+def test_records_with_cigar_sequence_and_tags(tmp_path):
+    """Real BAM records carry CIGAR, packed sequence, qualities and tags after the read name: the
+    emitter must hop over them by block_size and still read the fixed-offset fields."""
+    import struct
+    rng = np.random.default_rng(31)
+    payload = [bam_io.bam_header_bytes(REFS)]
+    want_rg, want_tid, group, last = [], [], -1, None
+    for i in range(700):
+        name = ("frag%04d" % (i // 3)).encode() + b"\x00"
+        n_cig, l_seq = int(rng.integers(0, 4)), int(rng.integers(0, 200))
+        tid, flag = int(rng.integers(0, len(REFS))), int(rng.choice([0, 16, 4, 256]))
+        tail = (rng.integers(0, 256, 4 * n_cig + (l_seq + 1) // 2 + l_seq + int(rng.integers(0, 40)), dtype=np.uint8)
+                .tobytes())
+        core = struct.pack("<iiBBHHHiiii", tid, int(rng.integers(0, 1000)), len(name), 30, 4680, n_cig, flag, l_seq,
+                           -1, -1, 0) + name + tail
+        payload.append(struct.pack("<i", len(core)) + core)
+        if not flag & 4:
+            if name != last:
+                group, last = group + 1, name
+            want_rg.append(group)
+            want_tid.append(tid)
+    raw = b"".join(payload)
+    path = str(tmp_path / "full.bam")
+    with open(path, "wb") as fh:
+        for off in range(0, len(raw), 777):                     # blocks cut records anywhere
+            fh.write(bam_io.bgzf_block(raw[off:off + 777]))
+        fh.write(bam_io.BGZF_EOF)
+    cols = _same_single(path)                                   # native == Python emitter
+    tables = TargetTables([r[0] for r in REFS], [r[1] for r in REFS], None)
+    assert cols["read_group"].tolist() == want_rg
+    assert np.array_equal(cols["target_idx"], tables.tid_target[np.array(want_tid)])
+    assert np.array_equal(cols["hap_idx"], tables.tid_hap[np.array(want_tid)])
