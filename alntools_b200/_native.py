@@ -20,6 +20,7 @@ ECB_OPT_HOT_CACHE = 5
 ECB_OPT_VERIFY_KEYS = 6
 ECB_OPT_CHUNK_LEN = 7
 ECB_OPT_PAGEABLE_RESULTS = 8
+ECB_OPT_TWO_PHASE = 9
 
 ECB_ERR_EMPTY = -5
 
@@ -186,7 +187,8 @@ class EcBuilder(object):
     _OPTIONS = {"result_on_device": ECB_OPT_RESULT_ON_DEVICE, "table_slots": ECB_OPT_TABLE_SLOTS,
                 "pair_slots": ECB_OPT_PAIR_SLOTS, "grid_ctas": ECB_OPT_GRID_CTAS,
                 "hot_cache": ECB_OPT_HOT_CACHE, "verify_keys": ECB_OPT_VERIFY_KEYS,
-                "chunk_len": ECB_OPT_CHUNK_LEN, "pageable_results": ECB_OPT_PAGEABLE_RESULTS}
+                "chunk_len": ECB_OPT_CHUNK_LEN, "pageable_results": ECB_OPT_PAGEABLE_RESULTS,
+                "two_phase": ECB_OPT_TWO_PHASE}
 
     def _check(self, rc):
         if rc != 0:

@@ -40,6 +40,8 @@ struct ecb_ctx {
   int use_cache = 1;
   int verify_keys = 0;
   int pageable_results = 0;
+  int two_phase = 0;
+  DevBuf plog, pcur;
   // EC table
   DevBuf table;
   u32 table_slots = 0;
@@ -305,6 +307,8 @@ GroupParams make_group_params(ecb_ctx* c, const int32_t* rg, const int32_t* tg, 
 int group_prepare_launch(ecb_ctx* c) {
   if (!c->group_attr_set) {
     CK(cudaFuncSetAttribute(ecb_group_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
@@ -607,6 +611,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
+    case ECB_OPT_TWO_PHASE: c->two_phase = value ? 1 : 0; break;
     case ECB_OPT_PAGEABLE_RESULTS:
       if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
       c->pageable_results = value ? 1 : 0; break;
@@ -680,11 +685,33 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
+  const bool two_phase = c->two_phase && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
+  if (two_phase) {
+    // logs sized from the push: misses are at most one per read, reads at most one per alignment
+    const u32 cap = (u32)std::min<int64_t>(0x7FFFFFFF / ECB_LOG_PARTS, n / ECB_LOG_PARTS * 3 / 4 + 4096);
+    CKR(ensure(c, c->plog, (size_t)cap * ECB_LOG_PARTS * sizeof(EcbLogEntry)));
+    CKR(ensure(c, c->pcur, ECB_LOG_PARTS * 4));
+    CK(cudaMemsetAsync(c->pcur.p, 0, ECB_LOG_PARTS * 4, c->stream));
+    P.plog = (EcbLogEntry*)c->plog.p;
+    P.pcur = (u32*)c->pcur.p;
+    P.plog_cap = cap;
+    u32 bits = 0;
+    while ((1u << bits) < c->table_slots) ++bits;
+    P.plog_shift = bits - ECB_LOG_PARTS_LOG2;   // partition = the top bits of the slot index
+    P.use_log = 1;
+    CKR(ensure(c, c->spill, ((size_t)grid * ECB_CACHE + 1024) * sizeof(EcbSpill)));
+    P.spill = (EcbSpill*)c->spill.p;
+  }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
   if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
+  if (two_phase) {
+    ecb_log_insert_kernel<<<c->sm_count, 1024, 0, c->stream>>>(P);
+    LAUNCH_CHECK("log_insert");
+  }
   CK(cudaEventRecord(c->ev[2], c->stream));
   CKR(sync_counters(c));
   CKR(check_device_error(c));
@@ -1403,7 +1430,7 @@ int ecb_destroy(ecb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->big_list, &c->count_of,
-                    &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell,
+                    &c->ttable, &c->plog, &c->pcur, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell,
                     &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,

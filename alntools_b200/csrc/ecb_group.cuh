@@ -53,6 +53,14 @@ struct EcbSpill {
   u32 count, first, rep, len;
 };
 
+// One miss of the hot-EC cache (count 1, first == rep) or one flushed cache entry, 32 bytes.
+struct __align__(32) EcbLogEntry {
+  u64 lo, hi;
+  u32 first, count, rep, len;
+};
+#define ECB_LOG_PARTS 1024  // many partitions: the cursor atomics of a launch spread over that many addresses
+#define ECB_LOG_PARTS_LOG2 10
+
 struct GroupParams {
   const int32_t* rg;
   const int32_t* tg;
@@ -73,6 +81,12 @@ struct GroupParams {
   EcbCounters* ctr;
   u32* overflow_bits;  // [ceil(n/32)] reads that must be replayed after a table growth
   EcbSpill* spill;     // [grid * ECB_CACHE] cache entries that must be replayed after a table growth
+  // two-phase insert (ECB_OPT_TWO_PHASE): misses go to per-partition logs, a second kernel inserts them
+  EcbLogEntry* plog;   // [ECB_LOG_PARTS * plog_cap]
+  u32* pcur;           // [ECB_LOG_PARTS] entries appended so far (beyond plog_cap: inserted directly instead)
+  u32 plog_cap;
+  u32 plog_shift;      // partition = (slot hash & mask) >> plog_shift: a contiguous range of table slots
+  int use_log;
   EcbEntry* ttable;    // (file, EC slot, cell) table, with cells only
   u32 tmask;
   u32 push_id;
@@ -376,6 +390,52 @@ __device__ __forceinline__ void insert_misses(const GroupParams& P, u32 qk, u32 
   }
 }
 
+// Two-phase insert, phase A: the misses are appended to the log of their table partition.  The two
+// appends of a lane are in flight together; the only round trip is the cursor atomic.  A full log
+// (never in practice: the logs are sized from the push) falls back to the direct insert.
+__device__ __forceinline__ bool log_append(const GroupParams& P, const Key128& key, u32 first, u32 count, u32 rep,
+                                           u32 len, u32 pos, u32 part) {
+  if (pos >= P.plog_cap) return false;
+  uint4* dst = reinterpret_cast<uint4*>(P.plog + (size_t)part * P.plog_cap + pos);
+  dst[0] = make_uint4((u32)key.lo, (u32)(key.lo >> 32), (u32)key.hi, (u32)(key.hi >> 32));
+  dst[1] = make_uint4(first, count, rep, len);
+  return true;
+}
+
+template <bool WITH_CELLS>
+__device__ __forceinline__ void log_misses(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb, bool hasB) {
+  uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
+  uint2 rA = make_uint2(0u, 0u), rB = rA;
+  if (hasA) {
+    kA = lds128(qk + qa * 16u);
+    rA = lds64(qr + qa * 8u);
+  }
+  if (hasB) {
+    kB = lds128(qk + qb * 16u);
+    rB = lds64(qr + qb * 8u);
+  }
+  const Key128 keyA = key_of(kA), keyB = key_of(kB);
+  const u32 pA = (ec_slot_hash(keyA) & P.mask) >> P.plog_shift, pB = (ec_slot_hash(keyB) & P.mask) >> P.plog_shift;
+  u32 posA = 0, posB = 0;
+  if (hasA) posA = atomicAdd(&P.pcur[pA], 1u);
+  if (hasB) posB = atomicAdd(&P.pcur[pB], 1u);
+  const bool okA = hasA && log_append(P, keyA, rA.x, 1u, rA.x, rA.y, posA, pA);
+  const bool okB = hasB && log_append(P, keyB, rB.x, 1u, rB.x, rB.y, posB, pB);
+  const bool redoA = hasA && !okA, redoB = hasB && !okB;
+  if (redoA || redoB) {
+    u32 slotA, slotB;
+    global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
+    if (redoA && slotA == ECB_NONE) {
+      atomicOr(&P.overflow_bits[rA.x >> 5], 1u << (rA.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    }
+    if (redoB && slotB == ECB_NONE) {
+      atomicOr(&P.overflow_bits[rB.x >> 5], 1u << (rB.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    }
+  }
+}
+
 struct LongRead {
   uint4 key;
   int len;
@@ -428,7 +488,9 @@ __device__ __noinline__ LongRead ecb_long_read(const int32_t* __restrict__ rg, c
   return r;
 }
 
-template <bool WITH_CELLS>
+// LOGGED: the experimental two-phase insert (ECB_OPT_TWO_PHASE); a template parameter so that the
+// default kernel carries none of it.
+template <bool WITH_CELLS, bool LOGGED = false>
 __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const GroupParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
@@ -644,13 +706,14 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
           const u32 q = qn + __popc(mm & lt_mask);
           sts128(qk + q * 16u, key);
           sts64(qr + q * 8u, s, len);
-          prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
+          if (!LOGGED) prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
         }
         qn += __popc(mm);
         __syncwarp();
         if (qn >= 64u) {
           qn -= 64u;
-          insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
+          if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
+          else insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           __syncwarp();
         }
       }
@@ -658,7 +721,10 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
-  if (qn) insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+  if (qn) {
+    if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+    else insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+  }
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
   __syncthreads();
@@ -669,6 +735,10 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         const Key128 key = key_of(S.c_key[i]);
         const u32 first = S.c_first[i];
         const uint2 rep = S.c_rep[i];
+        if (LOGGED) {
+          const u32 part = (ec_slot_hash(key) & P.mask) >> P.plog_shift;
+          if (log_append(P, key, first, cnt, rep.x, rep.y, atomicAdd(&P.pcur[part], 1u), part)) continue;
+        }
         const u32 slot = global_upsert(P, key, cnt, first, rep.x, rep.y);
         if (slot == ECB_NONE) {  // table too full: park the entry, the host grows the table and replays it
           const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
@@ -706,6 +776,30 @@ __device__ inline Key128 ecb_serial_read_key(const int32_t* rg, const int32_t* t
   }
   if (len_out) *len_out = j - s;
   return mix_to_key(sum);
+}
+
+// Two-phase insert, phase B: the logs go into the table, one partition per CTA at a time.  A partition
+// is a contiguous 1/1024 of the slots, so the slices the resident CTAs work on (148 x a few hundred KB)
+// stay in L2: probes, compare-and-swap and counters do not go to HBM.
+__global__ void __launch_bounds__(1024, 1) ecb_log_insert_kernel(const GroupParams P) {
+  for (u32 part = blockIdx.x; part < ECB_LOG_PARTS; part += gridDim.x) {
+    const u32 cnt = min(P.pcur[part], P.plog_cap);
+    const uint4* log = reinterpret_cast<const uint4*>(P.plog + (size_t)part * P.plog_cap);
+    for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const uint4 k = log[2 * (size_t)i], v = log[2 * (size_t)i + 1];
+      const Key128 key = key_of(k);
+      const u32 slot = global_upsert(P, key, v.y, v.x, v.z, v.w);
+      if (slot == ECB_NONE) {
+        if (v.y == 1u && v.x == v.z) {  // one read: flag it for the replay after the table has grown
+          atomicOr(&P.overflow_bits[v.z >> 5], 1u << (v.z & 31));
+          atomicAdd(&P.ctr->n_overflow, 1u);
+        } else {
+          const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
+          P.spill[si] = EcbSpill{key.lo, key.hi, v.y, v.x, v.z, v.w};
+        }
+      }
+    }
+  }
 }
 
 // ECB_OPT_VERIFY_KEYS: prove that no two different reads of this push were merged by the 128-bit key.

@@ -63,8 +63,11 @@ enum ecb_option {
                                    compares it with the row of the EC the read was counted in, turning
                                    a 128-bit key collision into ECB_ERR_LIMIT (slow; a debugging aid) */
   ECB_OPT_CHUNK_LEN = 7,        /* alignments per work chunk of the grouping kernel (0 = automatic) */
-  ECB_OPT_PAGEABLE_RESULTS = 8  /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
+  ECB_OPT_PAGEABLE_RESULTS = 8, /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
                                    cheaper for a context that finalizes once, slower when reused */
+  ECB_OPT_TWO_PHASE = 9         /* 1: the grouping kernel appends cache misses to per-partition logs and a second
+                                   kernel inserts them partition by partition (table slice resident in L2);
+                                   experimental, single-sample path only */
 };
 
 typedef struct ecb_result {

@@ -446,3 +446,19 @@ def test_key_verification_option_finds_no_collision(native):
         cols = synth.make_columns(n_reads, n_targets, n_haps, seed=9, mode=mode, dup_rate=dup)
         got, _ = _run(native, cols, n_targets, n_haps, verify_keys=1)
         _assert_same(got, _oracle(cols))
+
+
+def test_two_phase_insert_gives_the_same_result(native):
+    """ECB_OPT_TWO_PHASE: cache misses logged per table partition and inserted by a second kernel -
+    same matrices as the direct insert, also when the table is too small and the logged reads have to
+    be replayed after a growth."""
+    from alntools_b200 import synth
+    for n_reads, n_targets, n_haps, mode, dup, slots in ((200000, 2000, 2, "diploid", 0.02, 1 << 20),
+                                                         (3000000, 100000, 2, "diploid", 0.0, 1 << 20),
+                                                         (30000, 1500, 8, "heavy", 0.01, 1 << 20),
+                                                         (400000, 50000, 2, "light", 0.0, 1 << 21)):
+        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=5, mode=mode, dup_rate=dup)
+        want = _oracle(cols)
+        for cache in (1, 0):
+            got, stats = _run(native, cols, n_targets, n_haps, two_phase=1, table_slots=slots, hot_cache=cache)
+            _assert_same(got, want)
