@@ -51,18 +51,69 @@ struct GroupRows {
 
 }  // namespace
 
+// Cell dictionary: ids in order of first appearance (bam_utils_multisample.py:270-280).  Open addressing
+// over 64-bit name hashes (the hash can be computed by the parallel passes, the sequential part of a
+// lookup is one probe and one memcmp).
 struct bamcols_cells {
-  std::unordered_map<std::string, int32_t> ids;
   std::vector<std::string> names;
-  int32_t id_of(const char* s, size_t n) {
-    std::string key(s, n);
-    auto it = ids.find(key);
-    if (it != ids.end()) return it->second;
+  std::vector<uint64_t> slot_hash;   // 0 = empty
+  std::vector<int32_t> slot_id;
+  size_t mask = 0;
+  static uint64_t hash_of(const char* s, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      uint64_t w;
+      memcpy(&w, s + i, 8);
+      h = (h ^ w) * 0xFF51AFD7ED558CCDull;
+      h ^= h >> 32;
+    }
+    uint64_t w = 0;
+    if (i < n) memcpy(&w, s + i, n - i);
+    h = (h ^ w) * 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 29;
+    return h ? h : 1;
+  }
+  void grow() {
+    const size_t cap = mask ? (mask + 1) * 2 : 1024;
+    std::vector<uint64_t> h(cap, 0);
+    std::vector<int32_t> id(cap, 0);
+    for (size_t i = 0; i <= mask && mask; ++i)
+      if (slot_hash[i]) {
+        size_t j = slot_hash[i] & (cap - 1);
+        while (h[j]) j = (j + 1) & (cap - 1);
+        h[j] = slot_hash[i];
+        id[j] = slot_id[i];
+      }
+    slot_hash.swap(h);
+    slot_id.swap(id);
+    mask = cap - 1;
+  }
+  // read-only lookup (safe from several threads while nobody inserts): id, or -1
+  int32_t find(const char* s, size_t n, uint64_t h) const {
+    if (mask == 0) return -1;
+    for (size_t j = h & mask; slot_hash[j]; j = (j + 1) & mask)
+      if (slot_hash[j] == h) {
+        const std::string& nm = names[(size_t)slot_id[j]];
+        if (nm.size() == n && memcmp(nm.data(), s, n) == 0) return slot_id[j];
+      }
+    return -1;
+  }
+  int32_t id_of(const char* s, size_t n, uint64_t h) {
+    if ((names.size() + 1) * 2 > mask + 1 || mask == 0) grow();
+    size_t j = h & mask;
+    for (; slot_hash[j]; j = (j + 1) & mask)
+      if (slot_hash[j] == h) {
+        const std::string& nm = names[(size_t)slot_id[j]];
+        if (nm.size() == n && memcmp(nm.data(), s, n) == 0) return slot_id[j];
+      }
     const int32_t id = (int32_t)names.size();
-    ids.emplace(key, id);
-    names.push_back(std::move(key));
+    slot_hash[j] = h;
+    slot_id[j] = id;
+    names.emplace_back(s, n);
     return id;
   }
+  int32_t id_of(const char* s, size_t n) { return id_of(s, n, hash_of(s, n)); }
 };
 
 struct bamcols {
@@ -90,7 +141,9 @@ struct bamcols {
   bool records_done = false, all_flushed = false;
   int64_t all_alignments = 0;
   // single-sample batch path: rows of the current inflated window, produced by all worker threads
-  std::vector<int32_t> st_rg, st_tg, st_hp;
+  std::vector<int32_t> st_rg, st_tg, st_hp, st_cell;
+  size_t pending_row = 0;        // per-cell: stage row whose cell is resolved by the next valid alignment
+  bool sequential_cells = false; // BAMCOLS_SEQUENTIAL_CELLS: the one-pass statement of the per-cell rules
   size_t st_pos = 0;             // next row to hand out
   size_t st_whole = 0;           // rows [st_pos, st_whole) are whole reads; [st_whole, size) is the open last read
   std::vector<size_t> rec_off;   // scratch: record offsets of the window
@@ -278,18 +331,35 @@ inline size_t trimmed_len(const char* s, size_t n) {
   return i > 0 ? i : n;
 }
 
-// Field 14 of name.split('|||') (bam_utils_multisample.py:273).  false: fewer than 15 fields.
-bool cell_field(const std::string& name, const char** out, size_t* len) {
-  size_t start = 0;
-  for (int f = 0; f < 14; ++f) {
-    const size_t p = name.find("|||", start);
-    if (p == std::string::npos) return false;
-    start = p + 3;
+// Field 14 of name.split('|||') (bam_utils_multisample.py:273): separators are found left to right and
+// do not overlap.  false: fewer than 15 fields.
+inline bool cell_field(const char* s, size_t n, const char** out, size_t* len) {
+  size_t start = 0, i = 0;
+  int seps = 0;
+  while (i + 3 <= n) {
+    const void* bar = memchr(s + i, '|', n - 2 - i);
+    if (!bar) break;
+    i = (size_t)((const char*)bar - s);
+    if (s[i + 1] == '|' && s[i + 2] == '|') {
+      if (seps == 14) {
+        *out = s + start;
+        *len = i - start;
+        return true;
+      }
+      ++seps;
+      i += 3;
+      start = i;
+    } else {
+      ++i;
+    }
   }
-  const size_t e = name.find("|||", start);
-  *out = name.data() + start;
-  *len = (e == std::string::npos ? name.size() : e) - start;
+  if (seps < 14) return false;
+  *out = s + start;
+  *len = n - start;
   return true;
+}
+inline bool cell_field(const std::string& name, const char** out, size_t* len) {
+  return cell_field(name.data(), name.size(), out, len);
 }
 
 // Lock-free min / max on plain int32 slots shared by the worker threads (updates are rare after the
@@ -482,7 +552,267 @@ int process_window_single(bamcols* r) {
   return 0;
 }
 
-int64_t emit_single(bamcols* r, int32_t* read_group, int32_t* target_idx, int32_t* hap_idx, int64_t capacity, int* done) {
+// Per-cell rules (bam_utils_multisample.py:258-300) over the records of the inflated window, in
+// parallel except for two cheap sequential passes.  With P the previous valid record, a record B
+// starts a read iff the remembered name differs from trim(B), and the remembered name is
+//   - trim(first record of the file) until the first switch,
+//   - the UNTRIMMED name of the record that made the last switch (:292) afterwards,
+// which, because every record inside a read matches the remembered name, is trim(P) if P did not
+// switch and P's untrimmed name if it did.  So both outcomes are computed per record in parallel
+// ("differs from trim(P)", "differs from P untrimmed") and one pass over two bits per record picks.
+// The cell of a read is field 14 of its remembered name, looked up when the NEXT valid alignment
+// arrives (dictionary ids follow that order; a read that ends the file alone is never looked up).
+int process_window_cells(bamcols* r, bamcols_cells* cells) {
+  const size_t left = r->st_rg.size() - r->st_pos;
+  if (r->st_pos > 0) {
+    memmove(r->st_rg.data(), r->st_rg.data() + r->st_pos, left * 4);
+    memmove(r->st_tg.data(), r->st_tg.data() + r->st_pos, left * 4);
+    memmove(r->st_hp.data(), r->st_hp.data() + r->st_pos, left * 4);
+    memmove(r->st_cell.data(), r->st_cell.data() + r->st_pos, left * 4);
+  }
+  r->st_rg.resize(left);
+  r->st_tg.resize(left);
+  r->st_hp.resize(left);
+  r->st_cell.resize(left);
+  r->st_whole -= r->st_pos;
+  if (r->pending) r->pending_row -= r->st_pos;
+  r->st_pos = 0;
+
+  if (r->wend - r->wpos < 4 || r->wend - r->wpos < 4 + (size_t)le32(r->win.data() + r->wpos)) {
+    const int rc = refill(r);
+    if (rc < 0) return rc;
+  }
+  auto lap_t0 = std::chrono::steady_clock::now();
+  auto lap = [&](int phase) {   // time since the previous lap goes to `phase`
+    const auto now = std::chrono::steady_clock::now();
+    r->phase_s[phase] += std::chrono::duration<double>(now - lap_t0).count();
+    lap_t0 = now;
+  };
+  const uint8_t* base = r->win.data();
+  std::vector<size_t>& off = r->rec_off;
+  off.clear();
+  size_t p = r->wpos;
+  while (p + 4 <= r->wend) {
+    const size_t bs = le32(base + p);
+    if (bs < 32) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", bs);
+    if (p + 4 + bs > r->wend) break;
+    off.push_back(p);
+    p += 4 + bs;
+  }
+  r->wpos = p;
+  lap(1);
+  const size_t n = off.size();
+  if (n == 0) {
+    if (r->file_done) {
+      if (r->wend != r->wpos) return fail(r, BAMCOLS_ERR_FORMAT, "truncated BAM record at the end of the file");
+      r->records_done = true;
+      r->st_whole = r->st_rg.size();
+    }
+    return 0;
+  }
+  r->all_alignments += (int64_t)n;
+  std::vector<uint8_t>& fl = r->rec_flag;   // bit 0 valid, bit 1 differs from trim(P), bit 2 differs from P untrimmed
+  fl.assign(n, 0);
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, n / r->grain + 1));
+  const int32_t n_ref = (int32_t)r->tid_target.size();
+  std::vector<size_t> n_valid(nt + 1, 0), n_start(nt + 1, 0);
+  std::atomic<int> bad(0);
+  auto lo = [&](int t) { return n * (size_t)t / (size_t)nt; };
+  auto name_of = [&](size_t i, const char** nm, size_t* full, size_t* trimmed) {
+    const uint8_t* q = base + off[i] + 4;
+    *nm = (const char*)q + 32;
+    *full = (size_t)q[8] - 1;
+    *trimmed = trimmed_len(*nm, *full);
+  };
+  parallel_for(nt, [&](int t) {
+    size_t cnt = 0;
+    for (size_t i = lo(t); i < lo(t + 1); ++i) {
+      const uint8_t* q = base + off[i] + 4;
+      const size_t bs = le32(base + off[i]);
+      const int32_t tid = (int32_t)le32(q);
+      const size_t l_name = q[8];
+      const uint32_t flag = le16(q + 14);
+      const int32_t ntid = (int32_t)le32(q + 20), npos = (int32_t)le32(q + 24);
+      if (32 + l_name > bs || l_name == 0) { bad.store(1); continue; }
+      if (flag & 0x4) continue;
+      if ((flag & 0x1) && ((flag & 0x80) || !(flag & 0x2) || tid != ntid || npos < 0)) continue;
+      if (tid < 0 || tid >= n_ref) { bad.store(2); continue; }
+      if (r->track_ranges) note_position(r, tid, (int32_t)le32(q + 4));
+      fl[i] = 1;
+      ++cnt;
+    }
+    n_valid[t + 1] = cnt;
+  });
+  if (bad.load() == 1) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with a bad read-name length");
+  if (bad.load() == 2) return fail(r, BAMCOLS_ERR_TID, "alignment with a reference id outside the header's %d references", n_ref);
+  for (int t = 0; t < nt; ++t) n_valid[t + 1] += n_valid[t];
+  const size_t rows = n_valid[nt];
+  lap(2);
+  if (rows == 0) return 0;
+
+  // both comparison outcomes per valid record, against the previous valid record of the window
+  parallel_for(nt, [&](int t) {
+    const char* pn = nullptr;
+    size_t pf = 0, pt = 0;
+    bool have = false;
+    for (size_t j = lo(t); j-- > 0;)
+      if (fl[j]) {
+        name_of(j, &pn, &pf, &pt);
+        have = true;
+        break;
+      }
+    for (size_t i = lo(t); i < lo(t + 1); ++i) {
+      if (!fl[i]) continue;
+      const char* nm;
+      size_t nf, ntm;
+      name_of(i, &nm, &nf, &ntm);
+      if (have) {
+        if (ntm != pt || memcmp(nm, pn, ntm) != 0) fl[i] |= 2;   // differs from trim(P)
+        if (ntm != pf || memcmp(nm, pn, ntm) != 0) fl[i] |= 4;   // differs from P untrimmed
+      }
+      pn = nm;
+      pf = nf;
+      pt = ntm;
+      have = true;
+    }
+  });
+
+  // one pass over the flags: which records start a read (bit 3), openers in order
+  std::vector<size_t> openers;
+  {
+    bool first_in_window = true, prev_switch = false, prev_trimmed_name = false;
+    int t = 0;
+    for (size_t i = 0; i < n; ++i) {
+      while (i >= lo(t + 1)) ++t;
+      if (!fl[i]) continue;
+      bool sw;
+      if (!r->started && first_in_window) {
+        sw = true;                                   // the file's first read
+      } else if (first_in_window) {
+        const char* nm;
+        size_t nf, ntm;
+        name_of(i, &nm, &nf, &ntm);
+        sw = r->current.size() != ntm || memcmp(r->current.data(), nm, ntm) != 0;
+      } else {
+        sw = (prev_switch && !prev_trimmed_name) ? (fl[i] & 4) != 0 : (fl[i] & 2) != 0;
+      }
+      prev_trimmed_name = sw && !r->started && first_in_window;   // only the first read is remembered trimmed
+      first_in_window = false;
+      prev_switch = sw;
+      if (sw) {
+        fl[i] |= 8;
+        openers.push_back(i);
+        ++n_start[t + 1];
+      }
+    }
+    for (int k = 0; k < nt; ++k) n_start[k + 1] += n_start[k];
+  }
+  size_t last_valid = n;
+  for (size_t j = n; j-- > 0;)
+    if (fl[j]) {
+      last_valid = j;
+      break;
+    }
+
+  if (r->pending) {   // the read that was open alone at the end of the previous window: this window has a valid record
+    const char* cf;
+    size_t cl;
+    if (!cell_field(r->current, &cf, &cl)) return fail(r, BAMCOLS_ERR_CELL_FIELD, "list index out of range");
+    r->cell = cells->id_of(cf, cl);
+    r->st_cell[r->pending_row] = r->cell;
+    r->pending = false;
+  }
+
+  // cell names of the openers (field 14 of the remembered name), in parallel, looked up in the dictionary
+  // as it stands now; only cells that are NEW in this window go through the ordered pass below
+  const size_t n_open = openers.size();
+  std::vector<const char*> cell_ptr(n_open, nullptr);
+  std::vector<size_t> cell_len(n_open, 0);
+  std::vector<uint64_t> cell_hash(n_open, 0);
+  std::vector<int32_t> cell_id(n_open, -2);   // -2 no field 14, -1 not in the dictionary yet
+  const bamcols_cells* snapshot = cells;
+  const bool file_first_here = !r->started;
+  {
+    const int nto = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, n_open / r->grain + 1));
+    parallel_for(nto, [&](int t) {
+      for (size_t k = n_open * (size_t)t / (size_t)nto; k < n_open * (size_t)(t + 1) / (size_t)nto; ++k) {
+        const char* nm;
+        size_t nf, ntm;
+        name_of(openers[k], &nm, &nf, &ntm);
+        const size_t len = (file_first_here && k == 0) ? ntm : nf;   // remembered name of that read
+        const char* cf;
+        size_t cl;
+        if (!cell_field(nm, len, &cf, &cl)) continue;
+        cell_ptr[k] = cf;
+        cell_len[k] = cl;
+        cell_hash[k] = bamcols_cells::hash_of(cf, cl);
+        cell_id[k] = snapshot->find(cf, cl, cell_hash[k]);
+      }
+    });
+  }
+
+  // dictionary pass, in the order the reference resolves cells
+  const size_t row0 = r->st_rg.size();
+  r->st_rg.resize(row0 + rows);
+  r->st_tg.resize(row0 + rows);
+  r->st_hp.resize(row0 + rows);
+  r->st_cell.resize(row0 + rows);
+  std::vector<int32_t> group_cell(n_open + 1, 0);
+  group_cell[0] = r->cell;   // the read that is open when the window begins
+  bool pending_now = false;
+  for (size_t k = 0; k < n_open; ++k) {
+    const bool first_of_file = file_first_here && k == 0;
+    if (!first_of_file && openers[k] == last_valid) {   // alone at the end of the window: resolved later, or never
+      pending_now = true;
+      group_cell[k + 1] = 0;
+      continue;
+    }
+    if (cell_id[k] == -2) return fail(r, BAMCOLS_ERR_CELL_FIELD, "list index out of range");
+    group_cell[k + 1] = cell_id[k] >= 0 ? cell_id[k] : cells->id_of(cell_ptr[k], cell_len[k], cell_hash[k]);
+  }
+
+  lap(3);
+  // rows
+  const int64_t group0 = r->group;
+  int32_t* rg = r->st_rg.data() + row0;
+  int32_t* tg = r->st_tg.data() + row0;
+  int32_t* hp = r->st_hp.data() + row0;
+  int32_t* cc = r->st_cell.data() + row0;
+  parallel_for(nt, [&](int t) {
+    size_t k = n_valid[t];
+    size_t g = n_start[t];
+    for (size_t i = lo(t); i < lo(t + 1); ++i) {
+      if (!fl[i]) continue;
+      if (fl[i] & 8) ++g;
+      const int32_t tid = (int32_t)le32(base + off[i] + 4);
+      rg[k] = (int32_t)(group0 + (int64_t)g);
+      tg[k] = r->tid_target[tid];
+      hp[k] = r->tid_hap[tid];
+      cc[k] = group_cell[g];
+      ++k;
+    }
+  });
+  r->group = group0 + (int64_t)n_open;
+  if (n_open) {
+    const char* nm;
+    size_t nf, ntm;
+    name_of(openers[n_open - 1], &nm, &nf, &ntm);
+    r->current.assign(nm, (file_first_here && n_open == 1) ? ntm : nf);
+    r->cell = group_cell[n_open];
+    r->pending = pending_now;
+    if (pending_now) r->pending_row = row0 + rows - 1;   // that read's only row is the window's last row
+  }
+  r->started = true;
+  lap(4);
+  size_t w = r->st_rg.size();
+  const int32_t last = r->st_rg[w - 1];
+  while (w > 0 && r->st_rg[w - 1] == last) --w;
+  r->st_whole = w;
+  return 0;
+}
+
+int64_t emit_single(bamcols* r, bamcols_cells* cells, int32_t* read_group, int32_t* target_idx, int32_t* hap_idx,
+                    int32_t* cell_idx, int64_t capacity, int* done) {
   int64_t rows = 0;
   for (;;) {
     const size_t avail = r->st_whole - r->st_pos;
@@ -498,6 +828,7 @@ int64_t emit_single(bamcols* r, int32_t* read_group, int32_t* target_idx, int32_
       memcpy(read_group + rows, r->st_rg.data() + r->st_pos, take * 4);
       memcpy(target_idx + rows, r->st_tg.data() + r->st_pos, take * 4);
       memcpy(hap_idx + rows, r->st_hp.data() + r->st_pos, take * 4);
+      if (cells) memcpy(cell_idx + rows, r->st_cell.data() + r->st_pos, take * 4);
       rows += (int64_t)take;
       r->st_pos += take;
       if (rows == capacity) return rows;
@@ -507,7 +838,7 @@ int64_t emit_single(bamcols* r, int32_t* read_group, int32_t* target_idx, int32_
       *done = 1;
       return rows;
     }
-    const int rc = process_window_single(r);
+    const int rc = cells ? process_window_cells(r, cells) : process_window_single(r);
     if (rc < 0) return rc;
   }
 }
@@ -545,6 +876,8 @@ int bamcols_open(bamcols** out, const char* path, int n_threads) {
   }
   r->file = (const uint8_t*)m;
   madvise(m, r->file_size, MADV_SEQUENTIAL);
+  r->sequential_cells = getenv("BAMCOLS_SEQUENTIAL_CELLS") != nullptr;
+  if (const char* b = getenv("BAMCOLS_BATCH_BLOCKS")) r->batch_blocks = (size_t)std::max(1L, atol(b));  // tests: many small windows
   if (const char* g = getenv("BAMCOLS_GRAIN")) r->grain = (size_t)std::max(1L, atol(g));  // tests: split tiny inputs too
   const unsigned hw = std::thread::hardware_concurrency();
   r->n_threads = n_threads > 0 ? n_threads : (hw ? (int)hw : 1);
@@ -740,9 +1073,9 @@ int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int3
   const int want_mode = cells ? 2 : 1;
   if (r->mode == 0) r->mode = want_mode;
   if (r->mode != want_mode) return fail(r, BAMCOLS_ERR_INVALID, "a reader cannot switch between single-sample and per-cell rules");
-  if (!cells) return emit_single(r, read_group, target_idx, hap_idx, capacity, done);
-  // ---- per-cell rules: one sequential pass (the cell dictionary and the remembered-name quirk chain
-  // every read to the previous one) ------------------------------------------------------------------
+  if (!cells || !r->sequential_cells) return emit_single(r, cells, read_group, target_idx, hap_idx, cell_idx, capacity, done);
+  // ---- per-cell rules as ONE sequential pass (BAMCOLS_SEQUENTIAL_CELLS): the plain statement of
+  // bam_utils_multisample.py:258-300 that the parallel window code above is tested against -------------
   const int32_t n_ref = (int32_t)r->tid_target.size();
   int64_t rows = 0;
   for (;;) {

@@ -251,6 +251,7 @@ def test_randomised_small_bams(tmp_path, monkeypatch):
             alns.append((name, int(rng.choice(flags)), tid, int(rng.integers(0, 500)),
                          tid if rng.random() < 0.8 else int(rng.integers(0, len(REFS))), int(rng.choice([-1, 0, 77]))))
         monkeypatch.setenv("BAMCOLS_GRAIN", str(int(rng.choice([1, 5, 4096]))))
+        monkeypatch.setenv("BAMCOLS_BATCH_BLOCKS", str(int(rng.choice([1, 3, 2048]))))
         path = _write(tmp_path, alns, "rand%d.bam" % case, block_payload=int(rng.choice([64, 200, 5000])))
         _same_single(path, n_threads=int(rng.choice([1, 2, 5])))
 
@@ -326,3 +327,71 @@ def test_records_with_cigar_sequence_and_tags(tmp_path):
     assert cols["read_group"].tolist() == want_rg
     assert np.array_equal(cols["target_idx"], tables.tid_target[np.array(want_tid)])
     assert np.array_equal(cols["hap_idx"], tables.tid_hap[np.array(want_tid)])
+
+
+def _multisample_both(path, tables, cell_ids, cells, **reader_kw):
+    header, recs = load_records(path)
+    want = emitter.emit_multisample(recs, tables, cell_ids)
+    with bamcols.BamColumnReader(path, **reader_kw) as r:
+        r.set_tables(tables)
+        got = r.read_all(cells=cells, chunk=257)
+    for k, w in (("read_group", want.read_group), ("target_idx", want.target_idx), ("hap_idx", want.hap_idx),
+                 ("cell_idx", want.cell_idx)):
+        assert np.array_equal(got[k], w), k
+    assert cells.names() == [n for n, _ in sorted(cell_ids.items(), key=lambda kv: kv[1])]
+
+
+def test_randomised_per_cell_bams(tmp_path, monkeypatch):
+    """The parallel per-cell window code against the record-level Python emitter: names with blanks
+    (every alignment its own read), filtered records between reads, reads that end a file alone, several
+    files sharing one cell dictionary, tiny BGZF blocks, forced thread splits and window sizes."""
+    rng = np.random.default_rng(123)
+    flags = [0, 0, 0, 16, 4, 1 | 2 | 128, 1 | 2 | 64]
+    tables = TargetTables([r[0] for r in REFS], [r[1] for r in REFS], None)
+    for case in range(40):
+        monkeypatch.setenv("BAMCOLS_GRAIN", str(int(rng.choice([1, 3, 64, 4096]))))
+        monkeypatch.setenv("BAMCOLS_BATCH_BLOCKS", str(int(rng.choice([1, 2, 7, 2048]))))   # windows of a few records
+        cell_ids, cells = {}, bamcols.CellDictionary()
+        for f in range(int(rng.integers(1, 4))):
+            alns = []
+            for read in range(int(rng.integers(1, 300))):
+                cell = "CELL%03d" % int(rng.integers(0, 12))
+                extra = " x y" if rng.random() < 0.15 else ""
+                lead = " " if rng.random() < 0.03 else ""
+                name = lead + _cell_name("f%dq%04d" % (f, read), cell, extra)
+                for _ in range(int(rng.integers(1, 5))):
+                    tid = int(rng.integers(0, len(REFS)))
+                    alns.append((name, int(rng.choice(flags)), tid, 5, tid, 9))
+            path = _write(tmp_path, alns, "c%d_%d.bam" % (case, f), block_payload=int(rng.choice([90, 400, 60000])))
+            _multisample_both(path, tables, cell_ids, cells, n_threads=int(rng.choice([1, 2, 5])))
+
+
+def test_per_cell_parallel_equals_sequential_statement(tmp_path, monkeypatch):
+    """BAMCOLS_SEQUENTIAL_CELLS selects the one-pass C++ statement of the per-cell rules; both must agree,
+    including on WHERE a short name raises (only when a later valid alignment exists)."""
+    ok = [(_cell_name("a", "C1"), 0, 0), (_cell_name("a", "C1"), 0, 1), (_cell_name("b", "C2"), 0, 2)]
+    tail_bad = ok + [("short|||name", 0, 3)]                      # ends the file alone: never looked up
+    mid_bad = ok + [("short|||name", 0, 3), (_cell_name("c", "C3"), 0, 4)]
+    tables = TargetTables([r[0] for r in REFS], [r[1] for r in REFS], None)
+    for name, alns, raises in (("ok", ok, False), ("tail", tail_bad, False), ("mid", mid_bad, True)):
+        path = _write(tmp_path, alns, name + ".bam")
+        results = []
+        for seq in (False, True):
+            if seq:
+                monkeypatch.setenv("BAMCOLS_SEQUENTIAL_CELLS", "1")
+            else:
+                monkeypatch.delenv("BAMCOLS_SEQUENTIAL_CELLS", raising=False)
+            cells = bamcols.CellDictionary()
+            with bamcols.BamColumnReader(path) as r:
+                r.set_tables(tables)
+                if raises:
+                    with pytest.raises(IndexError):
+                        r.read_all(cells=cells)
+                    continue
+                got = r.read_all(cells=cells)
+            results.append((got["read_group"].tolist(), got["cell_idx"].tolist(), cells.names()))
+        if not raises:
+            assert results[0] == results[1]
+            header, recs = load_records(path)
+            want = emitter.emit_multisample(recs, tables, {})
+            assert results[0][0] == want.read_group.tolist() and results[0][1] == want.cell_idx.tolist()
