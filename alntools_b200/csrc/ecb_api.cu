@@ -11,6 +11,7 @@
 #include "ecb_common.cuh"
 #include "ecb_scan.cuh"
 #include "ecb_group.cuh"
+#include "ecb_strip.cuh"
 #include "ecb_harvest.cuh"
 #include "ecb_finalize.cuh"
 #include "ecb_sort.cuh"
@@ -41,6 +42,8 @@ struct ecb_ctx {
   int verify_keys = 0;
   int pageable_results = 0;
   int two_phase = 0;
+  int strip_kernel = 0;   // ECB_OPT_STRIP_KERNEL (initial value from the environment variable ECB_STRIP_KERNEL)
+  int strip_warps = 32;   // warps per CTA of the strip kernel: 32, or 24 (environment variable ECB_STRIP_WARPS)
   DevBuf plog, pcur;
   // EC table
   DevBuf table;
@@ -312,6 +315,14 @@ int group_prepare_launch(ecb_ctx* c) {
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
     c->group_attr_set = true;
   }
   return ECB_OK;
@@ -323,6 +334,7 @@ void group_geometry(ecb_ctx* c, int64_t n, int* grid, int* chunk_len) {
   const int64_t warps = (int64_t)c->sm_count * ECB_GWARPS;
   int64_t cl = c->opt_chunk_len > 0 ? c->opt_chunk_len : std::min<int64_t>(4096, std::max<int64_t>(256, n / (warps * 4)));
   cl = (cl + 31) / 32 * 32;
+  if (c->strip_kernel) cl = (cl + ECB_TILE - 1) / ECB_TILE * ECB_TILE;   // whole tiles of 32 strips
   const int64_t chunks = (n + cl - 1) / cl;
   int64_t g = c->opt_grid > 0 ? c->opt_grid : std::min<int64_t>(c->sm_count, (chunks + ECB_GWARPS - 1) / ECB_GWARPS);
   *grid = (int)std::max<int64_t>(1, g);
@@ -570,6 +582,8 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   c->n_haps = n_haps;
   c->with_cells = with_cells ? 1 : 0;
   c->hint = std::max<int64_t>(alignments_hint, 0);
+  if (const char* e = getenv("ECB_STRIP_KERNEL")) c->strip_kernel = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("ECB_STRIP_WARPS")) c->strip_warps = atoi(e) == 24 ? 24 : 32;
   auto bail = [&](int code) {
     g_create_error = c->err;
     ecb_destroy(c);
@@ -612,6 +626,10 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
     case ECB_OPT_TWO_PHASE: c->two_phase = value ? 1 : 0; break;
+    case ECB_OPT_STRIP_KERNEL:
+      c->strip_kernel = value ? 1 : 0;
+      if (value == 24 || value == 32) c->strip_warps = (int)value;
+      break;
     case ECB_OPT_PAGEABLE_RESULTS:
       if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
       c->pageable_results = value ? 1 : 0; break;
@@ -685,7 +703,7 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
-  const bool two_phase = c->two_phase && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
+  const bool two_phase = c->two_phase && !c->strip_kernel && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
   if (two_phase) {
     // logs sized from the push: misses are at most one per read, reads at most one per alignment
     const u32 cap = (u32)std::min<int64_t>(0x7FFFFFFF / ECB_LOG_PARTS, n / ECB_LOG_PARTS * 3 / 4 + 4096);
@@ -704,7 +722,14 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  if (c->strip_kernel && c->strip_warps == 24) {
+    if (c->with_cells) ecb_group_strip_kernel<true, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    else ecb_group_strip_kernel<false, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+  } else if (c->strip_kernel) {
+    if (c->with_cells) ecb_group_strip_kernel<true, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
+    else ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
+  }
+  else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");

@@ -31,10 +31,10 @@ struct Key128 {
   u64 lo, hi;
 };
 
-__device__ __forceinline__ bool key_eq(const Key128& a, const Key128& b) {
+__host__ __device__ __forceinline__ bool key_eq(const Key128& a, const Key128& b) {
   return a.lo == b.lo && a.hi == b.hi;
 }
-__device__ __forceinline__ bool key_empty(const Key128& a) { return (a.lo & a.hi) == ~0ull; }
+__host__ __device__ __forceinline__ bool key_empty(const Key128& a) { return (a.lo & a.hi) == ~0ull; }
 
 // 128-bit compare-and-swap in global memory (ATOMG.E.CAS.128 on sm_100a).
 __device__ __forceinline__ Key128 atomic_cas128(void* addr, Key128 cmp, Key128 val) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void load_entry_cg(const EcbEntry* e, Key128& key, u6
   aux = (u32)(w3 >> 32);
 }
 
-__device__ __forceinline__ u32 fmix32(u32 h) {
+__host__ __device__ __forceinline__ u32 fmix32(u32 h) {
   h ^= h >> 16;
   h *= 0x85ebca6bu;
   h ^= h >> 13;
@@ -73,7 +73,7 @@ __device__ __forceinline__ u32 fmix32(u32 h) {
 }
 
 // Element code of one alignment: (main target, haplotype) packed in 31 bits.
-__device__ __forceinline__ u32 ecb_code(int target, int hap) { return ((u32)target << 5) | (u32)hap; }
+__host__ __device__ __forceinline__ u32 ecb_code(int target, int hap) { return ((u32)target << 5) | (u32)hap; }
 
 // 128-bit contribution of one DISTINCT (target, haplotype) element.  A read's key is the lane-wise
 // sum (mod 2^32) of the contributions of its distinct elements: a commutative set hash, so no
@@ -83,11 +83,11 @@ struct Mix4 {
   u32 a, b, c, d;
 };
 // multiply-fold: low ^ high half of a 32x32 -> 64 bit product (one IMAD.WIDE + one LOP3)
-__device__ __forceinline__ u32 mum32(u32 x, u32 k) {
+__host__ __device__ __forceinline__ u32 mum32(u32 x, u32 k) {
   const u64 p = (u64)x * k;
   return (u32)p ^ (u32)(p >> 32);
 }
-__device__ __forceinline__ Mix4 ecb_mix(u32 code) {
+__host__ __device__ __forceinline__ Mix4 ecb_mix(u32 code) {
   Mix4 m;
   m.a = mum32(mum32(code ^ 0x9e3779b9u, 0x85ebca6bu) ^ 0x27d4eb2fu, 0xc2b2ae35u);
   m.b = mum32(mum32(code ^ 0x7f4a7c15u, 0x2545f491u) ^ 0x165667b1u, 0x9e3779b1u);
@@ -95,12 +95,12 @@ __device__ __forceinline__ Mix4 ecb_mix(u32 code) {
   m.d = mum32(mum32(code ^ 0x1b873593u, 0xe7037ed1u) ^ 0x8ebc6af1u, 0x589965cdu);
   return m;
 }
-__device__ __forceinline__ void mix_add(Mix4& x, const Mix4& y) {
+__host__ __device__ __forceinline__ void mix_add(Mix4& x, const Mix4& y) {
   x.a += y.a; x.b += y.b; x.c += y.c; x.d += y.d;
 }
-__device__ __forceinline__ Mix4 mix_zero() { return Mix4{0u, 0u, 0u, 0u}; }
+__host__ __device__ __forceinline__ Mix4 mix_zero() { return Mix4{0u, 0u, 0u, 0u}; }
 
-__device__ __forceinline__ Key128 mix_to_key(const Mix4& m) {
+__host__ __device__ __forceinline__ Key128 mix_to_key(const Mix4& m) {
   Key128 k;
   k.lo = ((u64)m.b << 32) | m.a;
   k.hi = ((u64)m.d << 32) | m.c;

@@ -330,7 +330,7 @@ __device__ __forceinline__ u32 atoms_cas(u32 a, u32 cmp, u32 v) {
 __device__ __forceinline__ Key128 key_of(const uint4& k) {
   return Key128{((u64)k.y << 32) | k.x, ((u64)k.w << 32) | k.z};
 }
-__device__ __forceinline__ uint4 key_words(const Mix4& m) {
+__host__ __device__ __forceinline__ uint4 key_words(const Mix4& m) {
   uint4 k = make_uint4(m.a, m.b, m.c, m.d);
   if ((k.x & k.y & k.z & k.w) == 0xFFFFFFFFu) k.x = k.y = 0u;  // all-ones is the empty marker (as mix_to_key)
   return k;

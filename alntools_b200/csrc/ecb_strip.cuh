@@ -1,0 +1,321 @@
+// ecb_strip.cuh — the strip form of the grouping kernel (ECB_OPT_STRIP_KERNEL).
+//
+// Same job and same table protocol as ecb_group_insert_kernel (ecb_group.cuh; replaces
+// alntools/bam_utils.py:258-344 on int32 columns), different decomposition of the stream:
+//
+//   * window kernel: lane = ONE alignment; read boundaries, duplicate elimination and the key sums of a
+//     32-alignment window are warp collectives (about 290 warp instructions per 30 alignments);
+//   * strip kernel:  lane = a STRIP of 8 consecutive alignments kept in registers, plus the 8 alignments
+//     behind it as look-ahead (they are the neighbour lane's strip; the loads hit L1).  A read belongs
+//     to the lane whose strip holds its FIRST alignment, wherever it ends, so there is no carry between
+//     lanes, tiles or work chunks: every lane walks its 16 positions alone - head bit, duplicate test
+//     against the up to 7 earlier elements of the same read (register compares), running 128-bit sum -
+//     and closes the reads that start in its strip.  Reads longer than 8 alignments cannot be seen
+//     whole by one lane; their starts are handed to the warp-cooperative routine of the window kernel
+//     (ecb_long_read) after the tile.  A warp instruction now works on 32 x 8 alignments.
+//
+// Closed reads go through the same per-CTA hot-EC cache, miss queue and batched HBM-table insert as in
+// the window kernel (the code below repeats that block; see the header of ecb_group.cuh).
+//
+// The per-lane walk is plain C++ (`__host__ __device__`): tests/strip_host_test.cu runs it on the CPU
+// against a serial statement of the grouping rule.
+#pragma once
+#include "ecb_group.cuh"
+
+#define ECB_STRIP 8                        // alignments per lane
+#define ECB_TILE (32 * ECB_STRIP)          // alignments per warp and tile
+#define ECB_STRIP_SPAN (2 * ECB_STRIP)     // positions a lane looks at (its strip + look-ahead)
+
+// What a lane knows about its 16 positions: element codes and a bit per position that starts a read
+// (bit i: position p0 + i; the first position beyond the push counts as a start, it closes the last read).
+struct StripLane {
+  u32 c[ECB_STRIP_SPAN];
+  u32 hm;
+};
+
+// Walking state of a lane.
+struct StripWalk {
+  Mix4 sum;        // key sum of the open read
+  int st;          // index (0..7) of the open read's first alignment
+  bool open;       // a read that started in this strip is open
+  bool has_long;   // this strip starts a read with more than 8 alignments ...
+  u32 long_start;  // ... at this position of the push
+};
+
+__host__ __device__ __forceinline__ void strip_walk_init(StripWalk& W) {
+  W.sum = mix_zero();
+  W.st = 0;
+  W.open = false;
+  W.has_long = false;
+  W.long_start = 0u;
+}
+
+// Head bits and codes from 16 + 1 read-group values (rgprev = the value in front of the strip; any value
+// that differs from rg[0] when the strip starts the push) and the target / haplotype columns.  Positions
+// at or beyond n must hold ECB_RG_SENTINEL in rg.
+__host__ __device__ __forceinline__ void strip_lane_build(StripLane& L, int rgprev, const int (&rg)[ECB_STRIP_SPAN],
+                                                          const int (&tg)[ECB_STRIP_SPAN],
+                                                          const int (&hp)[ECB_STRIP_SPAN]) {
+  u32 hm = rg[0] != rgprev ? 1u : 0u;
+#pragma unroll
+  for (int i = 1; i < ECB_STRIP_SPAN; ++i) hm |= rg[i] != rg[i - 1] ? (1u << i) : 0u;
+#pragma unroll
+  for (int i = 0; i < ECB_STRIP_SPAN; ++i) L.c[i] = ecb_code(tg[i], hp[i]);
+  L.hm = hm;
+}
+
+// One position of the walk (I is a compile-time constant after unrolling).  n_own = number of positions
+// of the strip that lie inside the push (<= 0: none).  Returns true when a read that started in this
+// strip closes in front of position I: then *s_idx / *len describe it and `key_sum` is its key sum.
+__host__ __device__ __forceinline__ bool strip_walk_step(const StripLane& L, int I, int n_own, StripWalk& W,
+                                                         Mix4& key_sum, int& s_idx, int& len) {
+  const bool h = ((L.hm >> I) & 1u) != 0u;
+  const bool closes = h && W.open;
+  if (closes) {
+    key_sum = W.sum;
+    s_idx = W.st;
+    len = I - W.st;
+  }
+  if (h) {
+    W.open = false;
+    if (I < ECB_STRIP && I < n_own) {
+      // the read is short iff another start (or the end of the push) follows within 8 positions
+      if (((L.hm >> (I + 1)) & 0xFFu) == 0u) {
+        W.has_long = true;
+        W.long_start = (u32)I;
+      } else {
+        W.open = true;
+        W.st = I;
+        W.sum = mix_zero();
+      }
+    }
+  }
+  if (W.open) {
+    // an element counts once per read: equal codes among the up to 7 earlier positions of this read
+    u32 eqm = 0u;
+#pragma unroll
+    for (int k = 1; k < ECB_STRIP; ++k)
+      if (I - k >= 0) eqm |= L.c[I] == L.c[I - k] ? (1u << (k - 1)) : 0u;
+    const bool dup = (eqm & ((1u << (I - W.st)) - 1u)) != 0u;
+    if (!dup) mix_add(W.sum, ecb_mix(L.c[I]));
+  }
+  return closes;
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ int4 ld_col4(const int32_t* p, u64 pol) {
+  int4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+
+// Hot-EC cache probe, miss queue and batched table insert for the closed reads of the warp (one per lane
+// at most; `ins` false = nothing).  Warp-uniform control flow: every lane calls it.  Same protocol as
+// the block at the end of the window loop of ecb_group_insert_kernel.
+struct StripSmemAddr {
+  u32 qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen;
+};
+
+// The batched table insert is reached from 17 places of the unrolled walk: one out-of-line copy keeps the
+// kernel inside the instruction cache (it runs once per 64 misses).
+template <bool WITH_CELLS>
+__device__ __noinline__ void strip_insert64(const GroupParams& P, u32 qk, u32 qr, u32 base, int lane) {
+  insert_misses<WITH_CELLS>(P, qk, qr, base + lane, true, base + 32 + lane, true);
+}
+
+template <bool WITH_CELLS>
+__device__ __forceinline__ void strip_commit(const GroupParams& P, const StripSmemAddr& A, bool use_cache, bool ins,
+                                             const uint4& key, u32 s, u32 len, u32& qn, u32 lt_mask, int lane) {
+  bool miss = ins;
+  if (use_cache && ins) {
+    const u32 cidx = (key.y >> 7) & (ECB_CACHE - 1);
+    const uint4 ck = lds128(A.a_key + cidx * 16u);
+    const u32 cf = lds32(A.a_first + cidx * 4u);
+    bool hit = ck.x == key.x && ck.y == key.y && ck.z == key.z && ck.w == key.w;
+    if (!hit && (ck.x & ck.y & ck.z & ck.w) == 0xFFFFFFFFu) {
+#if ECB_ADMIT_SECOND
+      const u32 sbit = 1u << (key.z & 31u);
+      const bool again = (atoms_or(A.a_seen + ((key.z >> 5) & (ECB_SEEN_WORDS - 1)) * 4u, sbit) & sbit) != 0u;
+#else
+      const bool again = true;
+#endif
+      if (again && atoms_cas(A.a_lock + cidx * 4u, 0u, 1u) == 0u) {
+        sts64(A.a_rep + cidx * 8u, s, len);
+        sts128(A.a_key + cidx * 16u, key);
+        hit = true;
+      }
+    }
+    if (hit) {
+      reds_add(A.a_cnt + cidx * 4u, 1u);
+      if (s < cf) reds_min(A.a_first + cidx * 4u, s);
+      miss = false;
+    }
+  }
+  const u32 mm = __ballot_sync(ECB_FULL, miss);
+  if (mm) {
+    if (miss) {
+      const u32 q = qn + __popc(mm & lt_mask);
+      sts128(A.qk + q * 16u, key);
+      sts64(A.qr + q * 8u, s, len);
+      prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
+    }
+    qn += __popc(mm);
+    __syncwarp();
+    if (qn >= 64u) {
+      qn -= 64u;
+      strip_insert64<WITH_CELLS>(P, A.qk, A.qr, qn, lane);
+      __syncwarp();
+    }
+  }
+}
+
+// WARPS: warps per CTA (one CTA per SM).  32 warps leave 64 registers per thread, 24 leave 80.
+template <bool WITH_CELLS, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __grid_constant__ GroupParams P) {
+  constexpr int THREADS = 32 * WARPS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 lt_mask = (1u << lane) - 1u;
+  const int n = P.n;
+  const bool use_cache = !WITH_CELLS && P.use_cache;
+  const int32_t* __restrict__ const c_rg = P.rg;
+  const int32_t* __restrict__ const c_tg = P.tg;
+  const int32_t* __restrict__ const c_hp = P.hp;
+  const u64 col_policy = make_evict_first_policy();
+  // lanes 0..23 pull the next tile into L2: 3 columns x 8 lines of 128 bytes
+  const int32_t* const pf_col = (lane < 8 ? c_rg : (lane < 16 ? c_tg : c_hp)) + (lane & 7) * 32;
+  const bool pf_lane = lane < 24;
+
+  if (use_cache) {
+    for (int i = tid; i < ECB_CACHE; i += THREADS) {
+      S.c_key[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      S.c_lock[i] = 0u;
+      S.c_cnt[i] = 0u;
+      S.c_first[i] = 0xFFFFFFFFu;
+    }
+    for (int i = tid; i < ECB_SEEN_WORDS; i += THREADS) S.seen[i] = 0u;
+  }
+  __syncthreads();
+
+  StripSmemAddr A;
+  A.qk = smem_u32(S.q_key[warp]);
+  A.qr = smem_u32(S.q_rep[warp]);
+  A.a_key = smem_u32(S.c_key);
+  A.a_lock = smem_u32(S.c_lock);
+  A.a_cnt = smem_u32(S.c_cnt);
+  A.a_first = smem_u32(S.c_first);
+  A.a_rep = smem_u32(S.c_rep);
+  A.a_seen = smem_u32(S.seen);
+  u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
+  u32 reads_counted = 0;  // per lane
+
+  for (;;) {
+    u32 ci = 0;
+    if (lane == 0) ci = atomicAdd(&P.ctr->chunk_next, 1u);
+    ci = __shfl_sync(ECB_FULL, ci, 0);
+    const long long cb64 = (long long)ci * P.chunk_len;   // chunk_len is a multiple of ECB_TILE here
+    if (cb64 >= n) break;
+    const int cb = (int)cb64;
+    const int ce = (int)min(cb64 + P.chunk_len, (long long)n);
+
+    for (int tb = cb; tb < ce; tb += ECB_TILE) {
+      const int p0 = tb + ECB_STRIP * lane;
+      if (pf_lane && tb + ECB_TILE + (lane & 7) * 32 < n) prefetch_l2(pf_col + tb + ECB_TILE);
+
+      // ---- the lane's 16 positions ------------------------------------------------------------------
+      StripLane L;
+      {
+        int rg[ECB_STRIP_SPAN], tg[ECB_STRIP_SPAN], hp[ECB_STRIP_SPAN];
+        int rgprev = ECB_RG_SENTINEL;
+        if (tb + ECB_TILE + ECB_STRIP <= n) {   // warp-uniform: every position of every lane is inside the push
+#pragma unroll
+          for (int q = 0; q < ECB_STRIP_SPAN / 4; ++q) {
+            const int4 a = ld_col4(c_rg + p0 + 4 * q, col_policy);
+            const int4 b = ld_col4(c_tg + p0 + 4 * q, col_policy);
+            const int4 d = ld_col4(c_hp + p0 + 4 * q, col_policy);
+            rg[4 * q] = a.x; rg[4 * q + 1] = a.y; rg[4 * q + 2] = a.z; rg[4 * q + 3] = a.w;
+            tg[4 * q] = b.x; tg[4 * q + 1] = b.y; tg[4 * q + 2] = b.z; tg[4 * q + 3] = b.w;
+            hp[4 * q] = d.x; hp[4 * q + 1] = d.y; hp[4 * q + 2] = d.z; hp[4 * q + 3] = d.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < ECB_STRIP_SPAN; ++i) {
+            const bool in = p0 + i < n;
+            rg[i] = in ? c_rg[p0 + i] : ECB_RG_SENTINEL;
+            tg[i] = in ? c_tg[p0 + i] : 0;
+            hp[i] = in ? c_hp[p0 + i] : 0;
+          }
+        }
+        if (p0 > 0 && p0 <= n) rgprev = c_rg[p0 - 1];
+        strip_lane_build(L, rgprev, rg, tg, hp);
+      }
+      const int n_own = n - p0;
+
+      // ---- walk: own strip, then the look-ahead for as long as some lane's last read is open ---------
+      StripWalk W;
+      strip_walk_init(W);
+#pragma unroll
+      for (int i = 0; i < ECB_STRIP_SPAN; ++i) {
+        if (i >= ECB_STRIP && !__any_sync(ECB_FULL, W.open)) break;
+        Mix4 ks = mix_zero();
+        int s_idx = 0, len = 0;
+        bool ins = strip_walk_step(L, i, n_own, W, ks, s_idx, len);
+        if (P.drop_last && p0 + i == n) ins = false;   // the read that ends the push is not counted
+        if (ins) ++reads_counted;
+        strip_commit<WITH_CELLS>(P, A, use_cache, ins, key_words(ks), (u32)(p0 + s_idx), (u32)len, qn, lt_mask, lane);
+      }
+
+      // ---- reads with more than 8 alignments: warp-cooperative, one after the other -----------------
+      u32 lm = __ballot_sync(ECB_FULL, W.has_long);
+      if (lm) {
+        bool ins = false;
+        uint4 key = make_uint4(0u, 0u, 0u, 0u);
+        u32 s = 0u, len = 0u;
+        int k = 0;
+        while (lm) {
+          const int src = __ffs(lm) - 1;
+          lm &= lm - 1;
+          const int start = tb + ECB_STRIP * src + (int)__shfl_sync(ECB_FULL, W.long_start, src);
+          const LongRead lr = ecb_long_read(c_rg, c_tg, c_hp, n, start, P.n_targets, P.n_haps, P.ctr);
+          if (lane == k) {   // the k-th long read of the tile is committed by lane k
+            key = lr.key;
+            s = (u32)start;
+            len = (u32)lr.len;
+            ins = !(P.drop_last && start + lr.len == n);
+          }
+          ++k;
+        }
+        if (ins) ++reads_counted;
+        strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
+      }
+    }
+  }
+
+  // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
+  if (qn) insert_misses<WITH_CELLS>(P, A.qk, A.qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+  reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
+  if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
+  __syncthreads();
+  if (use_cache) {
+    for (int i = tid; i < ECB_CACHE; i += THREADS) {
+      const u32 cnt = S.c_cnt[i];
+      if (cnt) {
+        const Key128 key = key_of(S.c_key[i]);
+        const u32 first = S.c_first[i];
+        const uint2 rep = S.c_rep[i];
+        const u32 slot = global_upsert(P, key, cnt, first, rep.x, rep.y);
+        if (slot == ECB_NONE) {  // table too full: park the entry, the host grows the table and replays it
+          const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
+          P.spill[si] = EcbSpill{key.lo, key.hi, cnt, first, rep.x, rep.y};
+        }
+      }
+    }
+  }
+}
+
+#endif  // __CUDACC__

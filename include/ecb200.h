@@ -65,9 +65,13 @@ enum ecb_option {
   ECB_OPT_CHUNK_LEN = 7,        /* alignments per work chunk of the grouping kernel (0 = automatic) */
   ECB_OPT_PAGEABLE_RESULTS = 8, /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
                                    cheaper for a context that finalizes once, slower when reused */
-  ECB_OPT_TWO_PHASE = 9         /* 1: the grouping kernel appends cache misses to per-partition logs and a second
+  ECB_OPT_TWO_PHASE = 9,        /* 1: the grouping kernel appends cache misses to per-partition logs and a second
                                    kernel inserts them partition by partition (table slice resident in L2);
                                    experimental, single-sample path only */
+  ECB_OPT_STRIP_KERNEL = 10     /* 1: the strip form of the grouping kernel (a lane walks 8 consecutive alignments
+                                   in registers instead of one alignment per lane; same table protocol, same
+                                   results); 24 or 32 also select that many warps per CTA.  Initial value:
+                                   environment variables ECB_STRIP_KERNEL (0/1) and ECB_STRIP_WARPS (24/32) */
 };
 
 typedef struct ecb_result {
