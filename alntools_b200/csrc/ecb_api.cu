@@ -44,6 +44,7 @@ struct ecb_ctx {
   int two_phase = 0;
   int strip_kernel = 0;   // ECB_OPT_STRIP_KERNEL (initial value from the environment variable ECB_STRIP_KERNEL)
   int strip_warps = 32;   // warps per CTA of the strip kernel: 32, or 24 (environment variable ECB_STRIP_WARPS)
+  int strip_dense = 0;    // 24 warps + closed reads parked and looked up 32 at a time (value 124)
   DevBuf plog, pcur;
   // EC table
   DevBuf table;
@@ -323,6 +324,10 @@ int group_prepare_launch(ecb_ctx* c) {
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
     c->group_attr_set = true;
   }
   return ECB_OK;
@@ -583,7 +588,10 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   c->with_cells = with_cells ? 1 : 0;
   c->hint = std::max<int64_t>(alignments_hint, 0);
   if (const char* e = getenv("ECB_STRIP_KERNEL")) c->strip_kernel = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("ECB_STRIP_WARPS")) c->strip_warps = atoi(e) == 24 ? 24 : 32;
+  if (const char* e = getenv("ECB_STRIP_WARPS")) {
+    c->strip_warps = (atoi(e) == 24 || atoi(e) == 124) ? 24 : 32;
+    c->strip_dense = atoi(e) == 124;
+  }
   auto bail = [&](int code) {
     g_create_error = c->err;
     ecb_destroy(c);
@@ -628,7 +636,8 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_TWO_PHASE: c->two_phase = value ? 1 : 0; break;
     case ECB_OPT_STRIP_KERNEL:
       c->strip_kernel = value ? 1 : 0;
-      if (value == 24 || value == 32) c->strip_warps = (int)value;
+      if (value == 24 || value == 32) { c->strip_warps = (int)value; c->strip_dense = 0; }
+      if (value == 124) { c->strip_warps = 24; c->strip_dense = 1; }
       break;
     case ECB_OPT_PAGEABLE_RESULTS:
       if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
@@ -722,7 +731,10 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (c->strip_kernel && c->strip_warps == 24) {
+  if (c->strip_kernel && c->strip_dense) {
+    if (c->with_cells) ecb_group_strip_kernel<true, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    else ecb_group_strip_kernel<false, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+  } else if (c->strip_kernel && c->strip_warps == 24) {
     if (c->with_cells) ecb_group_strip_kernel<true, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
     else ecb_group_strip_kernel<false, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
   } else if (c->strip_kernel) {

@@ -22,6 +22,12 @@
 #pragma once
 #include "ecb_group.cuh"
 
+// Timing experiments (never shipped; results are wrong by construction): 1 = misses are dropped instead of
+// being inserted into the HBM table, 2 = closed reads are only folded into a checksum (walk cost alone).
+#ifndef ECB_STRIP_EXPERIMENT
+#define ECB_STRIP_EXPERIMENT 0
+#endif
+
 #define ECB_STRIP 8                        // alignments per lane
 #define ECB_TILE (32 * ECB_STRIP)          // alignments per warp and tile
 #define ECB_STRIP_SPAN (2 * ECB_STRIP)     // positions a lane looks at (its strip + look-ahead)
@@ -33,20 +39,20 @@ struct StripLane {
   u32 hm;
 };
 
-// Walking state of a lane.
+// Walking state of a lane (plain 32-bit words: the compiler keeps them in registers and predicates).
 struct StripWalk {
   Mix4 sum;        // key sum of the open read
   int st;          // index (0..7) of the open read's first alignment
-  bool open;       // a read that started in this strip is open
-  bool has_long;   // this strip starts a read with more than 8 alignments ...
-  u32 long_start;  // ... at this position of the push
+  u32 open;        // 1: a read that started in this strip is open
+  u32 has_long;    // 1: this strip starts a read with more than 8 alignments ...
+  u32 long_start;  // ... at this index of the strip
 };
 
 __host__ __device__ __forceinline__ void strip_walk_init(StripWalk& W) {
   W.sum = mix_zero();
   W.st = 0;
-  W.open = false;
-  W.has_long = false;
+  W.open = 0u;
+  W.has_long = 0u;
   W.long_start = 0u;
 }
 
@@ -64,27 +70,25 @@ __host__ __device__ __forceinline__ void strip_lane_build(StripLane& L, int rgpr
   L.hm = hm;
 }
 
-// One position of the walk (I is a compile-time constant after unrolling).  n_own = number of positions
-// of the strip that lie inside the push (<= 0: none).  Returns true when a read that started in this
-// strip closes in front of position I: then *s_idx / *len describe it and `key_sum` is its key sum.
-__host__ __device__ __forceinline__ bool strip_walk_step(const StripLane& L, int I, int n_own, StripWalk& W,
-                                                         Mix4& key_sum, int& s_idx, int& len) {
-  const bool h = ((L.hm >> I) & 1u) != 0u;
-  const bool closes = h && W.open;
-  if (closes) {
-    key_sum = W.sum;
-    s_idx = W.st;
-    len = I - W.st;
-  }
-  if (h) {
-    W.open = false;
+// One position of the walk, in two halves (I is a compile-time constant after unrolling).
+// strip_walk_closes: a read that started in this strip closes in front of position I; it is the read
+// [W.st, I) of the strip and W.sum is its key sum - the caller uses them before strip_walk_advance.
+__host__ __device__ __forceinline__ bool strip_walk_closes(const StripLane& L, int I, const StripWalk& W) {
+  return (((L.hm >> I) & W.open) & 1u) != 0u;
+}
+
+// strip_walk_advance: take position I in.  n_own = number of positions of the strip that lie inside the
+// push (<= 0: none).
+__host__ __device__ __forceinline__ void strip_walk_advance(const StripLane& L, int I, int n_own, StripWalk& W) {
+  if ((L.hm >> I) & 1u) {
+    W.open = 0u;
     if (I < ECB_STRIP && I < n_own) {
       // the read is short iff another start (or the end of the push) follows within 8 positions
       if (((L.hm >> (I + 1)) & 0xFFu) == 0u) {
-        W.has_long = true;
+        W.has_long = 1u;
         W.long_start = (u32)I;
       } else {
-        W.open = true;
+        W.open = 1u;
         W.st = I;
         W.sum = mix_zero();
       }
@@ -96,10 +100,8 @@ __host__ __device__ __forceinline__ bool strip_walk_step(const StripLane& L, int
 #pragma unroll
     for (int k = 1; k < ECB_STRIP; ++k)
       if (I - k >= 0) eqm |= L.c[I] == L.c[I - k] ? (1u << (k - 1)) : 0u;
-    const bool dup = (eqm & ((1u << (I - W.st)) - 1u)) != 0u;
-    if (!dup) mix_add(W.sum, ecb_mix(L.c[I]));
+    if ((eqm & ((1u << (I - W.st)) - 1u)) == 0u) mix_add(W.sum, ecb_mix(L.c[I]));
   }
-  return closes;
 }
 
 #ifdef __CUDACC__
@@ -166,14 +168,74 @@ __device__ __forceinline__ void strip_commit(const GroupParams& P, const StripSm
     __syncwarp();
     if (qn >= 64u) {
       qn -= 64u;
+#if ECB_STRIP_EXPERIMENT != 1
       strip_insert64<WITH_CELLS>(P, A.qk, A.qr, qn, lane);
+#endif
       __syncwarp();
     }
   }
 }
 
-// WARPS: warps per CTA (one CTA per SM).  32 warps leave 64 registers per thread, 24 leave 80.
+// Queue depth per warp: the miss queue of the window kernel (96 entries), or - DENSE, 24 warps - 128
+// entries that hold two stacks: misses grow from entry 0 upwards, closed reads that have not been looked
+// up in the cache yet grow from entry 127 downwards.
+#define ECB_DQ 128
+
+template <int WARPS, bool DENSE>
+__device__ __forceinline__ StripSmemAddr strip_smem_addr(GroupSmem& S, int warp) {
+  static_assert(!DENSE || WARPS * ECB_DQ <= ECB_GWARPS * ECB_MQ, "dense queues do not fit in the miss-queue area");
+  StripSmemAddr A;
+  A.qk = smem_u32(&S.q_key[0][0]) + (DENSE ? (u32)warp * ECB_DQ * 16u : (u32)warp * ECB_MQ * 16u);
+  A.qr = smem_u32(&S.q_rep[0][0]) + (DENSE ? (u32)warp * ECB_DQ * 8u : (u32)warp * ECB_MQ * 8u);
+  A.a_key = smem_u32(S.c_key);
+  A.a_lock = smem_u32(S.c_lock);
+  A.a_cnt = smem_u32(S.c_cnt);
+  A.a_first = smem_u32(S.c_first);
+  A.a_rep = smem_u32(S.c_rep);
+  A.a_seen = smem_u32(S.seen);
+  return A;
+}
+
+// DENSE: closed reads are first parked (one ballot, two stores) ...
+__device__ __forceinline__ void strip_stage(const StripSmemAddr& A, bool ins, const uint4& key, u32 s, u32 len, u32& cn,
+                                            u32 lt_mask) {
+  const u32 mm = __ballot_sync(ECB_FULL, ins);
+  if (mm) {
+    if (ins) {
+      const u32 j = (ECB_DQ - 1u) - (cn + __popc(mm & lt_mask));
+      sts128(A.qk + j * 16u, key);
+      sts64(A.qr + j * 8u, s, len);
+    }
+    cn += __popc(mm);
+    __syncwarp();
+  }
+}
+
+// ... and go through the cache 32 at a time, every lane busy (`count` < 32 only for the leftovers at the
+// end).  Out of line: reached from every step of the unrolled walk.  cn = parked reads after this call.
+// Returns the new fill of the miss stack.
 template <bool WITH_CELLS, int WARPS>
+__device__ __noinline__ u32 strip_drain(const GroupParams& P, u32 cn, u32 count, u32 qn, bool use_cache) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const StripSmemAddr A = strip_smem_addr<WARPS, true>(S, warp);
+  const bool has = (u32)lane < count;
+  const u32 j = (ECB_DQ - 1u) - (cn + (u32)lane);
+  uint4 key = make_uint4(0u, 0u, 0u, 0u);
+  uint2 r = make_uint2(0u, 0u);
+  if (has) {
+    key = lds128(A.qk + j * 16u);
+    r = lds64(A.qr + j * 8u);
+  }
+  __syncwarp();
+  strip_commit<WITH_CELLS>(P, A, use_cache, has, key, r.x, r.y, qn, (1u << lane) - 1u, lane);
+  return qn;
+}
+
+// WARPS: warps per CTA (one CTA per SM).  32 warps leave 64 registers per thread, 24 leave 80.
+// DENSE (24 warps): cache look-ups and table inserts run on full warps (see strip_stage / strip_drain).
+template <bool WITH_CELLS, int WARPS, bool DENSE = false>
 __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __grid_constant__ GroupParams P) {
   constexpr int THREADS = 32 * WARPS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -202,16 +264,12 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
   }
   __syncthreads();
 
-  StripSmemAddr A;
-  A.qk = smem_u32(S.q_key[warp]);
-  A.qr = smem_u32(S.q_rep[warp]);
-  A.a_key = smem_u32(S.c_key);
-  A.a_lock = smem_u32(S.c_lock);
-  A.a_cnt = smem_u32(S.c_cnt);
-  A.a_first = smem_u32(S.c_first);
-  A.a_rep = smem_u32(S.c_rep);
-  A.a_seen = smem_u32(S.seen);
+  const StripSmemAddr A = strip_smem_addr<WARPS, DENSE>(S, warp);
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
+  u32 cn = 0;             // DENSE: closed reads parked in front of the cache (warp-uniform)
+#if ECB_STRIP_EXPERIMENT == 2
+  u32 sink = 0;
+#endif
   u32 reads_counted = 0;  // per lane
 
   for (;;) {
@@ -261,17 +319,30 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
       strip_walk_init(W);
 #pragma unroll
       for (int i = 0; i < ECB_STRIP_SPAN; ++i) {
-        if (i >= ECB_STRIP && !__any_sync(ECB_FULL, W.open)) break;
-        Mix4 ks = mix_zero();
-        int s_idx = 0, len = 0;
-        bool ins = strip_walk_step(L, i, n_own, W, ks, s_idx, len);
+        if (i >= ECB_STRIP && !__any_sync(ECB_FULL, W.open != 0u)) break;
+        bool ins = strip_walk_closes(L, i, W);
         if (P.drop_last && p0 + i == n) ins = false;   // the read that ends the push is not counted
         if (ins) ++reads_counted;
-        strip_commit<WITH_CELLS>(P, A, use_cache, ins, key_words(ks), (u32)(p0 + s_idx), (u32)len, qn, lt_mask, lane);
+        const uint4 key = key_words(W.sum);
+        const u32 s = (u32)(p0 + W.st), len = (u32)(i - W.st);
+#if ECB_STRIP_EXPERIMENT == 2
+        if (ins) sink ^= key.x ^ key.y ^ key.z ^ key.w ^ s ^ len;
+        ins = false;
+#endif
+        if constexpr (DENSE) {
+          strip_stage(A, ins, key, s, len, cn, lt_mask);
+          if (cn >= 32u) {
+            cn -= 32u;
+            qn = strip_drain<WITH_CELLS, WARPS>(P, cn, 32u, qn, use_cache);
+          }
+        } else {
+          strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
+        }
+        strip_walk_advance(L, i, n_own, W);
       }
 
       // ---- reads with more than 8 alignments: warp-cooperative, one after the other -----------------
-      u32 lm = __ballot_sync(ECB_FULL, W.has_long);
+      u32 lm = __ballot_sync(ECB_FULL, W.has_long != 0u);
       if (lm) {
         bool ins = false;
         uint4 key = make_uint4(0u, 0u, 0u, 0u);
@@ -291,12 +362,26 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
           ++k;
         }
         if (ins) ++reads_counted;
-        strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
+        if constexpr (DENSE) {
+          strip_stage(A, ins, key, s, len, cn, lt_mask);
+          if (cn >= 32u) {
+            cn -= 32u;
+            qn = strip_drain<WITH_CELLS, WARPS>(P, cn, 32u, qn, use_cache);
+          }
+        } else {
+          strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
+        }
       }
     }
   }
 
-  // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
+  // ---- leftovers of the queues, then the cache goes into the HBM table --------------------------------
+  if constexpr (DENSE) if (cn) qn = strip_drain<WITH_CELLS, WARPS>(P, 0u, cn, qn, use_cache);
+#if ECB_STRIP_EXPERIMENT == 1
+  qn = 0;
+#elif ECB_STRIP_EXPERIMENT == 2
+  if (sink == 0x12345678u) atomicAdd(&P.ctr->scratch[7], 1u);
+#endif
   if (qn) insert_misses<WITH_CELLS>(P, A.qk, A.qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);

@@ -70,7 +70,8 @@ enum ecb_option {
                                    experimental, single-sample path only */
   ECB_OPT_STRIP_KERNEL = 10     /* 1: the strip form of the grouping kernel (a lane walks 8 consecutive alignments
                                    in registers instead of one alignment per lane; same table protocol, same
-                                   results); 24 or 32 also select that many warps per CTA.  Initial value:
+                                   results); 24 or 32 also select that many warps per CTA, 124 = 24 warps with the
+                                   cache look-ups batched 32 at a time.  Initial value:
                                    environment variables ECB_STRIP_KERNEL (0/1) and ECB_STRIP_WARPS (24/32) */
 };
 

@@ -67,14 +67,13 @@ static int run_case(unsigned seed, int n, int mode, bool verbose) {
       StripWalk W;
       strip_walk_init(W);
       for (int k = 0; k < ECB_STRIP_SPAN; ++k) {
-        Mix4 ks = mix_zero();
-        int s_idx = 0, len = 0;
-        if (strip_walk_step(L, k, n - p0, W, ks, s_idx, len)) {
-          Closed& e = got[p0 + s_idx];
-          e.len = len;
-          e.key = mix_to_key(ks);
+        if (strip_walk_closes(L, k, W)) {
+          Closed& e = got[p0 + W.st];
+          e.len = k - W.st;
+          e.key = mix_to_key(W.sum);
           e.times++;
         }
+        strip_walk_advance(L, k, n - p0, W);
       }
       if (W.open) {
         if (verbose) printf("lane left a read open: tile %d lane %d\n", tb, lane);
