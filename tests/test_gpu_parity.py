@@ -451,9 +451,11 @@ def test_key_verification_option_finds_no_collision(native):
 STRIP_READY = os.environ.get("ECB_TEST_STRIP") == "1"
 
 
-@pytest.mark.skipif(not STRIP_READY, reason="strip kernel: written without GPU time left in round 1, first run "
-                                            "pending (set ECB_TEST_STRIP=1)")
-@pytest.mark.parametrize("warps", [32, 24])
+@pytest.mark.skipif(not STRIP_READY, reason="strip kernel (experimental, off by default): this test and the whole GPU "
+                    "suite under ECB_STRIP_KERNEL=1 ECB_STRIP_WARPS=124 passed on a B200 (profiles/r1_strip_eval.log); the "
+                    "address-space fix of its out-of-line insert came after the last GPU minute of round 1, so the "
+                    "test stays opt-in (ECB_TEST_STRIP=1) until it has run again")
+@pytest.mark.parametrize("warps", [32, 24, 124])
 def test_strip_kernel_gives_the_same_result(native, warps):
     """ECB_OPT_STRIP_KERNEL: a lane walks 8 consecutive alignments in registers.  Same matrices as the
     oracle over short reads, reads around the 8-alignment limit of a lane, long reads, duplicates, sizes
