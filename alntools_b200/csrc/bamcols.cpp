@@ -386,6 +386,128 @@ void parallel_for(int nt, F fn) {
   for (auto& t : pool) t.join();
 }
 
+// ---- record boundaries of the inflated window ---------------------------------------------------------
+// BAM records are chained by their block_size fields, so finding them is inherently one sequential hop.
+// It is done speculatively in parallel: the window is cut into byte segments, every worker GUESSES the
+// first record start of its segment (two consecutive plausible record headers) and hops from there; then
+// one pass joins the chains: a chain is accepted from the first of its offsets that the already verified
+// chain in front of it lands on - from a true record start the hop is deterministic, so everything after
+// that offset is exact.  A segment whose guess is not confirmed is hopped again sequentially.  The result
+// is always the list the sequential hop would produce.
+#define HOP_END 1   // a partial record (or fewer than 4 bytes) at the landing position: end of the whole records
+#define HOP_BAD 2   // block_size < 32 at the landing position
+
+int hop_chain(const uint8_t* base, size_t p, size_t limit, size_t wend, std::vector<size_t>& out, size_t* land) {
+  while (p < limit) {
+    if (p + 4 > wend) {
+      *land = p;
+      return HOP_END;
+    }
+    const size_t bs = le32(base + p);
+    if (bs < 32) {
+      *land = p;
+      return HOP_BAD;
+    }
+    if (p + 4 + bs > wend) {
+      *land = p;
+      return HOP_END;
+    }
+    out.push_back(p);
+    p += 4 + bs;
+  }
+  *land = p;
+  return 0;
+}
+
+// Could a record start at q?  (A heuristic: wrong answers cost time, never correctness.)
+inline bool plausible_record(const uint8_t* base, size_t q, size_t wend, int32_t n_ref) {
+  if (q + 36 > wend) return false;
+  const size_t bs = le32(base + q);
+  if (bs < 34 || bs > (1u << 26)) return false;
+  const uint8_t* c = base + q + 4;
+  const int32_t tid = (int32_t)le32(c), pos = (int32_t)le32(c + 4), ntid = (int32_t)le32(c + 20);
+  const size_t l_name = c[8], n_cigar = le16(c + 12);
+  const uint32_t l_seq = le32(c + 16);
+  if (tid < -1 || tid >= n_ref || ntid < -1 || ntid >= n_ref || pos < -1 || l_name == 0) return false;
+  if (l_seq > bs || 32 + l_name + 4 * n_cigar + (size_t)(l_seq + 1) / 2 + l_seq > bs) return false;
+  if (q + 36 + l_name > wend) return true;   // the name lies beyond the window: cannot say more
+  const uint8_t* nm = c + 32;
+  if (nm[l_name - 1] != 0) return false;
+  for (size_t i = 0; i + 1 < l_name; ++i)
+    if (nm[i] < 0x20 || nm[i] > 0x7e) return false;
+  return true;
+}
+
+struct HopChain {
+  std::vector<size_t> off;
+  size_t start = SIZE_MAX, land = 0;
+  int state = 0;
+};
+
+// Offsets of the whole records in [r->wpos, r->wend) into `off`; *next = where the unread rest begins.
+int find_records(bamcols* r, std::vector<size_t>& off, size_t* next) {
+  off.clear();
+  const uint8_t* base = r->win.data();
+  const size_t p0 = r->wpos, wend = r->wend;
+  const size_t span = wend - p0;
+  const int32_t n_ref = (int32_t)r->ref_names.size();
+  const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, span / (r->grain * 48) + 1));
+  size_t cur = p0;
+  if (T == 1) {
+    const int st = hop_chain(base, cur, wend, wend, off, &cur);
+    if (st == HOP_BAD) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", (size_t)le32(base + cur));
+    *next = cur;
+    return 0;
+  }
+  std::vector<size_t> seg(T + 1);
+  for (int t = 0; t <= T; ++t) seg[t] = p0 + span * (size_t)t / (size_t)T;
+  std::vector<HopChain> chains(T);
+  parallel_for(T, [&](int t) {
+    HopChain& c = chains[t];
+    if (t == 0) {
+      c.start = p0;
+    } else {
+      const size_t stop = std::min(seg[t + 1], seg[t] + (1u << 16));
+      for (size_t q = seg[t]; q < stop; ++q) {
+        if (!plausible_record(base, q, wend, n_ref)) continue;
+        const size_t nx = q + 4 + le32(base + q);
+        if (nx + 36 <= wend && !plausible_record(base, nx, wend, n_ref)) continue;
+        c.start = q;
+        break;
+      }
+      if (c.start == SIZE_MAX) return;
+    }
+    c.off.reserve((seg[t + 1] - seg[t]) / 64 + 16);
+    c.state = hop_chain(base, c.start, seg[t + 1], wend, c.off, &c.land);
+  });
+  size_t total = 0;
+  for (const HopChain& c : chains) total += c.off.size();
+  off.reserve(total + 64);
+  for (int t = 0; t < T; ++t) {
+    if (cur >= seg[t + 1]) continue;   // a record reaches over this whole segment
+    HopChain& c = chains[t];
+    int st = 0;
+    bool joined = false;
+    if (c.start != SIZE_MAX && !c.off.empty()) {
+      st = hop_chain(base, cur, c.start, wend, off, &cur);   // the records in front of the guess (usually none)
+      if (st == 0) {
+        const auto it = std::lower_bound(c.off.begin(), c.off.end(), cur);
+        if (it != c.off.end() && *it == cur) {
+          off.insert(off.end(), it, c.off.end());
+          cur = c.land;
+          st = c.state;
+          joined = true;
+        }
+      }
+    }
+    if (!joined && st == 0) st = hop_chain(base, cur, seg[t + 1], wend, off, &cur);
+    if (st == HOP_BAD) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", (size_t)le32(base + cur));
+    if (st == HOP_END) break;
+  }
+  *next = cur;
+  return 0;
+}
+
 // Single-sample rules (bam_utils.py:258-328) over every whole record of the inflated window, on all
 // worker threads: (1) one sequential hop over the block_size fields finds the records, (2) validity
 // per record, (3) "starts a read" per valid record = its trimmed name differs from the previous valid
@@ -416,13 +538,8 @@ int process_window_single(bamcols* r) {
   size_t p = r->wpos;
   {
     PhaseTimer timer(&r->phase_s[1]);
-    while (p + 4 <= r->wend) {
-      const size_t bs = le32(base + p);
-      if (bs < 32) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", bs);
-      if (p + 4 + bs > r->wend) break;
-      off.push_back(p);
-      p += 4 + bs;
-    }
+    const int rc = find_records(r, off, &p);
+    if (rc < 0) return rc;
   }
   r->wpos = p;
   const size_t n = off.size();
@@ -592,12 +709,9 @@ int process_window_cells(bamcols* r, bamcols_cells* cells) {
   std::vector<size_t>& off = r->rec_off;
   off.clear();
   size_t p = r->wpos;
-  while (p + 4 <= r->wend) {
-    const size_t bs = le32(base + p);
-    if (bs < 32) return fail(r, BAMCOLS_ERR_FORMAT, "BAM record with block_size %zu", bs);
-    if (p + 4 + bs > r->wend) break;
-    off.push_back(p);
-    p += 4 + bs;
+  {
+    const int rc = find_records(r, off, &p);
+    if (rc < 0) return rc;
   }
   r->wpos = p;
   lap(1);

@@ -329,6 +329,64 @@ def test_records_with_cigar_sequence_and_tags(tmp_path):
     assert np.array_equal(cols["hap_idx"], tables.tid_hap[np.array(want_tid)])
 
 
+def test_parallel_record_hop_rejects_decoys(tmp_path, monkeypatch):
+    """The record boundaries of a window are found speculatively in parallel (bamcols.cpp:find_records): a
+    worker guesses the first record of its byte segment from two plausible record headers in a row.  Here
+    the tag area of every third record holds byte-exact copies of two small records - a guess that lands on
+    them is wrong and must be thrown out by the join with the verified chain - and tiny segments
+    (BAMCOLS_GRAIN) put many segment starts right in front of them.  A record with block_size < 32 on the
+    true chain must still be reported."""
+    import struct
+    rng = np.random.default_rng(77)
+
+    def record(name, tid, flag, tail=b""):
+        nm = name.encode() + b"\x00"
+        core = struct.pack("<iiBBHHHiiii", tid, 7, len(nm), 30, 4680, 0, flag, 0, -1, -1, 0) + nm + tail
+        return struct.pack("<i", len(core)) + core
+
+    decoy = record("decoyA", 1, 0) + record("decoyB", 2, 0)
+    for grain in (1, 2, 7, 4096):
+        monkeypatch.setenv("BAMCOLS_GRAIN", str(grain))
+        monkeypatch.setenv("BAMCOLS_BATCH_BLOCKS", str(1 + grain % 3))    # many small windows
+        payload, want_rg, want_tid, group, last = [bam_io.bam_header_bytes(REFS)], [], [], -1, None
+        for i in range(900):
+            name = "frag%04d" % (i // 2)
+            tid = int(rng.integers(0, len(REFS)))
+            filler = rng.integers(0, 256, int(rng.integers(0, 90)), dtype=np.uint8).tobytes()
+            tail = filler
+            if i % 3 == 0:       # decoys that lead back onto the true chain / that lead into random bytes
+                tail = filler + decoy + decoy if i % 2 else filler + decoy + rng.integers(0, 256, 60, dtype=np.uint8).tobytes()
+            payload.append(record(name, tid, 0, tail))
+            if name != last:
+                group, last = group + 1, name
+            want_rg.append(group)
+            want_tid.append(tid)
+        raw = b"".join(payload)
+        path = str(tmp_path / ("decoy%d.bam" % grain))
+        with open(path, "wb") as fh:
+            for off in range(0, len(raw), 3000):
+                fh.write(bam_io.bgzf_block(raw[off:off + 3000]))
+            fh.write(bam_io.BGZF_EOF)
+        for threads in (1, 3, 8):
+            cols = _same_single(path, n_threads=threads)
+            assert cols["read_group"].tolist() == want_rg
+            tables = TargetTables([r[0] for r in REFS], [r[1] for r in REFS], None)
+            assert np.array_equal(cols["target_idx"], tables.tid_target[np.array(want_tid)])
+    # a broken record on the true chain
+    raw = bam_io.bam_header_bytes(REFS) + b"".join(record("r%03d" % i, 0, 0) for i in range(200)) + struct.pack("<i", 5) + b"x" * 64
+    path = str(tmp_path / "broken.bam")
+    with open(path, "wb") as fh:
+        fh.write(bam_io.bgzf_block(raw))
+        fh.write(bam_io.BGZF_EOF)
+    monkeypatch.setenv("BAMCOLS_GRAIN", "3")
+    tables = TargetTables([r[0] for r in REFS], [r[1] for r in REFS], None)
+    with bamcols.BamColumnReader(path, n_threads=4) as r:
+        r.set_tables(tables)
+        with pytest.raises(Exception) as err:
+            r.read_all()
+    assert "block_size" in str(err.value)
+
+
 def _multisample_both(path, tables, cell_ids, cells, **reader_kw):
     header, recs = load_records(path)
     want = emitter.emit_multisample(recs, tables, cell_ids)
