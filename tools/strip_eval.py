@@ -1,0 +1,87 @@
+"""One-shot evaluation of the strip kernel on cfg2: parity against the window kernel's result, group-kernel
+and whole-step times, and the two timing experiments (misses dropped / walk only).
+usage: python tools/strip_eval.py [n_reads]   -> prints a table, writes gpurun_out/strip_eval.json"""
+import json, os, sys, time
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch
+from alntools_b200 import synth, _native
+from alntools_b200._native import EcBuilder
+t0 = time.time()
+n_reads = int(os.environ.get("STRIP_EVAL_READS", "30000000"))
+want = set(sys.argv[1:])
+CACHE = "/tmp/cfg2_cols_%d.npz" % n_reads
+if os.path.isfile(CACHE):
+    z = np.load(CACHE)
+    cols = {k: z[k] for k in ("read_group", "target_idx", "hap_idx")}
+else:
+    cols = synth.make_columns(n_reads, 100000, 2, 2, mode="diploid")
+    np.savez(CACHE, **{k: cols[k] for k in ("read_group", "target_idx", "hap_idx")})
+dev = {k: torch.from_numpy(cols[k]).cuda() for k in ("read_group", "target_idx", "hap_idx")}
+n = len(cols["read_group"])
+print("columns ready %.1f s, %d alignments" % (time.time() - t0, n), flush=True)
+KEYS = ("a_indptr", "a_indices", "a_data", "n_data")
+HERE = os.path.dirname(os.path.abspath(__file__))
+base = None
+out = {}
+if os.path.isfile("gpurun_out/strip_eval.json") and n_reads == 30_000_000:
+    out = json.load(open("gpurun_out/strip_eval.json"))
+BASE = "/tmp/strip_eval_base_%d.npz" % n_reads
+if os.path.isfile(BASE):
+    z = np.load(BASE)
+    base = {k: z[k] for k in KEYS}
+    base["n_reads"], base["n_ec"] = int(z["n_reads"]), int(z["n_ec"])
+RUNS = [("window", None, {}), ("strip32", None, {"strip_kernel": 32}), ("strip24", None, {"strip_kernel": 24}),
+        ("dense24", None, {"strip_kernel": 124}), ("window_nocache", None, {"hot_cache": 0}),
+        ("dense24_nocache", None, {"strip_kernel": 124, "hot_cache": 0}),
+        ("X_noinsert_dense24", "libecb_strip_noinsert.so", {"strip_kernel": 124}),
+        ("X_noinsert_strip32", "libecb_strip_noinsert.so", {"strip_kernel": 32}),
+        ("X_walkonly_dense24", "libecb_strip_walkonly.so", {"strip_kernel": 124}),
+        ("X_walkonly_strip32", "libecb_strip_walkonly.so", {"strip_kernel": 32})]
+default_lib = _native.load_library()
+for name, lib, opts in RUNS:
+    if want and name not in want:
+        continue
+    try:
+        _native._lib = _native.load_library(os.path.join(HERE, "_build", lib)) if lib else default_lib
+        b = EcBuilder(100000, 2, alignments_hint=n, **opts)
+        ms, step, same, n_ec = [], [], "-", -1
+        for i in range(4):
+            b.reset()
+            torch.cuda.synchronize()
+            t1 = time.time()
+            b.push(dev["read_group"], dev["target_idx"], dev["hap_idx"])
+            ms.append(b.stats()["group_ms"])
+            try:
+                res = b.finalize()
+            except Exception as exc:
+                res = None
+            torch.cuda.synchronize()
+            step.append((time.time() - t1) * 1e3)
+        if res is not None and not name.startswith("X_"):
+            got = {k: np.array(res[k]) for k in KEYS}
+            got["n_reads"], got["n_ec"] = res["n_reads"], res["n_ec"]
+            n_ec = got["n_ec"]
+            if base is None:
+                base, same = got, "reference"
+                np.savez(BASE, **got)
+            else:
+                same = "SAME" if (all(np.array_equal(got[k], base[k]) for k in KEYS) and got["n_reads"] == base["n_reads"]
+                                  and got["n_ec"] == base["n_ec"]) else "DIFFERENT"
+        out[name] = {"group_ms": ms, "step_ms": step, "parity": same, "n_ec": int(n_ec)}
+        print("%-20s group_ms %s  step_ms %s  n_ec %d  %s" % (name, [round(x, 4) for x in ms],
+                                                              [round(x, 2) for x in step], n_ec, same), flush=True)
+        b.close()
+    except Exception as exc:
+        out[name] = {"error": str(exc)}
+        print(name, "ERROR:", exc, flush=True)
+    with open("gpurun_out/strip_eval%s.json" % ("" if n_reads == 30_000_000 else "_%d" % n_reads), "w") as fh:
+        json.dump(out, fh, indent=1)
+# which variant should the rest of the shot use?  the fastest one that reproduced the window kernel's result
+best, best_ms = "", 1e9
+for name, code in (("strip32", "32"), ("strip24", "24"), ("dense24", "124")):
+    r = out.get(name, {})
+    if r.get("parity") == "SAME" and min(r["group_ms"][1:]) < best_ms:
+        best, best_ms = code, min(r["group_ms"][1:])
+with open("gpurun_out/strip_best.txt", "w") as fh:
+    fh.write(best)
+print("best correct strip variant:", best or "none", best_ms)
