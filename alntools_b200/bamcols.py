@@ -42,6 +42,7 @@ SIGNATURES = {
     "bamcols_track_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bamcols_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_phase_seconds": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "bamcols_inflate_raw": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
 }
 
 BAMCOLS_ERR_IO, BAMCOLS_ERR_FORMAT, BAMCOLS_ERR_INVALID, BAMCOLS_ERR_CELL_FIELD, BAMCOLS_ERR_TID = -1, -2, -3, -4, -5
@@ -62,6 +63,18 @@ def load_library(path=None):
     if path is None:
         _lib = lib
     return lib
+
+
+def inflate_raw(data, out_len, mode=0):
+    """Inflate a raw DEFLATE stream of known inflated size with the reader's block decoder.
+    mode 0: as the reader does (whole-buffer decoder, zlib for what it declines), 1: zlib only,
+    2: whole-buffer decoder only.  Returns the bytes, or None if the decoder said no."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(max(1, int(out_len)))
+    rc = lib.bamcols_inflate_raw(bytes(data), len(data), buf, int(out_len), int(mode))
+    if rc < 0:
+        raise ValueError("bamcols_inflate_raw: bad arguments")
+    return buf.raw[:out_len] if rc == 1 else None
 
 
 def _raise(code, msg):

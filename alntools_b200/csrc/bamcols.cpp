@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -26,6 +28,7 @@
 #include <unistd.h>
 
 #include "../../include/bamcols.h"
+#include "fast_inflate.h"
 
 namespace {
 
@@ -116,13 +119,64 @@ struct bamcols_cells {
   int32_t id_of(const char* s, size_t n) { return id_of(s, n, hash_of(s, n)); }
 };
 
+// Grow-only buffer without value initialisation (std::vector::resize would write every new element first:
+// 128 MiB of window and 100 MiB of staged rows per refill), large ones on transparent huge pages so that the
+// first touch by the worker threads takes hundreds of page faults instead of tens of thousands.
+template <class T>
+struct RawBuf {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  bool mapped = false;
+  RawBuf() = default;
+  RawBuf(const RawBuf&) = delete;
+  RawBuf& operator=(const RawBuf&) = delete;
+  ~RawBuf() { release(p, cap, mapped); }
+  static void release(T* q, size_t c, bool m) {
+    if (!q) return;
+    if (m) munmap(q, c * sizeof(T)); else free(q);
+  }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  void resize(size_t want) {   // keeps the first min(n, want) elements; new elements are uninitialised
+    if (want > cap) {
+      size_t c = std::max(want, cap + cap / 2);
+      const size_t HUGE = (size_t)2 << 20;
+      T* q = nullptr;
+      bool m = false;
+      if (c * sizeof(T) >= 2 * HUGE) {
+        const size_t bytes = (c * sizeof(T) + HUGE - 1) / HUGE * HUGE;
+        void* a = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (a != MAP_FAILED) {
+#ifdef MADV_HUGEPAGE
+          madvise(a, bytes, MADV_HUGEPAGE);
+#endif
+          q = (T*)a;
+          c = bytes / sizeof(T);
+          m = true;
+        }
+      }
+      if (!q) q = (T*)malloc(c * sizeof(T));
+      if (!q) throw std::bad_alloc();
+      if (n) memcpy(q, p, std::min(n, want) * sizeof(T));
+      release(p, cap, mapped);
+      p = q;
+      cap = c;
+      mapped = m;
+    }
+    n = want;
+  }
+};
+
 struct bamcols {
   int fd = -1;
   const uint8_t* file = nullptr;
   size_t file_size = 0;
   size_t cpos = 0;               // compressed offset of the next BGZF block
   bool file_done = false;        // every block has been inflated
-  std::vector<uint8_t> win;      // inflated window
+  RawBuf<uint8_t> win;           // inflated window
   size_t wpos = 0, wend = 0;     // unread part of the window
   int n_threads = 1;
   size_t batch_blocks = 2048;    // up to 128 MiB inflated per refill
@@ -141,7 +195,7 @@ struct bamcols {
   bool records_done = false, all_flushed = false;
   int64_t all_alignments = 0;
   // single-sample batch path: rows of the current inflated window, produced by all worker threads
-  std::vector<int32_t> st_rg, st_tg, st_hp, st_cell;
+  RawBuf<int32_t> st_rg, st_tg, st_hp, st_cell;
   size_t pending_row = 0;        // per-cell: stage row whose cell is resolved by the next valid alignment
   bool sequential_cells = false; // BAMCOLS_SEQUENTIAL_CELLS: the one-pass statement of the per-cell rules
   size_t st_pos = 0;             // next row to hand out
@@ -213,16 +267,36 @@ int parse_block(bamcols* r, size_t off, BlockJob* job, size_t* bsize_out) {
   return 0;
 }
 
-bool inflate_block(z_stream* zs, const BlockJob& job, uint8_t* dst) {
-  if (job.isize == 0) return true;
-  if (inflateReset(zs) != Z_OK) return false;
-  zs->next_in = const_cast<Bytef*>(job.src);
-  zs->avail_in = job.src_len;
-  zs->next_out = dst;
-  zs->avail_out = job.isize;
-  const int rc = inflate(zs, Z_FINISH);
-  return rc == Z_STREAM_END && zs->avail_out == 0;
-}
+// Per-worker inflate state: the whole-buffer decoder's tables and a zlib stream for the blocks it declines.
+struct Inflater {
+  z_stream zs;
+  bool zs_ready = false;
+  fastinflate::Tables scratch, fixed;
+  bool fixed_ready = false;
+  bool zlib_only = false;   // BAMCOLS_ZLIB_ONLY: timing comparisons and tests
+  Inflater() { memset(&zs, 0, sizeof zs); }
+  ~Inflater() {
+    if (zs_ready) inflateEnd(&zs);
+  }
+  // raw deflate stream of known inflated size; true iff it decoded cleanly into exactly dst_len bytes
+  bool run(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len) {
+    if (dst_len == 0) return true;
+    if (!zlib_only && fastinflate::fast_inflate(src, src_len, dst, dst_len, scratch, fixed, fixed_ready)) return true;
+    // anything the fast decoder does not like is judged by zlib
+    if (!zs_ready) {
+      if (inflateInit2(&zs, -15) != Z_OK) return false;
+      zs_ready = true;
+    } else if (inflateReset(&zs) != Z_OK) {
+      return false;
+    }
+    zs.next_in = const_cast<Bytef*>(src);
+    zs.avail_in = (uInt)src_len;
+    zs.next_out = dst;
+    zs.avail_out = (uInt)dst_len;
+    const int rc = inflate(&zs, Z_FINISH);
+    return rc == Z_STREAM_END && zs.avail_out == 0;
+  }
+};
 
 // Inflate the next batch of blocks behind the unread part of the window.  Returns 0, or <0 on error;
 // sets file_done when the file has no more blocks.
@@ -257,21 +331,17 @@ int refill(bamcols* r) {
   const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, (jobs.size() + 15) / 16));
   std::atomic<size_t> next(0);
   std::atomic<int> bad(0);
+  const bool zlib_only = getenv("BAMCOLS_ZLIB_ONLY") != nullptr;
   auto work = [&]() {
-    z_stream zs;
-    memset(&zs, 0, sizeof zs);
-    if (inflateInit2(&zs, -15) != Z_OK) {
-      bad.store(1);
-      return;
-    }
+    std::unique_ptr<Inflater> inf(new Inflater());
+    inf->zlib_only = zlib_only;
     for (;;) {
       const size_t i0 = next.fetch_add(8);
       if (i0 >= jobs.size()) break;
       const size_t i1 = std::min(jobs.size(), i0 + 8);
       for (size_t i = i0; i < i1; ++i)
-        if (!inflate_block(&zs, jobs[i], base + jobs[i].dst_off)) bad.store(1);
+        if (!inf->run(jobs[i].src, jobs[i].src_len, base + jobs[i].dst_off, jobs[i].isize)) bad.store(1);
     }
-    inflateEnd(&zs);
   };
   if (nt == 1) {
     work();
@@ -939,10 +1009,23 @@ int64_t emit_single(bamcols* r, bamcols_cells* cells, int32_t* read_group, int32
         return rows;
       }
       PhaseTimer timer(&r->phase_s[5]);
-      memcpy(read_group + rows, r->st_rg.data() + r->st_pos, take * 4);
-      memcpy(target_idx + rows, r->st_tg.data() + r->st_pos, take * 4);
-      memcpy(hap_idx + rows, r->st_hp.data() + r->st_pos, take * 4);
-      if (cells) memcpy(cell_idx + rows, r->st_cell.data() + r->st_pos, take * 4);
+      {
+        // columns x slices on the worker threads (one memcpy stream does not fill the memory system)
+        int32_t* dst[4] = {read_group + rows, target_idx + rows, hap_idx + rows, cells ? cell_idx + rows : nullptr};
+        const int32_t* src[4] = {r->st_rg.data() + r->st_pos, r->st_tg.data() + r->st_pos, r->st_hp.data() + r->st_pos,
+                                 cells ? r->st_cell.data() + r->st_pos : nullptr};
+        const int ncol = cells ? 4 : 3;
+        const int slices = (int)std::max<size_t>(1, std::min<size_t>((size_t)std::max(1, r->n_threads / ncol), take / (1u << 18)));
+        parallel_for(take < (1u << 18) ? 1 : ncol * slices, [&](int t) {
+          if (take < (1u << 18)) {   // small: not worth a thread
+            for (int c = 0; c < ncol; ++c) memcpy(dst[c], src[c], take * 4);
+            return;
+          }
+          const int c = t / slices, k = t % slices;
+          const size_t a = take * (size_t)k / (size_t)slices, b = take * (size_t)(k + 1) / (size_t)slices;
+          memcpy(dst[c] + a, src[c] + a, (b - a) * 4);
+        });
+      }
       rows += (int64_t)take;
       r->st_pos += take;
       if (rows == capacity) return rows;
@@ -1163,6 +1246,18 @@ int bamcols_ranges(const bamcols* r, const int32_t** min_pos, const int32_t** ma
   *min_pos = r->range_min.data();
   *max_pos = r->range_max.data();
   return (int)r->range_min.size();
+}
+
+int bamcols_inflate_raw(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_len, int mode) {
+  if (!src || (!dst && dst_len) || src_len < 0 || dst_len < 0) return BAMCOLS_ERR_INVALID;
+  if (mode == 2) {   // the whole-buffer decoder alone: 1 = decoded, 0 = declined
+    std::unique_ptr<Inflater> inf(new Inflater());
+    if (dst_len == 0) return 1;
+    return fastinflate::fast_inflate(src, (size_t)src_len, dst, (size_t)dst_len, inf->scratch, inf->fixed, inf->fixed_ready) ? 1 : 0;
+  }
+  std::unique_ptr<Inflater> inf(new Inflater());
+  inf->zlib_only = mode == 1;
+  return inf->run(src, (size_t)src_len, dst, (size_t)dst_len) ? 1 : 0;
 }
 
 int bamcols_phase_seconds(const bamcols* r, double* out6) {

@@ -97,6 +97,12 @@ int bamcols_ranges(const bamcols* r, const int32_t** min_pos, const int32_t** ma
  * copy-out (single-sample path; diagnostics for the host-side timing report). */
 int bamcols_phase_seconds(const bamcols* r, double* out6);
 
+/* The block decoder on its own (tests, timing): inflate a raw DEFLATE stream whose inflated size is known,
+ * as every BGZF block is.  mode 0 = as the reader does it (whole-buffer decoder, zlib for anything it
+ * declines), 1 = zlib only, 2 = whole-buffer decoder only.  Returns 1 if exactly dst_len bytes were
+ * produced from a well-formed stream, 0 if not, < 0 on bad arguments. */
+int bamcols_inflate_raw(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_len, int mode);
+
 #ifdef __cplusplus
 }
 #endif
