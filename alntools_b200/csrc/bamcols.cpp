@@ -6,6 +6,9 @@
 // BGZF blocks are inflated a batch at a time by a pool of worker threads (blocks are independent
 // deflate streams, SAM spec 4.1), and one pass over the fixed-offset record fields produces the rows.
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -197,6 +200,13 @@ struct bamcols {
   // single-sample batch path: rows of the current inflated window, produced by all worker threads
   RawBuf<int32_t> st_rg, st_tg, st_hp, st_cell;
   size_t pending_row = 0;        // per-cell: stage row whose cell is resolved by the next valid alignment
+  // per-cell scratch, kept between windows (fresh allocations of this size are page-faulted in every time)
+  std::vector<size_t> sc_openers;
+  std::vector<std::vector<size_t>> sc_mine;
+  std::vector<const char*> sc_cell_ptr;
+  std::vector<size_t> sc_cell_len;
+  std::vector<uint64_t> sc_cell_hash;
+  std::vector<int32_t> sc_cell_id, sc_group_cell;
   bool sequential_cells = false; // BAMCOLS_SEQUENTIAL_CELLS: the one-pass statement of the per-cell rules
   size_t st_pos = 0;             // next row to hand out
   size_t st_whole = 0;           // rows [st_pos, st_whole) are whole reads; [st_whole, size) is the open last read
@@ -403,7 +413,7 @@ inline size_t trimmed_len(const char* s, size_t n) {
 
 // Field 14 of name.split('|||') (bam_utils_multisample.py:273): separators are found left to right and
 // do not overlap.  false: fewer than 15 fields.
-inline bool cell_field(const char* s, size_t n, const char** out, size_t* len) {
+inline bool cell_field_scalar(const char* s, size_t n, const char** out, size_t* len) {
   size_t start = 0, i = 0;
   int seps = 0;
   while (i + 3 <= n) {
@@ -428,6 +438,52 @@ inline bool cell_field(const char* s, size_t n, const char** out, size_t* len) {
   *len = n - start;
   return true;
 }
+
+#if defined(__SSE2__)
+// Names of up to 128 bytes (all 10x-style names): one bit per '|' from 16-byte compares, then the starts
+// of "|||" as m & m>>1 & m>>2, walked greedily.
+inline bool cell_field(const char* s, size_t n, const char** out, size_t* len) {
+  if (n > 128) return cell_field_scalar(s, n, out, len);
+  unsigned __int128 m = 0;
+  const __m128i bar = _mm_set1_epi8('|');
+  size_t i = 0;
+  for (; i + 16 <= n; i += 16) {
+    const __m128i v = _mm_loadu_si128((const __m128i*)(s + i));
+    m |= (unsigned __int128)(unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, bar)) << i;
+  }
+  if (i < n) {
+    char tail[16] = {0};
+    memcpy(tail, s + i, n - i);
+    const __m128i v = _mm_loadu_si128((const __m128i*)tail);
+    m |= (unsigned __int128)(unsigned)_mm_movemask_epi8(_mm_cmpeq_epi8(v, bar)) << i;
+  }
+  unsigned __int128 m3 = m & (m >> 1) & (m >> 2);   // bit p: s[p..p+2] == "|||"
+  size_t start = 0;
+  int seps = 0;
+  uint64_t part[2] = {(uint64_t)m3, (uint64_t)(m3 >> 64)};
+  for (int h = 0; h < 2; ++h) {
+    uint64_t w = part[h];
+    while (w) {
+      const size_t p = (size_t)__builtin_ctzll(w) + 64 * (size_t)h;
+      w &= w - 1;
+      if (p < start) continue;   // overlaps the separator just taken ("||||")
+      if (seps == 14) {
+        *out = s + start;
+        *len = p - start;
+        return true;
+      }
+      ++seps;
+      start = p + 3;
+    }
+  }
+  if (seps < 14) return false;
+  *out = s + start;
+  *len = n - start;
+  return true;
+}
+#else
+inline bool cell_field(const char* s, size_t n, const char** out, size_t* len) { return cell_field_scalar(s, n, out, len); }
+#endif
 inline bool cell_field(const std::string& name, const char** out, size_t* len) {
   return cell_field(name.data(), name.size(), out, len);
 }
@@ -861,35 +917,85 @@ int process_window_cells(bamcols* r, bamcols_cells* cells) {
     }
   });
 
-  // one pass over the flags: which records start a read (bit 3), openers in order
-  std::vector<size_t> openers;
+  // Which records start a read (bit 3), openers in order.  After the first two valid records of the
+  // window (the file's first read is remembered trimmed, :261-262) the rule is a two-state machine:
+  // sw(i) = sw(previous valid record) ? bit 2 : bit 1.  Every worker runs its range for both incoming
+  // states, the states are chained over the workers, then every worker runs its range again for real.
+  std::vector<size_t>& openers = r->sc_openers;
   {
-    bool first_in_window = true, prev_switch = false, prev_trimmed_name = false;
-    int t = 0;
-    for (size_t i = 0; i < n; ++i) {
-      while (i >= lo(t + 1)) ++t;
-      if (!fl[i]) continue;
-      bool sw;
-      if (!r->started && first_in_window) {
-        sw = true;                                   // the file's first read
-      } else if (first_in_window) {
-        const char* nm;
-        size_t nf, ntm;
-        name_of(i, &nm, &nf, &ntm);
-        sw = r->current.size() != ntm || memcmp(r->current.data(), nm, ntm) != 0;
-      } else {
-        sw = (prev_switch && !prev_trimmed_name) ? (fl[i] & 4) != 0 : (fl[i] & 2) != 0;
+    size_t i0 = n, i1 = n;   // first and second valid record of the window
+    for (size_t i = 0; i < n; ++i)
+      if (fl[i]) {
+        if (i0 == n) {
+          i0 = i;
+        } else {
+          i1 = i;
+          break;
+        }
       }
-      prev_trimmed_name = sw && !r->started && first_in_window;   // only the first read is remembered trimmed
-      first_in_window = false;
-      prev_switch = sw;
-      if (sw) {
-        fl[i] |= 8;
-        openers.push_back(i);
-        ++n_start[t + 1];
+    bool sw0, sw1 = false;
+    if (!r->started) {
+      sw0 = true;                                    // the file's first read
+    } else {
+      const char* nm;
+      size_t nf, ntm;
+      name_of(i0, &nm, &nf, &ntm);
+      sw0 = r->current.size() != ntm || memcmp(r->current.data(), nm, ntm) != 0;
+    }
+    if (i1 < n) {
+      const bool prev_trimmed_name = sw0 && !r->started;   // only the first read is remembered trimmed
+      sw1 = (sw0 && !prev_trimmed_name) ? (fl[i1] & 4) != 0 : (fl[i1] & 2) != 0;
+    }
+    std::vector<uint8_t> out0(nt, 0), out1(nt, 1), in_state(nt, 0);
+    parallel_for(nt, [&](int t) {
+      bool s0 = false, s1 = true;
+      for (size_t i = std::max(lo(t), i1 == n ? n : i1 + 1); i < lo(t + 1); ++i) {
+        const uint8_t f = fl[i];
+        if (!f) continue;
+        s0 = s0 ? (f & 4) != 0 : (f & 2) != 0;
+        s1 = s1 ? (f & 4) != 0 : (f & 2) != 0;
+      }
+      out0[t] = s0;
+      out1[t] = s1;
+    });
+    {
+      bool cur = sw1;
+      for (int t = 0; t < nt; ++t) {
+        in_state[t] = cur;
+        cur = cur ? out1[t] != 0 : out0[t] != 0;
       }
     }
-    for (int k = 0; k < nt; ++k) n_start[k + 1] += n_start[k];
+    std::vector<std::vector<size_t>>& mine = r->sc_mine;
+    if ((int)mine.size() < nt) mine.resize(nt);
+    parallel_for(nt, [&](int t) {
+      std::vector<size_t>& op = mine[t];
+      op.clear();
+      bool st = in_state[t] != 0;
+      for (size_t i = lo(t); i < lo(t + 1); ++i) {
+        const uint8_t f = fl[i];
+        if (!f) continue;
+        bool sw;
+        if (i == i0) {
+          sw = sw0;
+        } else if (i == i1) {
+          sw = sw1;
+        } else if (i < i1) {
+          continue;   // unreachable: no valid record lies between i0 and i1
+        } else {
+          sw = st ? (f & 4) != 0 : (f & 2) != 0;
+          st = sw;
+        }
+        if (sw) {
+          fl[i] = f | 8;
+          op.push_back(i);
+        }
+      }
+    });
+    for (int t = 0; t < nt; ++t) n_start[t + 1] = n_start[t] + mine[t].size();
+    openers.resize(n_start[nt]);
+    parallel_for(nt, [&](int t) {
+      if (!mine[t].empty()) memcpy(openers.data() + n_start[t], mine[t].data(), mine[t].size() * sizeof(size_t));
+    });
   }
   size_t last_valid = n;
   for (size_t j = n; j-- > 0;)
@@ -910,10 +1016,16 @@ int process_window_cells(bamcols* r, bamcols_cells* cells) {
   // cell names of the openers (field 14 of the remembered name), in parallel, looked up in the dictionary
   // as it stands now; only cells that are NEW in this window go through the ordered pass below
   const size_t n_open = openers.size();
-  std::vector<const char*> cell_ptr(n_open, nullptr);
-  std::vector<size_t> cell_len(n_open, 0);
-  std::vector<uint64_t> cell_hash(n_open, 0);
-  std::vector<int32_t> cell_id(n_open, -2);   // -2 no field 14, -1 not in the dictionary yet
+  std::vector<const char*>& cell_ptr = r->sc_cell_ptr;
+  std::vector<size_t>& cell_len = r->sc_cell_len;
+  std::vector<uint64_t>& cell_hash = r->sc_cell_hash;
+  std::vector<int32_t>& cell_id = r->sc_cell_id;   // -2 no field 14, -1 not in the dictionary yet
+  if (cell_ptr.size() < n_open) {
+    cell_ptr.resize(n_open);
+    cell_len.resize(n_open);
+    cell_hash.resize(n_open);
+    cell_id.resize(n_open);
+  }
   const bamcols_cells* snapshot = cells;
   const bool file_first_here = !r->started;
   {
@@ -926,6 +1038,7 @@ int process_window_cells(bamcols* r, bamcols_cells* cells) {
         const size_t len = (file_first_here && k == 0) ? ntm : nf;   // remembered name of that read
         const char* cf;
         size_t cl;
+        cell_id[k] = -2;
         if (!cell_field(nm, len, &cf, &cl)) continue;
         cell_ptr[k] = cf;
         cell_len[k] = cl;
@@ -941,7 +1054,8 @@ int process_window_cells(bamcols* r, bamcols_cells* cells) {
   r->st_tg.resize(row0 + rows);
   r->st_hp.resize(row0 + rows);
   r->st_cell.resize(row0 + rows);
-  std::vector<int32_t> group_cell(n_open + 1, 0);
+  std::vector<int32_t>& group_cell = r->sc_group_cell;
+  if (group_cell.size() < n_open + 1) group_cell.resize(n_open + 1);
   group_cell[0] = r->cell;   // the read that is open when the window begins
   bool pending_now = false;
   for (size_t k = 0; k < n_open; ++k) {
