@@ -1396,7 +1396,13 @@ int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int3
   const int want_mode = cells ? 2 : 1;
   if (r->mode == 0) r->mode = want_mode;
   if (r->mode != want_mode) return fail(r, BAMCOLS_ERR_INVALID, "a reader cannot switch between single-sample and per-cell rules");
-  if (!cells || !r->sequential_cells) return emit_single(r, cells, read_group, target_idx, hap_idx, cell_idx, capacity, done);
+  if (!cells || !r->sequential_cells) {
+    try {   // no exception may cross the C ABI
+      return emit_single(r, cells, read_group, target_idx, hap_idx, cell_idx, capacity, done);
+    } catch (const std::bad_alloc&) {
+      return fail(r, BAMCOLS_ERR_IO, "out of memory while decoding the window");
+    }
+  }
   // ---- per-cell rules as ONE sequential pass (BAMCOLS_SEQUENTIAL_CELLS): the plain statement of
   // bam_utils_multisample.py:258-300 that the parallel window code above is tested against -------------
   const int32_t n_ref = (int32_t)r->tid_target.size();
