@@ -274,6 +274,13 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
   const int32_t* const pf_col = (lane < 8 ? c_rg : (lane < 16 ? c_tg : c_hp)) + (lane & 7) * 32;
   const bool pf_lane = lane < 24;
 
+  // The out-of-line routines take the parameter block by reference.  A reference to the kernel parameter
+  // itself turns every field access over there into a generic load from the parameter window; a copy in
+  // shared memory is read with ordinary shared-memory latency (hypothesis for the slow insert of DESIGN.md
+  // 4.1b, not measured yet).
+  __shared__ GroupParams SP;
+  for (int i = tid; i < (int)(sizeof(GroupParams) / 4); i += THREADS)
+    reinterpret_cast<u32*>(&SP)[i] = reinterpret_cast<const u32*>(&P)[i];
   if (use_cache) {
     for (int i = tid; i < ECB_CACHE; i += THREADS) {
       S.c_key[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -354,7 +361,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
           strip_stage(A, ins, key, s, len, cn, lt_mask);
           if (cn >= 32u) {
             cn -= 32u;
-            qn = strip_drain<WITH_CELLS, WARPS>(P, cn, 32u, qn, use_cache);
+            qn = strip_drain<WITH_CELLS, WARPS>(SP, cn, 32u, qn, use_cache);
           }
         } else {
           strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
@@ -387,7 +394,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
           strip_stage(A, ins, key, s, len, cn, lt_mask);
           if (cn >= 32u) {
             cn -= 32u;
-            qn = strip_drain<WITH_CELLS, WARPS>(P, cn, 32u, qn, use_cache);
+            qn = strip_drain<WITH_CELLS, WARPS>(SP, cn, 32u, qn, use_cache);
           }
         } else {
           strip_commit<WITH_CELLS>(P, A, use_cache, ins, key, s, len, qn, lt_mask, lane);
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) ecb_group_strip_kernel(const __
   }
 
   // ---- leftovers of the queues, then the cache goes into the HBM table --------------------------------
-  if constexpr (DENSE) if (cn) qn = strip_drain<WITH_CELLS, WARPS>(P, 0u, cn, qn, use_cache);
+  if constexpr (DENSE) if (cn) qn = strip_drain<WITH_CELLS, WARPS>(SP, 0u, cn, qn, use_cache);
 #if ECB_STRIP_EXPERIMENT == 1
   qn = 0;
 #elif ECB_STRIP_EXPERIMENT == 2
