@@ -316,6 +316,8 @@ int group_prepare_launch(ecb_ctx* c) {
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -633,7 +635,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
-    case ECB_OPT_TWO_PHASE: c->two_phase = value ? 1 : 0; break;
+    case ECB_OPT_TWO_PHASE: c->two_phase = value == 2 ? 2 : (value ? 1 : 0); break;
     case ECB_OPT_STRIP_KERNEL:
       c->strip_kernel = value ? 1 : 0;
       if (value == 24 || value == 32) { c->strip_warps = (int)value; c->strip_dense = 0; }
@@ -712,7 +714,8 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
-  const bool two_phase = c->two_phase && !c->strip_kernel && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
+  const bool flat_log = c->two_phase == 2 && !c->strip_kernel && !c->with_cells;
+  const bool two_phase = c->two_phase == 1 && !c->strip_kernel && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
   if (two_phase) {
     // logs sized from the push: misses are at most one per read, reads at most one per alignment
     const u32 cap = (u32)std::min<int64_t>(0x7FFFFFFF / ECB_LOG_PARTS, n / ECB_LOG_PARTS * 3 / 4 + 4096);
@@ -729,6 +732,20 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     CKR(ensure(c, c->spill, ((size_t)grid * ECB_CACHE + 1024) * sizeof(EcbSpill)));
     P.spill = (EcbSpill*)c->spill.p;
   }
+  if (flat_log) {
+    // one flat log: three quarters of an entry per alignment (misses <= reads <= alignments; what does not
+    // fit is inserted directly) plus one block per warp for the padding
+    const int64_t cap64 = n / 4 * 3 + (int64_t)grid * ECB_GWARPS * ECB_LOG_BLOCK + ECB_LOG_BLOCK;
+    const u32 cap = (u32)std::min<int64_t>(0x7FFFFF00, cap64);
+    CKR(ensure(c, c->plog, (size_t)cap * sizeof(EcbLogEntry)));
+    CKR(ensure(c, c->pcur, ECB_LOG_PARTS * 4));
+    CK(cudaMemsetAsync(c->pcur.p, 0, 4, c->stream));
+    P.plog = (EcbLogEntry*)c->plog.p;
+    P.pcur = (u32*)c->pcur.p;
+    P.plog_cap = cap;
+    P.plog_shift = 0;
+    P.use_log = 1;
+  }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
   if (c->strip_kernel && c->strip_dense) {
@@ -742,12 +759,17 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     else ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
   }
   else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  else if (flat_log) ecb_group_insert_kernel<false, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
   if (two_phase) {
     ecb_log_insert_kernel<<<c->sm_count, 1024, 0, c->stream>>>(P);
     LAUNCH_CHECK("log_insert");
+  }
+  if (flat_log) {
+    ecb_log_insert_flat_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P);
+    LAUNCH_CHECK("log_insert_flat");
   }
   CK(cudaEventRecord(c->ev[2], c->stream));
   CKR(sync_counters(c));

@@ -60,6 +60,7 @@ struct __align__(32) EcbLogEntry {
 };
 #define ECB_LOG_PARTS 1024  // many partitions: the cursor atomics of a launch spread over that many addresses
 #define ECB_LOG_PARTS_LOG2 10
+#define ECB_LOG_BLOCK 256   // ECB_OPT_TWO_PHASE = 2: entries a warp takes from the flat log at a time (4 batches)
 
 struct GroupParams {
   const int32_t* rg;
@@ -436,6 +437,49 @@ __device__ __forceinline__ void log_misses(const GroupParams& P, u32 qk, u32 qr,
   }
 }
 
+// Two-phase insert, second form (ECB_OPT_TWO_PHASE = 2), phase A: ONE flat log; a warp takes blocks of
+// ECB_LOG_BLOCK entries from it (one atomic with return value per 256 misses instead of one per miss) and
+// fills them with whole batches of 64 - two coalesced 1 KB stores, no round trip.  Entries that are absent
+// in the last, partial batch of a warp are written as empty entries (count 0) so that a block has no holes;
+// lb / lu = base and fill of the warp's current block.
+__device__ __forceinline__ void log_misses_priv(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb,
+                                                bool hasB, u32& lb, u32& lu) {
+  const int lane = threadIdx.x & 31;
+  uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
+  uint2 rA = make_uint2(0u, 0u), rB = rA;
+  if (hasA) {
+    kA = lds128(qk + qa * 16u);
+    rA = lds64(qr + qa * 8u);
+  }
+  if (hasB) {
+    kB = lds128(qk + qb * 16u);
+    rB = lds64(qr + qb * 8u);
+  }
+  if (lu >= ECB_LOG_BLOCK) {   // warp-uniform: the block is full (or there is none yet)
+    u32 b = 0;
+    if (lane == 0) b = atomicAdd(&P.pcur[0], (u32)ECB_LOG_BLOCK);
+    lb = __shfl_sync(ECB_FULL, b, 0);
+    lu = 0u;
+  }
+  const Key128 keyA = key_of(kA), keyB = key_of(kB);
+  const bool okA = log_append(P, keyA, rA.x, hasA ? 1u : 0u, rA.x, rA.y, lb + lu + (u32)lane, 0u);
+  const bool okB = log_append(P, keyB, rB.x, hasB ? 1u : 0u, rB.x, rB.y, lb + lu + 32u + (u32)lane, 0u);
+  lu += 64u;
+  const bool redoA = hasA && !okA, redoB = hasB && !okB;   // the log is full: insert directly
+  if (redoA || redoB) {
+    u32 slotA, slotB;
+    global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
+    if (redoA && slotA == ECB_NONE) {
+      atomicOr(&P.overflow_bits[rA.x >> 5], 1u << (rA.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    }
+    if (redoB && slotB == ECB_NONE) {
+      atomicOr(&P.overflow_bits[rB.x >> 5], 1u << (rB.x & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
+    }
+  }
+}
+
 struct LongRead {
   uint4 key;
   int len;
@@ -490,7 +534,8 @@ __device__ __noinline__ LongRead ecb_long_read(const int32_t* __restrict__ rg, c
 
 // LOGGED: the experimental two-phase insert (ECB_OPT_TWO_PHASE); a template parameter so that the
 // default kernel carries none of it.
-template <bool WITH_CELLS, bool LOGGED = false>
+// PRIVLOG (with LOGGED): the flat log with per-warp blocks instead of the per-partition logs.
+template <bool WITH_CELLS, bool LOGGED = false, bool PRIVLOG = false>
 __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const GroupParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
@@ -526,6 +571,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   const u32 a_first = smem_u32(S.c_first), a_rep = smem_u32(S.c_rep), a_seen = smem_u32(S.seen);
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
   u32 reads_counted = 0;  // per lane
+  u32 lb = 0u, lu = ECB_LOG_BLOCK;   // PRIVLOG: base and fill of this warp's block of the flat log (none yet)
 
   for (;;) {
     // ---- next chunk of the stream (dynamic: whichever warp is free takes it) -------------------------
@@ -712,7 +758,8 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         __syncwarp();
         if (qn >= 64u) {
           qn -= 64u;
-          if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
+          if (PRIVLOG) log_misses_priv(P, qk, qr, qn + lane, true, qn + 32 + lane, true, lb, lu);
+          else if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           else insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           __syncwarp();
         }
@@ -722,8 +769,13 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
   if (qn) {
-    if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+    if (PRIVLOG) log_misses_priv(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn, lb, lu);
+    else if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
     else insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+  }
+  if (PRIVLOG) {   // the rest of the warp's last block: empty entries
+    for (u32 i = lu + (u32)lane; i < ECB_LOG_BLOCK; i += 32u)
+      log_append(P, Key128{0ull, 0ull}, 0u, 0u, 0u, 0u, lb + i, 0u);
   }
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
@@ -735,7 +787,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         const Key128 key = key_of(S.c_key[i]);
         const u32 first = S.c_first[i];
         const uint2 rep = S.c_rep[i];
-        if (LOGGED) {
+        if (LOGGED && !PRIVLOG) {
           const u32 part = (ec_slot_hash(key) & P.mask) >> P.plog_shift;
           if (log_append(P, key, first, cnt, rep.x, rep.y, atomicAdd(&P.pcur[part], 1u), part)) continue;
         }
@@ -798,6 +850,24 @@ __global__ void __launch_bounds__(1024, 1) ecb_log_insert_kernel(const GroupPara
           P.spill[si] = EcbSpill{key.lo, key.hi, v.y, v.x, v.z, v.w};
         }
       }
+    }
+  }
+}
+
+// Two-phase insert, second form, phase B: the flat log goes into the table, one entry per thread, with as
+// many threads resident as the SMs take (the probes are independent chains of round trips; there is
+// nothing else to wait for here).  Empty entries (count 0) pad the blocks.
+__global__ void __launch_bounds__(256) ecb_log_insert_flat_kernel(const GroupParams P) {
+  const u32 cnt = min(P.pcur[0], P.plog_cap);
+  const uint4* log = reinterpret_cast<const uint4*>(P.plog);
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const uint4 k = log[2 * (size_t)i], v = log[2 * (size_t)i + 1];
+    if (v.y == 0u) continue;
+    const Key128 key = key_of(k);
+    const u32 slot = global_upsert(P, key, v.y, v.x, v.z, v.w);
+    if (slot == ECB_NONE) {   // one read: flag it for the replay after the table has grown
+      atomicOr(&P.overflow_bits[v.z >> 5], 1u << (v.z & 31));
+      atomicAdd(&P.ctr->n_overflow, 1u);
     }
   }
 }

@@ -67,7 +67,9 @@ enum ecb_option {
                                    cheaper for a context that finalizes once, slower when reused */
   ECB_OPT_TWO_PHASE = 9,        /* 1: the grouping kernel appends cache misses to per-partition logs and a second
                                    kernel inserts them partition by partition (table slice resident in L2);
-                                   experimental, single-sample path only */
+                                   2: one flat log filled in per-warp blocks of 256 entries (no atomic with a
+                                   return value in the streaming loop), inserted by a second kernel with one
+                                   entry per thread.  Experimental, single-sample path only */
   ECB_OPT_STRIP_KERNEL = 10     /* 1: the strip form of the grouping kernel (a lane walks 8 consecutive alignments
                                    in registers instead of one alignment per lane; same table protocol, same
                                    results); 24 or 32 also select that many warps per CTA, 124 = 24 warps with the

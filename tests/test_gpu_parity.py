@@ -486,6 +486,41 @@ def test_strip_kernel_gives_the_same_result(native, warps):
     _assert_same(got, _oracle(cols, drop_last=True))
 
 
+@pytest.mark.skipif(os.environ.get("ECB_TEST_FLATLOG") != "1", reason="ECB_OPT_TWO_PHASE = 2 (flat log, per-warp blocks) was "
+                    "written after the last GPU minute of round 1; first run pending (ECB_TEST_FLATLOG=1)")
+def test_flat_log_two_phase_insert_gives_the_same_result(native):
+    """ECB_OPT_TWO_PHASE = 2: misses appended to one flat log in per-warp blocks, inserted by a second kernel -
+    same matrices as the direct insert, with and without the cache, with a table that has to grow, with a
+    log too small for the misses (alignments that are all their own read) and across several pushes."""
+    from alntools_b200 import synth
+    for n_reads, n_targets, n_haps, mode, dup, slots in ((200000, 2000, 2, "diploid", 0.02, 1 << 20),
+                                                         (3000000, 100000, 2, "diploid", 0.0, 1 << 20),
+                                                         (30000, 1500, 8, "heavy", 0.01, 1 << 20),
+                                                         (400000, 50000, 2, "light", 0.0, 1 << 21),
+                                                         (50000, 40000, 2, 1, 0.0, 1 << 12)):
+        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=5, mode=mode, dup_rate=dup)
+        want = _oracle(cols)
+        for cache in (1, 0):
+            got, stats = _run(native, cols, n_targets, n_haps, two_phase=2, table_slots=slots, hot_cache=cache)
+            _assert_same(got, want)
+    # more misses than the log holds (every alignment its own read, no cache): the rest is inserted directly
+    cols = synth.make_columns(8000000, 2000000, 1, seed=3, mode=1)
+    got, _ = _run(native, cols, 2000000, 1, two_phase=2, hot_cache=0)
+    _assert_same(got, _oracle(cols))
+    for n_reads in (1, 31, 64, 65, 300, 5000):
+        cols = synth.make_columns(n_reads, 50, 2, seed=n_reads, mode="diploid", dup_rate=0.1)
+        got, _ = _run(native, cols, 50, 2, two_phase=2, grid_ctas=2, chunk_len=64)
+        _assert_same(got, _oracle(cols))
+    cols = synth.make_columns(120000, 3000, 2, seed=8, mode="diploid")
+    rg = cols["read_group"]
+    cut = int(np.flatnonzero(rg[1:] != rg[:-1])[len(rg) // 5] + 1)
+    with native.EcBuilder(3000, 2, two_phase=2) as b:
+        b.push(rg[:cut], cols["target_idx"][:cut], cols["hap_idx"][:cut])
+        b.push(rg[cut:], cols["target_idx"][cut:], cols["hap_idx"][cut:], order_base=cut)
+        got = b.finalize()
+    _assert_same(got, _oracle(cols))
+
+
 def test_two_phase_insert_gives_the_same_result(native):
     """ECB_OPT_TWO_PHASE: cache misses logged per table partition and inserted by a second kernel -
     same matrices as the direct insert, also when the table is too small and the logged reads have to
