@@ -83,9 +83,18 @@ struct Mix4 {
   u32 a, b, c, d;
 };
 // multiply-fold: low ^ high half of a 32x32 -> 64 bit product (one IMAD.WIDE + one LOP3)
+#ifndef ECB_MUM_PTX
+#define ECB_MUM_PTX 0   // 1: spell the 32x32->64 multiply out in PTX (experiment: the compiler's version carries
+#endif                  // dead add-with-zero instructions in the grouping kernel)
 __host__ __device__ __forceinline__ u32 mum32(u32 x, u32 k) {
+#if ECB_MUM_PTX && defined(__CUDA_ARCH__)
+  u32 lo, hi;
+  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(k));
+  return lo ^ hi;
+#else
   const u64 p = (u64)x * k;
   return (u32)p ^ (u32)(p >> 32);
+#endif
 }
 __host__ __device__ __forceinline__ Mix4 ecb_mix(u32 code) {
   Mix4 m;
