@@ -2,7 +2,7 @@
 # First GPU call of round 2 (about 4 minutes of box time): parity of the default tree, the strip kernel
 # re-evaluated, and ncu captures of both grouping kernels so that the open question of DESIGN.md 4.1b
 # (why an insert batch costs 25 us in the strip kernel and 6 us in the window kernel) can be read off the
-# stall reasons / local-memory traffic.   usage: gpurun --timeout 420 -- 'bash tools/round2_first_call.sh'
+# stall reasons / local-memory traffic.   usage: bash tools/build_strip_variants.sh (here, once), then gpurun --timeout 420 -- 'bash tools/round2_first_call.sh'
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -2 gpurun_out/r2_pytest_gpu.log
 rm -f gpurun_out/strip_eval.json
