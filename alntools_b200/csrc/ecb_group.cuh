@@ -121,6 +121,48 @@ __device__ __forceinline__ u32 table_probe_from(EcbEntry* table, u32 mask, const
   return ECB_NONE;
 }
 
+#ifndef ECB_WARP_PROBE
+#define ECB_WARP_PROBE 0   // 1 (experiment, to be measured): probe continuation of the batched insert as a warp-uniform loop
+#endif
+
+// Warp-uniform form of table_probe_from for code that the whole warp executes together: every lane stays in
+// the loop until the last one is done (lanes without work idle), so the loop has ONE exit, decided by a
+// vote.  With the per-lane exits of table_probe_from inlined into the window loop, ptxas can no longer
+// prove that loop convergent and guards every shuffle / vote in it with a BRA.DIV check: 25 of them, 28
+// warp instructions per window (10 %).  With this form the kernel has none (3040 -> 2880 instructions).
+__device__ __forceinline__ u32 table_probe_warp(EcbEntry* table, u32 mask, const Key128& key, u32 slot,
+                                                int max_probe, bool need, bool& claimed, u64& first_seen) {
+  u32 result = ECB_NONE;
+  bool active = need;
+  for (int p = 0; p < max_probe; ++p) {
+    if (!__any_sync(ECB_FULL, active)) break;
+    if (active) {
+      EcbEntry* e = table + slot;
+      Key128 k;
+      u64 first;
+      u32 cm1, aux;
+      load_entry_cg(e, k, first, cm1, aux);
+      if (key_eq(k, key)) {
+        first_seen = first;
+        result = slot;
+        active = false;
+      } else if (key_empty(k)) {
+        Key128 old = atomic_cas128(e, Key128{~0ull, ~0ull}, key);
+        if (key_empty(old)) {
+          claimed = true;
+          result = slot;
+          active = false;
+        } else if (key_eq(old, key)) {
+          result = slot;
+          active = false;
+        }
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+  return result;
+}
+
 // Find `key` or claim an empty slot for it.  EC selects the EC table's slot hash.
 template <bool EC = false>
 __device__ __forceinline__ u32 table_find_or_claim(EcbEntry* table, u32 mask, const Key128& key,
@@ -229,6 +271,17 @@ __device__ __forceinline__ void global_upsert2(const GroupParams& P, const Key12
   if (casB) fB = ~0ull;
   slotA = (eqA || clA || (casA && key_eq(kA, keyA))) ? hA : ECB_NONE;
   slotB = (eqB || clB || (casB && key_eq(kB, keyB))) ? hB : ECB_NONE;
+#if ECB_WARP_PROBE
+  {  // the home slot holds another key: walk on - the whole warp together (see table_probe_warp)
+    const bool moreA = hasA && slotA == ECB_NONE, moreB = hasB && slotB == ECB_NONE;
+    if (moreA) fA = ~0ull;
+    if (moreB) fB = ~0ull;
+    const u32 wa = table_probe_warp(P.table, P.mask, keyA, (hA + 1) & P.mask, ECB_MAX_PROBE - 1, moreA, clA, fA);
+    const u32 wb = table_probe_warp(P.table, P.mask, keyB, (hB + 1) & P.mask, ECB_MAX_PROBE - 1, moreB, clB, fB);
+    if (moreA) slotA = wa;
+    if (moreB) slotB = wb;
+  }
+#else
   if (hasA && slotA == ECB_NONE) {  // the home slot holds another key: walk on
     fA = ~0ull;
     slotA = table_probe_from(P.table, P.mask, keyA, (hA + 1) & P.mask, ECB_MAX_PROBE - 1, clA, fA);
@@ -237,6 +290,7 @@ __device__ __forceinline__ void global_upsert2(const GroupParams& P, const Key12
     fB = ~0ull;
     slotB = table_probe_from(P.table, P.mask, keyB, (hB + 1) & P.mask, ECB_MAX_PROBE - 1, clB, fB);
   }
+#endif
   if (slotA != ECB_NONE) {
     EcbEntry* e = P.table + slotA;
     atomicAdd(&e->countm1, 1u);

@@ -6,5 +6,7 @@ F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -
 nvcc $F -DECB_STRIP_EXPERIMENT=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_strip_noinsert.so &
 nvcc $F -DECB_STRIP_EXPERIMENT=2 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_strip_walkonly.so &
 nvcc $F -DECB_MUM_PTX=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_mumptx.so &
+nvcc $F -DECB_WARP_PROBE=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_warpprobe.so &
+nvcc $F -DECB_WARP_PROBE=1 -DECB_MUM_PTX=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_lean.so &
 wait
 ls -la tools/_build/

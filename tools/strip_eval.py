@@ -32,7 +32,9 @@ if os.path.isfile(BASE):
     base["n_reads"], base["n_ec"] = int(z["n_reads"]), int(z["n_ec"])
 RUNS = [("window", None, {}), ("strip32", None, {"strip_kernel": 32}), ("strip24", None, {"strip_kernel": 24}),
         ("dense24", None, {"strip_kernel": 124}), ("flatlog", None, {"two_phase": 2}), ("partlog", None, {"two_phase": 1}),
-        ("window_mumptx", "libecb_mumptx.so", {}), ("flatlog_mumptx", "libecb_mumptx.so", {"two_phase": 2}),
+        ("window_mumptx", "libecb_mumptx.so", {}), ("window_warpprobe", "libecb_warpprobe.so", {}),
+        ("window_lean", "libecb_lean.so", {}), ("flatlog_lean", "libecb_lean.so", {"two_phase": 2}),
+        ("dense24_lean", "libecb_lean.so", {"strip_kernel": 124}),
         ("window_nocache", None, {"hot_cache": 0}),
         ("dense24_nocache", None, {"strip_kernel": 124, "hot_cache": 0}),
         ("X_noinsert_dense24", "libecb_strip_noinsert.so", {"strip_kernel": 124}),
