@@ -477,7 +477,11 @@ __device__ __forceinline__ void log_misses(const GroupParams& P, u32 qk, u32 qr,
   const bool okA = hasA && log_append(P, keyA, rA.x, 1u, rA.x, rA.y, posA, pA);
   const bool okB = hasB && log_append(P, keyB, rB.x, 1u, rB.x, rB.y, posB, pB);
   const bool redoA = hasA && !okA, redoB = hasB && !okB;
+#if ECB_WARP_PROBE
+  if (__any_sync(ECB_FULL, redoA || redoB)) {   // global_upsert2 is a whole-warp routine in this build
+#else
   if (redoA || redoB) {
+#endif
     u32 slotA, slotB;
     global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
     if (redoA && slotA == ECB_NONE) {
@@ -520,7 +524,11 @@ __device__ __forceinline__ void log_misses_priv(const GroupParams& P, u32 qk, u3
   const bool okB = log_append(P, keyB, rB.x, hasB ? 1u : 0u, rB.x, rB.y, lb + lu + 32u + (u32)lane, 0u);
   lu += 64u;
   const bool redoA = hasA && !okA, redoB = hasB && !okB;   // the log is full: insert directly
+#if ECB_WARP_PROBE
+  if (__any_sync(ECB_FULL, redoA || redoB)) {   // global_upsert2 is a whole-warp routine in this build
+#else
   if (redoA || redoB) {
+#endif
     u32 slotA, slotB;
     global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
     if (redoA && slotA == ECB_NONE) {
