@@ -28,6 +28,7 @@
 //     first load and the first CAS of both reads of a lane are in flight together: a warp pays for the
 //     slowest lane's chain of round trips once per batch.  The cache is flushed when the CTA is done.
 #pragma once
+#include <cstddef>
 #include "ecb_common.cuh"
 
 #define ECB_GWARPS 32                  // warps per CTA of the grouping kernel
@@ -121,6 +122,9 @@ __device__ __forceinline__ u32 table_probe_from(EcbEntry* table, u32 mask, const
   return ECB_NONE;
 }
 
+#ifndef ECB_SMEM_BASE_ASM
+#define ECB_SMEM_BASE_ASM 0   // 1 (experiment, to be measured): shared-window base of the grouping kernel from one opaque asm
+#endif
 #ifndef ECB_WARP_PROBE
 #define ECB_WARP_PROBE 0   // 1 (experiment, to be measured): probe continuation of the batched insert as a warp-uniform loop
 #endif
@@ -627,10 +631,22 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
   __syncthreads();
 
+#if ECB_SMEM_BASE_ASM
+  // one opaque base: the compiler keeps it (in a uniform register) instead of re-deriving the shared window
+  // from SR_CgaCtaId in every window (S2R + MOV + LEA + 2 adds in front of the cache look-up)
+  u32 sbase;
+  asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(sbase) : "l"(smem_raw));
+  const u32 qk = sbase + (u32)offsetof(GroupSmem, q_key) + (u32)warp * ECB_MQ * 16u;   // this warp's miss queue
+  const u32 qr = sbase + (u32)offsetof(GroupSmem, q_rep) + (u32)warp * ECB_MQ * 8u;
+  const u32 a_key = sbase + (u32)offsetof(GroupSmem, c_key), a_lock = sbase + (u32)offsetof(GroupSmem, c_lock);
+  const u32 a_cnt = sbase + (u32)offsetof(GroupSmem, c_cnt), a_first = sbase + (u32)offsetof(GroupSmem, c_first);
+  const u32 a_rep = sbase + (u32)offsetof(GroupSmem, c_rep), a_seen = sbase + (u32)offsetof(GroupSmem, seen);
+#else
   const u32 qk = smem_u32(S.q_key[warp]);  // this warp's miss queue (shared-window addresses)
   const u32 qr = smem_u32(S.q_rep[warp]);
   const u32 a_key = smem_u32(S.c_key), a_lock = smem_u32(S.c_lock), a_cnt = smem_u32(S.c_cnt);
   const u32 a_first = smem_u32(S.c_first), a_rep = smem_u32(S.c_rep), a_seen = smem_u32(S.seen);
+#endif
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
   u32 reads_counted = 0;  // per lane
   u32 lb = 0u, lu = ECB_LOG_BLOCK;   // PRIVLOG: base and fill of this warp's block of the flat log (none yet)
