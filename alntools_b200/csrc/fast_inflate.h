@@ -314,9 +314,9 @@ static inline void copy_match_fast(uint8_t* out, uint32_t distance, uint32_t len
 static bool inflate_codes(BitReader& br, const Tables& T, uint8_t* const dst, uint8_t*& out_ref, uint8_t* const out_end) {
   uint8_t* out = out_ref;
   // ---- fast loop: far enough from both ends that no single step can leave the buffers -------------------
-  // one step writes at most 3 literals + a 258-byte match (+ 15 bytes of copy overshoot) and reads at most
-  // 8 bytes beyond br.in twice
-  constexpr long OUT_MARGIN = 3 + 258 + 16, IN_MARGIN = 24;
+  // one step writes at most 3 literals + a 258-byte match (+ 15 bytes of copy overshoot) and refills up to
+  // three times (8 bytes read at br.in, which advances by at most 7 each time)
+  constexpr long OUT_MARGIN = 3 + 258 + 16, IN_MARGIN = 32;
   if (out_end - out > OUT_MARGIN && br.in_end - br.in > IN_MARGIN && br.cnt >= 0) {
     uint8_t* const out_safe = out_end - OUT_MARGIN;
     const uint8_t* const in_safe = br.in_end - IN_MARGIN;
@@ -327,8 +327,9 @@ static bool inflate_codes(BitReader& br, const Tables& T, uint8_t* const dst, ui
   buf |= load64(in) << cnt;       \
   in += (63 - cnt) >> 3;          \
   cnt |= 56;
-#define FI_LOOKUP(e)                                                   \
-  e = T.lit[buf & ((1u << LIT_BITS) - 1)];                             \
+    bool ok = true, done = false;
+#define FI_PRIMARY(e) e = T.lit[buf & ((1u << LIT_BITS) - 1)];
+#define FI_CONSUME(e)                                                  \
   if (e & F_SUB) {                                                     \
     buf >>= LIT_BITS;                                                  \
     cnt -= LIT_BITS;                                                   \
@@ -336,23 +337,29 @@ static bool inflate_codes(BitReader& br, const Tables& T, uint8_t* const dst, ui
   }                                                                    \
   buf >>= (e & 0xFFu);                                                 \
   cnt -= (int)(e & 0xFFu);
-    bool ok = true, done = false;
+    // e = primary table entry of the upcoming symbol, looked up right after a refill, nothing consumed yet;
+    // it is fetched BEFORE the match copy of the previous symbol so that the table load hides behind the copy
+    uint32_t e;
+    FI_REFILL()
+    FI_PRIMARY(e)
     while (out < out_safe && in < in_safe) {
-      FI_REFILL()
-      uint32_t e;
-      FI_LOOKUP(e)
+      FI_CONSUME(e)                       // >= 41 bits left
       if (e & F_LITERAL) {
         *out++ = (uint8_t)(e >> 16);
-        FI_LOOKUP(e)
+        FI_PRIMARY(e)
+        FI_CONSUME(e)                     // >= 26
         if (e & F_LITERAL) {
           *out++ = (uint8_t)(e >> 16);
-          FI_LOOKUP(e)
+          FI_PRIMARY(e)
+          FI_CONSUME(e)                   // >= 11
           if (e & F_LITERAL) {
             *out++ = (uint8_t)(e >> 16);
+            FI_REFILL()
+            FI_PRIMARY(e)
             continue;
           }
         }
-        FI_REFILL()
+        FI_REFILL()                       // a length / distance pair needs up to 33 bits
       }
       if (!(e & F_BASE)) {
         if (((e >> 12) & 15u) == K_EOB) done = true; else ok = false;
@@ -382,11 +389,14 @@ static bool inflate_codes(BitReader& br, const Tables& T, uint8_t* const dst, ui
         ok = false;
         break;
       }
+      FI_REFILL()
+      FI_PRIMARY(e)                       // next symbol's entry is on its way while the match is copied
       copy_match_fast(out, distance, length);
       out += length;
     }
+#undef FI_PRIMARY
+#undef FI_CONSUME
 #undef FI_REFILL
-#undef FI_LOOKUP
     br.buf = buf;
     br.cnt = cnt;
     br.in = in;
