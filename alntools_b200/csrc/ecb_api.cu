@@ -318,6 +318,8 @@ int group_prepare_launch(ecb_ctx* c) {
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
+    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)sizeof(GroupSmem)));
     CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -635,7 +637,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
-    case ECB_OPT_TWO_PHASE: c->two_phase = value == 2 ? 2 : (value ? 1 : 0); break;
+    case ECB_OPT_TWO_PHASE: c->two_phase = (value == 2 || value == 3) ? (int)value : (value ? 1 : 0); break;
     case ECB_OPT_STRIP_KERNEL:
       c->strip_kernel = value ? 1 : 0;
       if (value == 24 || value == 32) { c->strip_warps = (int)value; c->strip_dense = 0; }
@@ -714,7 +716,7 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
-  const bool flat_log = c->two_phase == 2 && !c->strip_kernel && !c->with_cells;
+  const bool flat_log = (c->two_phase == 2 || c->two_phase == 3) && !c->strip_kernel && !c->with_cells;
   const bool two_phase = c->two_phase == 1 && !c->strip_kernel && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
   if (two_phase) {
     // logs sized from the push: misses are at most one per read, reads at most one per alignment
@@ -759,6 +761,8 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     else ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
   }
   else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  else if (flat_log && c->two_phase == 3)
+    ecb_group_insert_kernel<false, true, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else if (flat_log) ecb_group_insert_kernel<false, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);

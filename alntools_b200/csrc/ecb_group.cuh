@@ -505,7 +505,7 @@ __device__ __forceinline__ void log_misses(const GroupParams& P, u32 qk, u32 qr,
 // in the last, partial batch of a warp are written as empty entries (count 0) so that a block has no holes;
 // lb / lu = base and fill of the warp's current block.
 __device__ __forceinline__ void log_misses_priv(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb,
-                                                bool hasB, u32& lb, u32& lu) {
+                                                bool hasB, u32& lb, u32& lu, const bool pair = true) {
   const int lane = threadIdx.x & 31;
   uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
   uint2 rA = make_uint2(0u, 0u), rB = rA;
@@ -524,9 +524,10 @@ __device__ __forceinline__ void log_misses_priv(const GroupParams& P, u32 qk, u3
     lu = 0u;
   }
   const Key128 keyA = key_of(kA), keyB = key_of(kB);
+  // pair = false: a batch of 32 (entry qa of every lane only)
   const bool okA = log_append(P, keyA, rA.x, hasA ? 1u : 0u, rA.x, rA.y, lb + lu + (u32)lane, 0u);
-  const bool okB = log_append(P, keyB, rB.x, hasB ? 1u : 0u, rB.x, rB.y, lb + lu + 32u + (u32)lane, 0u);
-  lu += 64u;
+  const bool okB = pair ? log_append(P, keyB, rB.x, hasB ? 1u : 0u, rB.x, rB.y, lb + lu + 32u + (u32)lane, 0u) : true;
+  lu += pair ? 64u : 32u;
   const bool redoA = hasA && !okA, redoB = hasB && !okB;   // the log is full: insert directly
 #if ECB_WARP_PROBE
   if (__any_sync(ECB_FULL, redoA || redoB)) {   // global_upsert2 is a whole-warp routine in this build
@@ -598,10 +599,71 @@ __device__ __noinline__ LongRead ecb_long_read(const int32_t* __restrict__ rg, c
   return r;
 }
 
+// DENSEQ: cache look-up of up to 32 parked reads (entry idx of every lane that `has` one), misses to the
+// lower end of the warp's queue and from there to the flat log, 32 at a time.  The whole warp calls it.
+struct DenseAddr {
+  u32 qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen;
+};
+__device__ __forceinline__ void dense_commit(const GroupParams& P, const DenseAddr& A, bool use_cache, bool has, u32 idx,
+                                             u32 lt_mask, int lane, u32& qn, u32& lb, u32& lu) {
+  const u32 qk = A.qk, qr = A.qr, a_key = A.a_key, a_lock = A.a_lock, a_cnt = A.a_cnt, a_first = A.a_first,
+            a_rep = A.a_rep, a_seen = A.a_seen;
+  uint4 k2 = make_uint4(0u, 0u, 0u, 0u);
+  uint2 r2 = make_uint2(0u, 0u);
+  if (has) {
+    k2 = lds128(qk + idx * 16u);
+    r2 = lds64(qr + idx * 8u);
+  }
+  __syncwarp();
+  bool miss2 = has;
+  if (use_cache && has) {
+    const u32 cidx = (k2.y >> 7) & (ECB_CACHE - 1);
+    const uint4 ck = lds128(a_key + cidx * 16u);
+    const u32 cf = lds32(a_first + cidx * 4u);
+    bool hit = ck.x == k2.x && ck.y == k2.y && ck.z == k2.z && ck.w == k2.w;
+    if (!hit && (ck.x & ck.y & ck.z & ck.w) == 0xFFFFFFFFu) {
+#if ECB_ADMIT_SECOND
+      const u32 sbit = 1u << (k2.z & 31u);
+      const bool again = (atoms_or(a_seen + ((k2.z >> 5) & (ECB_SEEN_WORDS - 1)) * 4u, sbit) & sbit) != 0u;
+#else
+      const bool again = true;
+#endif
+      if (again && atoms_cas(a_lock + cidx * 4u, 0u, 1u) == 0u) {
+        sts64(a_rep + cidx * 8u, r2.x, r2.y);
+        sts128(a_key + cidx * 16u, k2);
+        hit = true;
+      }
+    }
+    if (hit) {
+      reds_add(a_cnt + cidx * 4u, 1u);
+      if (r2.x < cf) reds_min(a_first + cidx * 4u, r2.x);
+      miss2 = false;
+    }
+  }
+  const u32 mm2 = __ballot_sync(ECB_FULL, miss2);
+  if (mm2) {
+    if (miss2) {
+      const u32 q = qn + __popc(mm2 & lt_mask);
+      sts128(qk + q * 16u, k2);
+      sts64(qr + q * 8u, r2.x, r2.y);
+    }
+    qn += __popc(mm2);
+    __syncwarp();
+    if (qn >= 32u) {
+      qn -= 32u;
+      log_misses_priv(P, qk, qr, qn + lane, true, 0u, false, lb, lu, false);
+      __syncwarp();
+    }
+  }
+}
+
 // LOGGED: the experimental two-phase insert (ECB_OPT_TWO_PHASE); a template parameter so that the
 // default kernel carries none of it.
 // PRIVLOG (with LOGGED): the flat log with per-warp blocks instead of the per-partition logs.
-template <bool WITH_CELLS, bool LOGGED = false, bool PRIVLOG = false>
+// DENSEQ (with PRIVLOG, ECB_OPT_TWO_PHASE = 3): closed reads are parked in the upper end of the warp's queue
+// and looked up in the cache 32 at a time with every lane busy (in the plain form about 14 of 32 lanes are,
+// once per window); misses grow from the lower end and go to the log in batches of 32.
+template <bool WITH_CELLS, bool LOGGED = false, bool PRIVLOG = false, bool DENSEQ = false>
 __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const GroupParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
@@ -650,6 +712,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
   u32 reads_counted = 0;  // per lane
   u32 lb = 0u, lu = ECB_LOG_BLOCK;   // PRIVLOG: base and fill of this warp's block of the flat log (none yet)
+  [[maybe_unused]] u32 cn = 0u;      // DENSEQ: closed reads parked at the upper end of the queue (warp-uniform)
 
   for (;;) {
     // ---- next chunk of the stream (dynamic: whichever warp is free takes it) -------------------------
@@ -792,6 +855,26 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       }
       w = wnext;
 
+      if constexpr (DENSEQ) {
+        // ---- closed reads are parked; 32 of them at a time go through the cache ----------------------
+        if (ins) ++reads_counted;
+        const u32 cm = __ballot_sync(ECB_FULL, ins);
+        if (cm) {
+          if (ins) {
+            const u32 j = (ECB_MQ - 1u) - (cn + __popc(cm & lt_mask));
+            sts128(qk + j * 16u, key);
+            sts64(qr + j * 8u, s, len);
+          }
+          cn += __popc(cm);
+          __syncwarp();
+          if (cn >= 32u) {
+            cn -= 32u;
+            dense_commit(P, DenseAddr{qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen}, use_cache, true,
+                         (ECB_MQ - 1u) - (cn + (u32)lane), lt_mask, lane, qn, lb, lu);
+          }
+        }
+        continue;
+      }
       // ---- closed reads: hot-EC cache first --------------------------------------------------------
       bool miss = ins;
       if (ins) ++reads_counted;
@@ -846,6 +929,13 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
+  if constexpr (DENSEQ) {   // the parked reads that are left, then the misses that are left, in batches of 32
+    if (cn) dense_commit(P, DenseAddr{qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen}, use_cache, (u32)lane < cn,
+                         (ECB_MQ - 1u) - (u32)lane, lt_mask, lane, qn, lb, lu);
+    if (qn) log_misses_priv(P, qk, qr, lane, (u32)lane < qn, 0u, false, lb, lu, false);
+    if (qn > 32u) log_misses_priv(P, qk, qr, lane + 32, (u32)lane + 32u < qn, 0u, false, lb, lu, false);
+    qn = 0u;
+  }
   if (qn) {
     if (PRIVLOG) log_misses_priv(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn, lb, lu);
     else if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);

@@ -347,7 +347,7 @@ def main():
     if args.chunk_len:
         opts["chunk_len"] = args.chunk_len
     if args.two_phase:
-        opts["two_phase"] = args.two_phase          # 1: per-partition logs, 2: flat log in per-warp blocks
+        opts["two_phase"] = args.two_phase          # 1: per-partition logs, 2: flat log in per-warp blocks, 3: + dense cache look-ups
     stream = torch.cuda.current_stream()
 
     def barrier():

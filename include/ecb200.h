@@ -69,7 +69,8 @@ enum ecb_option {
                                    kernel inserts them partition by partition (table slice resident in L2);
                                    2: one flat log filled in per-warp blocks of 256 entries (no atomic with a
                                    return value in the streaming loop), inserted by a second kernel with one
-                                   entry per thread.  Experimental, single-sample path only */
+                                   entry per thread; 3: as 2, with the cache look-ups of the grouping kernel
+                                   batched 32 at a time on full warps.  Experimental, single-sample path only */
   ECB_OPT_STRIP_KERNEL = 10     /* 1: the strip form of the grouping kernel (a lane walks 8 consecutive alignments
                                    in registers instead of one alignment per lane; same table protocol, same
                                    results); 24 or 32 also select that many warps per CTA, 124 = 24 warps with the

@@ -488,8 +488,9 @@ def test_strip_kernel_gives_the_same_result(native, warps):
 
 @pytest.mark.skipif(os.environ.get("ECB_TEST_FLATLOG") != "1", reason="ECB_OPT_TWO_PHASE = 2 (flat log, per-warp blocks) was "
                     "written after the last GPU minute of round 1; first run pending (ECB_TEST_FLATLOG=1)")
-def test_flat_log_two_phase_insert_gives_the_same_result(native):
-    """ECB_OPT_TWO_PHASE = 2: misses appended to one flat log in per-warp blocks, inserted by a second kernel -
+@pytest.mark.parametrize("form", [2, 3])
+def test_flat_log_two_phase_insert_gives_the_same_result(native, form):
+    """ECB_OPT_TWO_PHASE = 2 (3: with the cache look-ups batched on full warps): misses appended to one flat log in per-warp blocks, inserted by a second kernel -
     same matrices as the direct insert, with and without the cache, with a table that has to grow, with a
     log too small for the misses (alignments that are all their own read) and across several pushes."""
     from alntools_b200 import synth
@@ -501,20 +502,20 @@ def test_flat_log_two_phase_insert_gives_the_same_result(native):
         cols = synth.make_columns(n_reads, n_targets, n_haps, seed=5, mode=mode, dup_rate=dup)
         want = _oracle(cols)
         for cache in (1, 0):
-            got, stats = _run(native, cols, n_targets, n_haps, two_phase=2, table_slots=slots, hot_cache=cache)
+            got, stats = _run(native, cols, n_targets, n_haps, two_phase=form, table_slots=slots, hot_cache=cache)
             _assert_same(got, want)
     # more misses than the log holds (every alignment its own read, no cache): the rest is inserted directly
     cols = synth.make_columns(8000000, 2000000, 1, seed=3, mode=1)
-    got, _ = _run(native, cols, 2000000, 1, two_phase=2, hot_cache=0)
+    got, _ = _run(native, cols, 2000000, 1, two_phase=form, hot_cache=0)
     _assert_same(got, _oracle(cols))
     for n_reads in (1, 31, 64, 65, 300, 5000):
         cols = synth.make_columns(n_reads, 50, 2, seed=n_reads, mode="diploid", dup_rate=0.1)
-        got, _ = _run(native, cols, 50, 2, two_phase=2, grid_ctas=2, chunk_len=64)
+        got, _ = _run(native, cols, 50, 2, two_phase=form, grid_ctas=2, chunk_len=64)
         _assert_same(got, _oracle(cols))
     cols = synth.make_columns(120000, 3000, 2, seed=8, mode="diploid")
     rg = cols["read_group"]
     cut = int(np.flatnonzero(rg[1:] != rg[:-1])[len(rg) // 5] + 1)
-    with native.EcBuilder(3000, 2, two_phase=2) as b:
+    with native.EcBuilder(3000, 2, two_phase=form) as b:
         b.push(rg[:cut], cols["target_idx"][:cut], cols["hap_idx"][:cut])
         b.push(rg[cut:], cols["target_idx"][cut:], cols["hap_idx"][cut:], order_base=cut)
         got = b.finalize()
