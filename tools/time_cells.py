@@ -1,5 +1,5 @@
 """Timing of the per-cell host emitter (parallel window code vs BAMCOLS_SEQUENTIAL_CELLS) on a synthetic
-10x-style BAM with fixed-length '|||' names.  Usage: python _variants/time_cells.py [n_reads]"""
+10x-style BAM with fixed-length '|||' names.  Usage: python tools/time_cells.py [n_reads]"""
 import os, sys, time, struct
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
