@@ -308,30 +308,20 @@ GroupParams make_group_params(ecb_ctx* c, const int32_t* rg, const int32_t* tg, 
   return P;
 }
 
+// Opt-in shared memory of the grouping kernels.  The default kernels are prepared once per context; an
+// experimental variant is prepared when it is first launched, so that nothing it needs can get in the way
+// of the default path.
+template <class K>
+int allow_group_smem(ecb_ctx* c, K kernel) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)));
+  return ECB_OK;
+}
+
 int group_prepare_launch(ecb_ctx* c) {
   if (!c->group_attr_set) {
-    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_insert_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<false, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
-    CK(cudaFuncSetAttribute(ecb_group_strip_kernel<true, 24, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)sizeof(GroupSmem)));
+    CKR(allow_group_smem(c, ecb_group_insert_kernel<true>));
+    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true>));
+    CKR(allow_group_smem(c, ecb_group_insert_kernel<false>));
     c->group_attr_set = true;
   }
   return ECB_OK;
@@ -748,22 +738,45 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     P.plog_shift = 0;
     P.use_log = 1;
   }
+  // experimental variants: opt-in shared memory of the one that is about to run (outside the timed interval)
+  if (c->strip_kernel && c->strip_dense) {
+    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 24, true>) : allow_group_smem(c, ecb_group_strip_kernel<false, 24, true>));
+  } else if (c->strip_kernel && c->strip_warps == 24) {
+    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 24>) : allow_group_smem(c, ecb_group_strip_kernel<false, 24>));
+  } else if (c->strip_kernel) {
+    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 32>) : allow_group_smem(c, ecb_group_strip_kernel<false, 32>));
+  } else if (flat_log && c->two_phase == 3) {
+    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true, true, true>));
+  } else if (flat_log) {
+    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true, true>));
+  }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
   if (c->strip_kernel && c->strip_dense) {
-    if (c->with_cells) ecb_group_strip_kernel<true, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    else ecb_group_strip_kernel<false, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    if (c->with_cells) {
+      ecb_group_strip_kernel<true, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    } else {
+      ecb_group_strip_kernel<false, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    }
   } else if (c->strip_kernel && c->strip_warps == 24) {
-    if (c->with_cells) ecb_group_strip_kernel<true, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    else ecb_group_strip_kernel<false, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    if (c->with_cells) {
+      ecb_group_strip_kernel<true, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    } else {
+      ecb_group_strip_kernel<false, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
+    }
   } else if (c->strip_kernel) {
-    if (c->with_cells) ecb_group_strip_kernel<true, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
-    else ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
+    if (c->with_cells) {
+      ecb_group_strip_kernel<true, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
+    } else {
+      ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
+    }
   }
   else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
-  else if (flat_log && c->two_phase == 3)
+  else if (flat_log && c->two_phase == 3) {
     ecb_group_insert_kernel<false, true, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
-  else if (flat_log) ecb_group_insert_kernel<false, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  } else if (flat_log) {
+    ecb_group_insert_kernel<false, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  }
   else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
