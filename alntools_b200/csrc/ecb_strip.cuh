@@ -17,7 +17,7 @@
 // Closed reads go through the same per-CTA hot-EC cache, miss queue and batched HBM-table insert as in
 // the window kernel (the code below repeats that block; see the header of ecb_group.cuh).
 //
-// The per-lane walk is plain C++ (`__host__ __device__`): tests/strip_host_test.cu runs it on the CPU
+// The per-lane walk is plain C++ (`__host__ __device__`): tests/native/strip_host_test.cu runs it on the CPU
 // against a serial statement of the grouping rule.
 #pragma once
 #include "ecb_group.cuh"
