@@ -120,11 +120,30 @@ class BamColumnReader(object):
         if rc != 0:
             _raise(rc, self._lib.bamcols_last_error(None).decode())
         self._h = h
-        n = self._lib.bamcols_n_references(h)
+        self.n_references = int(self._lib.bamcols_n_references(h))
+        self._references = self._lengths = None
+
+    def _load_references(self):
+        # 200 000 Python strings cost more than decoding a few million alignments: built on first use only
+        n = self.n_references
         names, lens = ctypes.c_void_p(), ctypes.c_void_p()
-        nbytes = self._lib.bamcols_reference_blob(h, ctypes.byref(names), ctypes.byref(lens))
-        self.references = tuple(ctypes.string_at(names, nbytes).decode().split("\0")[:n]) if n else ()
-        self.lengths = tuple((ctypes.c_int32 * n).from_address(lens.value)) if n else ()
+        nbytes = self._lib.bamcols_reference_blob(self._h, ctypes.byref(names), ctypes.byref(lens))
+        self._references = tuple(ctypes.string_at(names, nbytes).decode().split("\0")[:n]) if n else ()
+        self._lengths = tuple((ctypes.c_int32 * n).from_address(lens.value)) if n else ()
+
+    @property
+    def references(self):
+        """@SQ names in tid order, as pysam's .references."""
+        if self._references is None:
+            self._load_references()
+        return self._references
+
+    @property
+    def lengths(self):
+        """@SQ lengths in tid order, as pysam's .lengths."""
+        if self._lengths is None:
+            self._load_references()
+        return self._lengths
 
     def set_tables(self, tables):
         tt = np.ascontiguousarray(tables.tid_target, dtype=np.int32)
@@ -135,7 +154,6 @@ class BamColumnReader(object):
 
     def build_tables(self, target_filename=None):
         """Header -> TargetTables-compatible object, built natively and installed in this reader."""
-        from collections import OrderedDict
         from . import utils
         first = b""
         if target_filename:
@@ -152,13 +170,13 @@ class BamColumnReader(object):
         tl, hl = ctypes.c_int64(), ctypes.c_int64()
         self._lib.bamcols_tables(self._h, ctypes.byref(nt), ctypes.byref(nh), ctypes.byref(tp), ctypes.byref(tl),
                                  ctypes.byref(hp_), ctypes.byref(hl), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
-        n_ref = len(self.references)
+        n_ref = self.n_references
 
         class _Tables(object):
             pass
         t = _Tables()
         names = ctypes.string_at(tp, tl.value).decode().split("\0")[:nt.value] if nt.value else []
-        t.main_targets = OrderedDict(zip(names, range(len(names))))
+        t.main_targets = dict(zip(names, range(len(names))))   # insertion-ordered; OrderedDict costs 5x as much here
         t.haplotypes = ctypes.string_at(hp_, hl.value).decode().split("\0")[:nh.value] if nh.value else []
         t.tid_target = np.array((ctypes.c_int32 * n_ref).from_address(a.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)
         t.tid_hap = np.array((ctypes.c_int32 * n_ref).from_address(b.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)

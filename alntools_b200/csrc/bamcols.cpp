@@ -21,6 +21,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <string_view>
 #include <thread>
 #include <unordered_map>
 #include <vector>
@@ -1249,48 +1250,75 @@ int bamcols_set_tables(bamcols* r, const int32_t* tid_target, const int32_t* tid
 // haplotype; main targets are numbered target-file ids first, then in header order; haplotypes are
 // sorted; lengths[target][haplotype] = reference length.  first_targets: the target file's ids, each
 // followed by a NUL (may be empty).
+// Distinct strings in order of first appearance -> dense ids.  Open addressing over views into memory the
+// caller keeps alive (the reference names, the target list): no per-name allocation.
+struct ViewIds {
+  std::vector<std::string_view> views;
+  std::vector<int32_t> slot;   // -1 = empty
+  size_t mask = 0;
+  explicit ViewIds(size_t expect) {
+    size_t cap = 16;
+    while (cap < 2 * expect + 16) cap <<= 1;
+    slot.assign(cap, -1);
+    mask = cap - 1;
+    views.reserve(expect);
+  }
+  int32_t id_of(std::string_view v) {
+    if ((views.size() + 1) * 2 > mask + 1) {   // grow (only when `expect` was too small)
+      std::vector<int32_t> bigger((mask + 1) * 2, -1);
+      const size_t m2 = bigger.size() - 1;
+      for (size_t i = 0; i < views.size(); ++i) {
+        size_t j = bamcols_cells::hash_of(views[i].data(), views[i].size()) & m2;
+        while (bigger[j] >= 0) j = (j + 1) & m2;
+        bigger[j] = (int32_t)i;
+      }
+      slot.swap(bigger);
+      mask = m2;
+    }
+    size_t j = bamcols_cells::hash_of(v.data(), v.size()) & mask;
+    for (; slot[j] >= 0; j = (j + 1) & mask)
+      if (views[(size_t)slot[j]] == v) return slot[j];
+    slot[j] = (int32_t)views.size();
+    views.push_back(v);
+    return slot[j];
+  }
+};
+
 int bamcols_build_tables(bamcols* r, const char* first_targets, int64_t first_len) {
   if (!r || first_len < 0 || (first_len > 0 && !first_targets)) return BAMCOLS_ERR_INVALID;
   const size_t n = r->ref_names.size();
-  std::unordered_map<std::string, int32_t> target_id;
-  std::vector<const std::string*> target_names;
-  target_id.reserve(n);
-  auto add_target = [&](const std::string& t) -> int32_t {
-    auto it = target_id.find(t);
-    if (it != target_id.end()) return it->second;
-    const int32_t id = (int32_t)target_names.size();
-    auto ins = target_id.emplace(t, id);
-    target_names.push_back(&ins.first->first);
-    return id;
-  };
+  // main targets: the target list first, then unseen targets in header order (bam_utils.py:571-598)
+  ViewIds targets(n);
   for (int64_t p = 0; p < first_len;) {
     const size_t l = strnlen(first_targets + p, (size_t)(first_len - p));
-    add_target(std::string(first_targets + p, l));
+    targets.id_of(std::string_view(first_targets + p, l));
     p += (int64_t)l + 1;
   }
-  std::vector<std::string> haps(n);
-  std::vector<int32_t> tt(n);
+  // target / haplotype of every reference: split at the last '_' unless it is the first character (:584-591)
+  ViewIds hap_seen(64);
+  std::vector<int32_t> tt(n), hraw(n);
   for (size_t i = 0; i < n; ++i) {
     const std::string& name = r->ref_names[i];
     const size_t cut = name.rfind('_');
     if (cut != std::string::npos && cut > 0) {
-      tt[i] = add_target(name.substr(0, cut));
-      haps[i] = name.substr(cut + 1);
+      tt[i] = targets.id_of(std::string_view(name.data(), cut));
+      hraw[i] = hap_seen.id_of(std::string_view(name.data() + cut + 1, name.size() - cut - 1));
     } else {
-      tt[i] = add_target(name);
+      tt[i] = targets.id_of(std::string_view(name));
+      hraw[i] = hap_seen.id_of(std::string_view());
     }
   }
-  std::vector<std::string> sorted_haps(haps);
-  std::sort(sorted_haps.begin(), sorted_haps.end());
-  sorted_haps.erase(std::unique(sorted_haps.begin(), sorted_haps.end()), sorted_haps.end());
-  std::unordered_map<std::string, int32_t> hap_id;
-  for (size_t h = 0; h < sorted_haps.size(); ++h) hap_id.emplace(sorted_haps[h], (int32_t)h);
-  const size_t T = target_names.size(), H = sorted_haps.size();
+  // haplotypes = sorted(set) (:602): ids of the distinct ones in sorted order
+  const size_t T = targets.views.size(), H = hap_seen.views.size();
+  std::vector<int32_t> order(H), rank(H);
+  for (size_t h = 0; h < H; ++h) order[h] = (int32_t)h;
+  std::sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return hap_seen.views[(size_t)x] < hap_seen.views[(size_t)y]; });
+  for (size_t k = 0; k < H; ++k) rank[(size_t)order[k]] = (int32_t)k;
   std::vector<int32_t> th(n);
   std::vector<int32_t> owner(T * H, -1);
   r->tb_lengths.assign(T * H, 0);
   for (size_t i = 0; i < n; ++i) {
-    th[i] = hap_id[haps[i]];
+    th[i] = rank[(size_t)hraw[i]];
     int32_t& o = owner[(size_t)tt[i] * H + (size_t)th[i]];
     if (o >= 0)
       return fail(r, BAMCOLS_ERR_INVALID, "@SQ names '%s' and '%s' map to the same (target, haplotype)",
@@ -1299,13 +1327,17 @@ int bamcols_build_tables(bamcols* r, const char* first_targets, int64_t first_le
     r->tb_lengths[(size_t)tt[i] * H + (size_t)th[i]] = r->ref_lengths[i];
   }
   r->tb_targets.clear();
-  for (const std::string* t : target_names) {
-    r->tb_targets.append(*t);
+  size_t bytes = 0;
+  for (const std::string_view& t : targets.views) bytes += t.size() + 1;
+  r->tb_targets.reserve(bytes);
+  for (const std::string_view& t : targets.views) {
+    r->tb_targets.append(t.data(), t.size());
     r->tb_targets.push_back('\0');
   }
   r->tb_haps.clear();
-  for (const std::string& h : sorted_haps) {
-    r->tb_haps.append(h);
+  for (size_t k = 0; k < H; ++k) {
+    const std::string_view& h = hap_seen.views[(size_t)order[k]];
+    r->tb_haps.append(h.data(), h.size());
     r->tb_haps.push_back('\0');
   }
   r->tb_n_targets = (int32_t)T;
