@@ -72,7 +72,8 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
         LOG.info("# Unique Reads: {:,}".format(res["n_reads"]))
         a_csr = (res["a_indptr"], res["a_indices"], res["a_data"])
         n_csc = (res["n_indptr"], res["n_indices"], res["n_data"])
-        target_names = list(tables.main_targets.keys())
+        section = tables.target_section() if hasattr(tables, "target_section") else None   # native tables only
+        target_names = list(tables.main_targets.keys()) if (emase_filename or section is None) else None
         if emase_filename:
             LOG.info("Saving to {}...".format(emase_filename))
             try:
@@ -90,7 +91,7 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
                 pass
             temp_time = time.time()
             bin_utils.ecsave2_arrays(ec_filename, tables.haplotypes, target_names, tables.lengths, [sample],
-                                     a_csr, n_csc)
+                                     a_csr, n_csc, target_section=section, n_targets=tables.num_targets)
             LOG.info("{} created in {}, total time: {}".format(ec_filename,
                                                                utils.format_time(temp_time, time.time()),
                                                                utils.format_time(start_time, time.time())))

@@ -42,6 +42,7 @@ SIGNATURES = {
     "bamcols_track_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bamcols_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_phase_seconds": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
+    "bamcols_target_section": (ctypes.c_int64, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_inflate_raw": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]),
 }
 
@@ -172,11 +173,30 @@ class BamColumnReader(object):
                                  ctypes.byref(hp_), ctypes.byref(hl), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
         n_ref = self.n_references
 
+        names_blob = ctypes.string_at(tp, tl.value)
+        n_targets = nt.value
+
         class _Tables(object):
-            pass
+            """TargetTables-compatible view of the native tables; the 100 000-entry name structures are only
+            built when something asks for them (convert() writes the EC file from target_section())."""
+            _main_targets = None
+
+            @property
+            def main_targets(self):
+                if self._main_targets is None:
+                    names = names_blob.decode().split("\0")[:n_targets] if n_targets else []
+                    self._main_targets = dict(zip(names, range(len(names))))   # insertion-ordered
+                return self._main_targets
         t = _Tables()
-        names = ctypes.string_at(tp, tl.value).decode().split("\0")[:nt.value] if nt.value else []
-        t.main_targets = dict(zip(names, range(len(names))))   # insertion-ordered; OrderedDict costs 5x as much here
+        reader = self
+
+        def target_section():
+            p = ctypes.c_void_p()
+            nbytes = reader._lib.bamcols_target_section(reader._h, ctypes.byref(p))
+            if nbytes < 0:
+                _raise(int(nbytes), reader._lib.bamcols_last_error(reader._h).decode())
+            return ctypes.string_at(p, nbytes) if nbytes > 0 else None    # None: non-ASCII names, use the name list
+        t.target_section = target_section
         t.haplotypes = ctypes.string_at(hp_, hl.value).decode().split("\0")[:nh.value] if nh.value else []
         t.tid_target = np.array((ctypes.c_int32 * n_ref).from_address(a.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)
         t.tid_hap = np.array((ctypes.c_int32 * n_ref).from_address(b.value), dtype=np.int32) if n_ref else np.zeros(0, np.int32)

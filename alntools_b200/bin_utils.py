@@ -48,17 +48,24 @@ def _target_section(target_names, lengths, n_haps):
     return out.tobytes()
 
 
-def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names, a_csr, n_csc):
-    """a_csr / n_csc: (indptr, indices, data) int32 arrays."""
+def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names, a_csr, n_csc, target_section=None,
+                   n_targets=None):
+    """a_csr / n_csc: (indptr, indices, data) int32 arrays.  target_section (with n_targets): the bytes of the
+    targets section when the caller already has them (the native header tables build them without creating
+    a Python string per target); then target_names / lengths are not looked at."""
     with open(ec_filename, "wb") as fh:
         fh.write(struct.pack("<i", 2))
         fh.write(struct.pack("<i", len(haplotypes)))
         for hap in haplotypes:
             fh.write(struct.pack("<i", len(hap)))
             fh.write(hap.encode("utf-8"))
-        lengths = np.asarray(lengths).astype(int)
-        fh.write(struct.pack("<i", len(target_names)))
-        fh.write(_target_section(target_names, lengths, len(haplotypes)))
+        if target_section is not None:
+            fh.write(struct.pack("<i", int(n_targets)))
+            fh.write(target_section)
+        else:
+            lengths = np.asarray(lengths).astype(int)
+            fh.write(struct.pack("<i", len(target_names)))
+            fh.write(_target_section(target_names, lengths, len(haplotypes)))
         fh.write(struct.pack("<i", len(sample_names)))
         parts = []
         for sample in sample_names:

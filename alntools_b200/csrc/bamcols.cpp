@@ -222,6 +222,7 @@ struct bamcols {
   std::string tb_haps;           // sorted haplotype names, each followed by a NUL
   std::vector<int32_t> tb_lengths;  // [n_targets x n_haps]
   int32_t tb_n_targets = 0, tb_n_haps = 0;
+  std::string tb_section;        // the targets section of the EC file, built on demand
   // the first batch of blocks is inflated in the background while the caller builds its header tables
   std::thread prefetch;
   int prefetch_rc = 0;
@@ -1362,6 +1363,34 @@ int bamcols_tables(const bamcols* r, int32_t* n_targets, int32_t* n_haps, const 
   *tid_hap = r->tid_hap.data();
   *lengths = r->tb_lengths.data();
   return BAMCOLS_OK;
+}
+
+int64_t bamcols_target_section(bamcols* r, const char** bytes) {
+  if (!r || !bytes) return BAMCOLS_ERR_INVALID;
+  if (r->tb_n_targets == 0 && r->tb_targets.empty()) return fail(r, BAMCOLS_ERR_INVALID, "bamcols_build_tables was not called");
+  // T x [len(name), name bytes, H x length], little-endian int32s (alntools/bin_utils.py:153-159)
+  std::string& out = r->tb_section;
+  out.clear();
+  const size_t H = (size_t)r->tb_n_haps;
+  out.reserve(r->tb_targets.size() + (size_t)r->tb_n_targets * (4 + 4 * H));
+  auto put32 = [&](uint32_t v) {
+    const char b[4] = {(char)(v & 0xFF), (char)((v >> 8) & 0xFF), (char)((v >> 16) & 0xFF), (char)((v >> 24) & 0xFF)};
+    out.append(b, 4);
+  };
+  // the reference writes len(name) in CHARACTERS in front of the UTF-8 bytes: only for ASCII names is that the
+  // byte count, anything else is left to the caller (who reproduces the reference's bytes in Python)
+  for (const char ch : r->tb_targets)
+    if ((unsigned char)ch >= 0x80) return 0;
+  const char* p = r->tb_targets.data();
+  for (int32_t t = 0; t < r->tb_n_targets; ++t) {
+    const size_t l = strlen(p);
+    put32((uint32_t)l);
+    out.append(p, l);
+    for (size_t h = 0; h < H; ++h) put32((uint32_t)r->tb_lengths[(size_t)t * H + h]);
+    p += l + 1;
+  }
+  *bytes = out.data();
+  return (int64_t)out.size();
 }
 
 int bamcols_cells_create(bamcols_cells** out) {

@@ -68,6 +68,11 @@ int bamcols_build_tables(bamcols* r, const char* first_targets, int64_t first_le
 int bamcols_tables(const bamcols* r, int32_t* n_targets, int32_t* n_haps, const char** targets, int64_t* targets_len,
                    const char** haps, int64_t* haps_len, const int32_t** tid_target, const int32_t** tid_hap,
                    const int32_t** lengths);
+/* The targets section of the EC file, T x [len(name), name bytes, H x length] as little-endian int32s
+ * (alntools/bin_utils.py:153-159), from the tables of bamcols_build_tables.  Returns the number of bytes (the
+ * buffer belongs to the reader), or 0 when a target name is not ASCII: the reference writes the length in
+ * characters there and the caller has to reproduce that from the decoded names. */
+int64_t bamcols_target_section(bamcols* r, const char** bytes);
 
 /* Cell-name dictionary of one per-cell job: names get dense ids in order of first appearance. */
 int bamcols_cells_create(bamcols_cells** out);

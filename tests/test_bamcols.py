@@ -453,3 +453,25 @@ def test_per_cell_parallel_equals_sequential_statement(tmp_path, monkeypatch):
             header, recs = load_records(path)
             want = emitter.emit_multisample(recs, tables, {})
             assert results[0][0] == want.read_group.tolist() and results[0][1] == want.cell_idx.tolist()
+
+
+def test_native_target_section_equals_the_python_one(tmp_path):
+    """The EC file's targets section built by libbamcols (convert() writes it without creating a Python string
+    per target) against bin_utils._target_section on the same tables; non-ASCII names are declined (the
+    reference writes their length in characters) and the caller falls back to the name list."""
+    from alntools_b200 import bin_utils
+    refs = [("t1_A", 10), ("t1_B", 11), ("t2", 5), ("_x", 7), ("longer_name_here_C", 99), ("t3_A", 1)]
+    path = str(tmp_path / "sec.bam")
+    bam_io.write_bam(path, refs, [("r1", 0, 0, 0, -1, -1), ("r2", 0, 2, 0, -1, -1)])
+    with bamcols.BamColumnReader(path) as r:
+        t = r.build_tables(None)
+        got = t.target_section()
+        names = list(t.main_targets.keys())
+        want = bin_utils._target_section(names, np.asarray(t.lengths).astype(int), len(t.haplotypes))
+        assert got == want
+    path2 = str(tmp_path / "uni.bam")
+    bam_io.write_bam(path2, [("tr\u00e4_A", 3), ("t2_A", 4)], [("r1", 0, 0, 0, -1, -1)])
+    with bamcols.BamColumnReader(path2) as r:
+        t = r.build_tables(None)
+        assert t.target_section() is None
+        assert list(t.main_targets.keys()) == ["tr\u00e4", "t2"]
