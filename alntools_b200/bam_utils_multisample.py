@@ -38,12 +38,14 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
     else:
         cells = bamcols.CellDictionary()
         tables = None
-        range_lo = range_hi = references = None
+        range_lo = range_hi = references = section = None
         for bam_file in bam_files:
             with bamcols.BamColumnReader(bam_file) as reader:
                 if tables is None:                            # tables from the first file only (:399)
                     tables = reader.build_tables(target_filename)
-                    references = reader.references
+                    section = tables.target_section()         # the EC file's targets block, while the reader lives
+                    if range_filename is not None:
+                        references = reader.references
                 else:
                     reader.set_tables(tables)
                 if range_filename is not None:
@@ -77,7 +79,9 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
     sample_names = [cell_names[c] for c in res["cell_order"].tolist()]
     a_csr = (res["a_indptr"], res["a_indices"], res["a_data"])
     n_csc = (res["n_indptr"], res["n_indices"], res["n_data"])
-    target_names = list(tables.main_targets.keys())
+    if emitter.use_python_emitter():
+        section = None
+    target_names = list(tables.main_targets.keys()) if (emase_filename or section is None) else None
     if emase_filename:
         try:
             os.remove(emase_filename)
@@ -92,7 +96,7 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
         except OSError:
             pass
         bin_utils.ecsave2_arrays(ec_filename, tables.haplotypes, target_names, tables.lengths, sample_names,
-                                 a_csr, n_csc)
+                                 a_csr, n_csc, target_section=section, n_targets=tables.num_targets)
         LOG.info("{} created, total time: {}".format(ec_filename, utils.format_time(start_time, time.time())))
     return res
 

@@ -191,6 +191,8 @@ class BamColumnReader(object):
         reader = self
 
         def target_section():
+            if reader._h is None:                      # the reader is gone: the caller uses the name list
+                return None
             p = ctypes.c_void_p()
             nbytes = reader._lib.bamcols_target_section(reader._h, ctypes.byref(p))
             if nbytes < 0:
