@@ -95,3 +95,59 @@ def test_ec_file_round_trip(tmp_path):
 def test_partition_matches_reference_semantics():
     assert utils.partition(list(range(7)), 3) == [[0, 1, 2], [3, 4], [5, 6]]
     assert utils.partition(list(range(2)), 4) == [[0], [1]]
+
+
+class _StubBuilder(object):
+    """Stands in for the GPU builder: accepts every push and returns fixed, well-formed result arrays, so that
+    the host side of convert() (decode, tables, file writing) can run on a machine without a GPU."""
+
+    def __init__(self, *a, **k):
+        self.rows = 0
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def push(self, rg, tg, hp, cell=None, order_base=0, drop_last_group=False, n=None):
+        self.rows += int(n) if n is not None else len(rg)
+
+    def finalize(self, min_cell_count=0, copy=True):
+        i32 = lambda *v: np.array(v, dtype=np.int32)
+        return {"n_ec": 2, "n_reads": 3, "n_samples": 2, "a_indptr": i32(0, 1, 3), "a_indices": i32(0, 0, 1),
+                "a_data": i32(1, 3, 1), "n_indptr": i32(0, 1, 2), "n_indices": i32(0, 1), "n_data": i32(2, 1),
+                "cell_order": i32(0, 1)}
+
+
+def test_convert_writes_the_same_file_with_native_and_python_target_sections(tmp_path, monkeypatch):
+    """convert() / convert_files() write the EC file's targets block from libbamcols when the tables are native;
+    the bytes must equal what the Python writer produces from the name list (stub builder: no GPU needed)."""
+    from conftest import GOLDEN, golden_cases
+    from alntools_b200 import bam_utils, bam_utils_multisample, bamcols
+    monkeypatch.setattr(bam_utils, "EcBuilder", _StubBuilder)
+    monkeypatch.setattr(bam_utils_multisample, "EcBuilder", _StubBuilder)
+    real_build = bamcols.BamColumnReader.build_tables
+
+    def build_without_section(self, target_filename=None):
+        t = real_build(self, target_filename)
+        t.target_section = lambda: None
+        return t
+
+    outputs = {}
+    for mode in ("native", "python"):
+        if mode == "python":
+            monkeypatch.setattr(bamcols.BamColumnReader, "build_tables", build_without_section)
+        case = golden_cases("single")[0]
+        out = str(tmp_path / ("single_%s.bin" % mode))
+        tfile = os.path.join(GOLDEN, case["targets"]) if case["targets"] else None
+        bam_utils.convert(os.path.join(GOLDEN, case["bam"]), out, None, num_chunks=1, number_processes=1,
+                          target_filename=tfile)
+        mcase = golden_cases("multisample")[0]
+        mout = str(tmp_path / ("multi_%s.bin" % mode))
+        files = [os.path.join(GOLDEN, mcase["dir"], fn) for fn in mcase["file_order"]]
+        bam_utils_multisample.convert_files(files, mout, None, mcase["mincount"])
+        outputs[mode] = (open(out, "rb").read(), open(mout, "rb").read())
+    assert outputs["native"][0] == outputs["python"][0]
+    assert outputs["native"][1] == outputs["python"][1]
+    assert len(outputs["native"][0]) > 60 and len(outputs["native"][1]) > 60
