@@ -50,7 +50,7 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
                     reader.set_tables(tables)
                 if range_filename is not None:
                     reader.track_ranges(True)
-                c = reader.read_all(cells=cells)
+                c = reader.read_all(cells=cells, chunk=1 << 23)
                 if range_filename is not None:                # merged over the files (:568-576)
                     lo, hi = reader.ranges()
                     range_lo = lo if range_lo is None else np.minimum(range_lo, lo)
