@@ -109,11 +109,18 @@ __host__ __device__ __forceinline__ void mix_add(Mix4& x, const Mix4& y) {
 }
 __host__ __device__ __forceinline__ Mix4 mix_zero() { return Mix4{0u, 0u, 0u, 0u}; }
 
+#ifndef ECB_KEY127
+#define ECB_KEY127 0   // 1 (experiment, to be measured): the top bit of every key is cleared, so the all-ones empty
+#endif                 // marker cannot occur and the per-read test for it (6 instructions per window) goes away
 __host__ __device__ __forceinline__ Key128 mix_to_key(const Mix4& m) {
   Key128 k;
   k.lo = ((u64)m.b << 32) | m.a;
+#if ECB_KEY127
+  k.hi = ((u64)(m.d & 0x7FFFFFFFu) << 32) | m.c;
+#else
   k.hi = ((u64)m.d << 32) | m.c;
   if (key_empty(k)) k.lo = 0;  // all-ones is the empty marker
+#endif
   return k;
 }
 // Slot hash over all 128 key bits (EC keys are already uniform; (file, EC, cell) keys are not).

@@ -390,9 +390,13 @@ __device__ __forceinline__ Key128 key_of(const uint4& k) {
   return Key128{((u64)k.y << 32) | k.x, ((u64)k.w << 32) | k.z};
 }
 __host__ __device__ __forceinline__ uint4 key_words(const Mix4& m) {
+#if ECB_KEY127
+  return make_uint4(m.a, m.b, m.c, m.d & 0x7FFFFFFFu);   // as mix_to_key
+#else
   uint4 k = make_uint4(m.a, m.b, m.c, m.d);
   if ((k.x & k.y & k.z & k.w) == 0xFFFFFFFFu) k.x = k.y = 0u;  // all-ones is the empty marker (as mix_to_key)
   return k;
+#endif
 }
 // Column loads: read once (twice by overlapping windows, which L1 absorbs), so they are marked
 // evict-first in L2 and leave the cache to the EC table.

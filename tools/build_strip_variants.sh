@@ -9,5 +9,6 @@ nvcc $F -DECB_MUM_PTX=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_mum
 nvcc $F -DECB_WARP_PROBE=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_warpprobe.so &
 nvcc $F -DECB_WARP_PROBE=1 -DECB_MUM_PTX=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_lean.so &
 nvcc $F -DECB_WARP_PROBE=1 -DECB_MUM_PTX=1 -DECB_SMEM_BASE_ASM=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_lean2.so &
+nvcc $F -DECB_WARP_PROBE=1 -DECB_MUM_PTX=1 -DECB_SMEM_BASE_ASM=1 -DECB_KEY127=1 alntools_b200/csrc/ecb_api.cu -o tools/_build/libecb_lean3.so &
 wait
 ls -la tools/_build/

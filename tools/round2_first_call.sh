@@ -7,8 +7,8 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -2 gpurun_out/r2_pytest_gpu.log
 rm -f gpurun_out/strip_eval.json
 # separate processes: a variant that faults takes only its own group with it
-timeout 90 python tools/strip_eval.py window window_mumptx window_warpprobe window_lean window_lean2 > gpurun_out/r2_strip_eval.log 2>&1
-timeout 90 python tools/strip_eval.py flatlog flatlog3 partlog flatlog_lean flatlog_lean2 flatlog3_lean2 >> gpurun_out/r2_strip_eval.log 2>&1
+timeout 90 python tools/strip_eval.py window window_mumptx window_warpprobe window_lean window_lean2 window_lean3 > gpurun_out/r2_strip_eval.log 2>&1
+timeout 90 python tools/strip_eval.py flatlog flatlog3 partlog flatlog_lean flatlog_lean2 flatlog3_lean2 flatlog3_lean3 >> gpurun_out/r2_strip_eval.log 2>&1
 timeout 90 python tools/strip_eval.py strip32 strip24 dense24 dense24_lean >> gpurun_out/r2_strip_eval.log 2>&1
 grep -v "^columns ready\|^best correct" gpurun_out/r2_strip_eval.log
 ECB_TEST_STRIP=1 ECB_TEST_FLATLOG=1 timeout 150 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "strip or flat_log" > gpurun_out/r2_pytest_strip.log 2>&1; tail -2 gpurun_out/r2_pytest_strip.log

@@ -33,7 +33,8 @@ if os.path.isfile(BASE):
 RUNS = [("window", None, {}), ("strip32", None, {"strip_kernel": 32}), ("strip24", None, {"strip_kernel": 24}),
         ("dense24", None, {"strip_kernel": 124}), ("flatlog", None, {"two_phase": 2}), ("flatlog3", None, {"two_phase": 3}), ("partlog", None, {"two_phase": 1}),
         ("window_mumptx", "libecb_mumptx.so", {}), ("window_warpprobe", "libecb_warpprobe.so", {}),
-        ("window_lean", "libecb_lean.so", {}), ("window_lean2", "libecb_lean2.so", {}), ("flatlog_lean2", "libecb_lean2.so", {"two_phase": 2}), ("flatlog3_lean2", "libecb_lean2.so", {"two_phase": 3}), ("flatlog_lean", "libecb_lean.so", {"two_phase": 2}),
+        ("window_lean", "libecb_lean.so", {}), ("window_lean2", "libecb_lean2.so", {}), ("flatlog_lean2", "libecb_lean2.so", {"two_phase": 2}), ("flatlog3_lean2", "libecb_lean2.so", {"two_phase": 3}),
+        ("window_lean3", "libecb_lean3.so", {}), ("flatlog3_lean3", "libecb_lean3.so", {"two_phase": 3}), ("flatlog_lean", "libecb_lean.so", {"two_phase": 2}),
         ("dense24_lean", "libecb_lean.so", {"strip_kernel": 124}),
         ("window_nocache", None, {"hot_cache": 0}),
         ("dense24_nocache", None, {"strip_kernel": 124, "hot_cache": 0}),
