@@ -861,9 +861,9 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
 
       if constexpr (DENSEQ) {
         // ---- closed reads are parked; 32 of them at a time go through the cache ----------------------
-        if (ins) ++reads_counted;
         const u32 cm = __ballot_sync(ECB_FULL, ins);
         if (cm) {
+          if (lane == 0) reads_counted += __popc(cm);   // the count of the vote is there anyway
           if (ins) {
             const u32 j = (ECB_MQ - 1u) - (cn + __popc(cm & lt_mask));
             sts128(qk + j * 16u, key);
