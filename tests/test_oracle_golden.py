@@ -112,3 +112,36 @@ def test_goldens_regenerate_identically(tmp_path):
     run_reference.bam2ec(bam, out, 1, 1, None, temp_dir=str(tmp_path))
     with open(out, "rb") as a, open(os.path.join(GOLDEN, case["ec"]), "rb") as b:
         assert a.read() == b.read()
+
+
+def test_reference_ecfile_reader_decodes_our_files_like_we_do(tmp_path):
+    """the reference's own ECFile reader (bin_file.py:99-402) as an independent
+    decoder.  Every golden EC file, and the same content written again by bin_utils.ecsave2_arrays, must
+    come back from it with the names and matrices that bin_utils.ecload_arrays reads."""
+    from oracle import run_reference
+    if not run_reference.available():
+        pytest.skip("the reference tree is not on this machine")
+    run_reference._import_reference()
+    from alntools import bin_file                      # the reference package
+    from alntools_b200 import bin_utils
+    import json
+    with open(os.path.join(GOLDEN, "manifest.json")) as fh:
+        cases = json.load(fh)
+    for case in cases:
+        src = os.path.join(GOLDEN, case["ec"])
+        ours = bin_utils.ecload_arrays(src)
+        again = str(tmp_path / (case["name"] + ".again.bin"))
+        bin_utils.ecsave2_arrays(again, ours["haplotypes"], ours["targets"], ours["lengths"], ours["samples"],
+                                 ours["a"], ours["n"])
+        with open(src, "rb") as a, open(again, "rb") as b:
+            assert a.read() == b.read(), case["name"]
+        ref = bin_file.ECFile(again)
+        text = lambda v: v.decode() if isinstance(v, bytes) else v   # names come back as bytes on py3 (SURVEY A9)
+        assert [text(h) for h in ref.haplotypes_idx] == ours["haplotypes"], case["name"]
+        assert [text(t) for t in ref.targets_idx] == ours["targets"], case["name"]
+        assert [text(s) for s in ref.samples_idx] == ours["samples"], case["name"]
+        assert np.array_equal(ref.a_matrix.indptr, ours["a"][0]) and np.array_equal(ref.a_matrix.indices, ours["a"][1])
+        assert np.array_equal(ref.a_matrix.data, ours["a"][2]), case["name"]
+        assert np.array_equal(ref.n_matrix.indptr, ours["n"][0]) and np.array_equal(ref.n_matrix.indices, ours["n"][1])
+        assert np.array_equal(ref.n_matrix.data, ours["n"][2]), case["name"]
+        assert ref.a_matrix.shape[0] == len(ours["a"][0]) - 1
