@@ -145,3 +145,51 @@ def test_reference_ecfile_reader_decodes_our_files_like_we_do(tmp_path):
         assert np.array_equal(ref.n_matrix.indptr, ours["n"][0]) and np.array_equal(ref.n_matrix.indices, ours["n"][1])
         assert np.array_equal(ref.n_matrix.data, ours["n"][2]), case["name"]
         assert ref.a_matrix.shape[0] == len(ours["a"][0]) - 1
+
+
+def test_reference_writers_accept_our_output_object(tmp_path):
+    """SURVEY section 8b, 'Output object': alntools_b200.apm.ApmArrays carries the fields the reference's writers
+    read.  Built from the arrays of every golden EC file and handed to the UNMODIFIED reference's
+    bin_utils.ecsave2, it must produce the golden bytes again; handed to the reference's APM.save code path
+    (run against the recording `tables` shim) it must leave the committed EMASE record."""
+    from oracle import run_reference
+    if not run_reference.available():
+        pytest.skip("the reference tree is not on this machine")
+    run_reference._import_reference()
+    from alntools import bin_utils as ref_bin_utils          # the reference package
+    from alntools.matrix.AlignmentPropertyMatrix import AlignmentPropertyMatrix as RefAPM
+    from alntools_b200 import bin_utils
+    from alntools_b200.apm import ApmArrays
+    import json
+    import pickle
+    import tables                                            # the shim (on sys.path after _import_reference)
+    with open(os.path.join(GOLDEN, "manifest.json")) as fh:
+        cases = json.load(fh)
+    for case in cases:
+        src = os.path.join(GOLDEN, case["ec"])
+        ec = bin_utils.ecload_arrays(src)
+        apm = ApmArrays(ec["haplotypes"], ec["targets"], ec["lengths"], ec["samples"], ec["a"], ec["n"])
+        # the reference's save() as an unbound function over our object (convert() calls it before ecsave2,
+        # bam_utils.py:849-876, and ecsave2 widens apm.lengths in place)
+        single = case["kind"] == "single"
+        rec = tables.start_recording()
+        h5 = str(tmp_path / (case["name"] + ".h5"))
+        try:
+            RefAPM.save(apm, h5, title="bam2ec" if single else "Multisample APM", incidence_only=single)
+        finally:
+            tables.stop_recording()
+        with open(os.path.join(GOLDEN, case["name"] + ".emase.pkl"), "rb") as fh:
+            want = pickle.load(fh)
+        got = rec[h5]
+        assert len(got) == len(want), case["name"]
+        for g, w in zip(got, want):
+            assert g["op"] == w["op"] and g.get("node") == w.get("node"), case["name"]
+            if g["op"] == "carray":
+                assert str(np.asarray(g["array"]).dtype) == str(np.asarray(w["array"]).dtype), (case["name"], g["node"])
+                assert np.array_equal(g["array"], w["array"]), (case["name"], g["node"])
+            if g["op"] == "attr":
+                assert g["value"] == w["value"], (case["name"], g["name"])
+        out = str(tmp_path / (case["name"] + ".ref.bin"))
+        ref_bin_utils.ecsave2(out, apm)
+        with open(src, "rb") as a, open(out, "rb") as b:
+            assert a.read() == b.read(), case["name"]
