@@ -224,3 +224,35 @@ def iter_records(raw, offset):
         tid, pos, l_name, _mq, _bin, _nc, flag, _ls, ntid, npos, _tl = unpack(raw, offset + 4)
         yield raw[offset + 36:offset + 36 + l_name - 1].decode(), flag, tid, pos, ntid, npos
         offset += 4 + bs
+
+
+def read_virtual(filename, virtual_offset, nbytes):
+    """`nbytes` inflated bytes starting at a BGZF virtual offset (compressed block start << 16 | offset inside
+    the inflated block), continuing over as many blocks as it takes - what the reference does with
+    Bio.bgzf.BgzfReader.seek() + read() when it cuts a chunk (bam_utils.py:173-179, 185-191)."""
+    out, need = [], int(nbytes)
+    block, within = int(virtual_offset) >> 16, int(virtual_offset) & 0xFFFF
+    with open(filename, "rb") as fh:
+        while need > 0:
+            fh.seek(block)
+            head = fh.read(18)
+            if len(head) < 18 or head[:4] != b"\x1f\x8b\x08\x04":
+                break
+            xlen = struct.unpack_from("<H", head, 10)[0]
+            fh.seek(block + 12)
+            extra = fh.read(xlen)
+            bsize, p = None, 0
+            while p < xlen:
+                slen = struct.unpack_from("<H", extra, p + 2)[0]
+                if extra[p:p + 2] == b"BC":
+                    bsize = struct.unpack_from("<H", extra, p + 4)[0] + 1
+                p += 4 + slen
+            if bsize is None:
+                raise ValueError("BGZF block without BC field")
+            data = zlib.decompress(fh.read(bsize - 12 - xlen - 8), -15)
+            take = data[within:within + need]
+            out.append(take)
+            need -= len(take)
+            block += bsize
+            within = 0
+    return b"".join(out)

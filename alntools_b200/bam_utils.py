@@ -5,6 +5,7 @@ Call stack: convert -> header tables (host) -> column emitter (host decode + fil
 -> EcBuilder.push (H2D + sm_100a kernels) -> EcBuilder.finalize (CSR A, CSC N) -> EC file writer.
 """
 import multiprocessing
+import collections
 import os
 import time
 
@@ -15,6 +16,131 @@ from ._native import EcBuilder
 from .header import TargetTables
 
 LOG = utils.get_logger()
+
+
+# ---- the reference's chunk-worker interface (bam_utils.py:30-62, 157-195, 198-363, 490-498) -------------
+# convert() below does not use it - it decodes the file once and streams it to the GPU - but code that drives
+# the reference's workers directly (a ConvertParams per process, wrapper_convert through Pool.imap, results
+# merged in chunk order) finds the same names, fields and results here.
+ParseRecord = collections.namedtuple("ParseRecord", ["header_size", "begin_read_offset", "begin_read_size",
+                                                     "file_offset", "file_bytes", "end_read_offset", "end_read_size"])
+
+
+class ConvertParams(object):
+    slots = ['input_file', 'temp_dir', 'process_id', 'track_ranges', 'data']
+
+    def __init__(self):
+        self.input_file = None
+        self.temp_dir = None
+        self.process_id = None
+        self.track_ranges = False
+        self.data = []                      # tuples of (idx, ParseRecord)
+
+    def __str__(self):
+        return "Input: {}\nProcess ID: {}\nData: {}".format(self.input_file, self.process_id, self.data)
+
+
+class ConvertResults(object):
+    slots = ['valid_alignments', 'all_alignments', 'ec', 'unique_reads', 'init', 'tid_ranges']
+
+    def __init__(self):
+        self.valid_alignments = None
+        self.all_alignments = None
+        self.ec = None
+        self.unique_reads = None
+        self.init = False
+        self.tid_ranges = None
+
+
+def chunk_bam_file(bam_filename, new_filename, parse_rec):
+    """A BAM file holding one chunk of `bam_filename` (bam_utils.py:157-195): the header blocks, the tail of
+    the block the chunk starts in, the whole blocks in between, the head of the block it ends in, EOF."""
+    from . import bam_io
+    with open(bam_filename, "rb") as src, open(new_filename, "wb") as out:
+        out.write(src.read(parse_rec.header_size))
+        if parse_rec.begin_read_offset > 0:
+            data = bam_io.read_virtual(bam_filename, parse_rec.begin_read_offset, parse_rec.begin_read_size)
+            for off in range(0, len(data), 60000):
+                out.write(bam_io.bgzf_block(data[off:off + 60000]))
+        src.seek(parse_rec.file_offset)
+        out.write(src.read(parse_rec.file_bytes))
+        if parse_rec.end_read_offset > 0:
+            data = bam_io.read_virtual(bam_filename, parse_rec.end_read_offset, parse_rec.end_read_size)
+            for off in range(0, len(data), 60000):
+                out.write(bam_io.bgzf_block(data[off:off + 60000]))
+        out.write(bam_io.BGZF_EOF)
+
+
+def process_convert_bam(cp, device=0):
+    """One worker of the reference (bam_utils.py:198-363): the chunks of cp.data, in order, through the GPU
+    EC build; returns ConvertResults with `ec` = OrderedDict 'tid,tid,...' (tids as strings, sorted as
+    strings, :306) -> number of reads, in first-occurrence order, exactly as the reference's worker.
+    unique_reads (log-only in the reference, every read name of the chunk) is left empty.  As in the
+    reference, a chunk without a valid alignment ends the worker with what it has (:336-349)."""
+    from collections import OrderedDict
+    ret = ConvertResults()
+    ret.valid_alignments = 0
+    ret.all_alignments = 0
+    ret.ec = OrderedDict()
+    ret.unique_reads = {}
+    ret.tid_ranges = {}
+    builder = tables = None
+    pushed = 0
+    try:
+        for idx, parse_record in cp.data:
+            temp_file = os.path.join(cp.temp_dir, "_bam2ec.{}.bam".format(idx))
+            utils.delete_file(temp_file)
+            chunk_bam_file(cp.input_file, temp_file, parse_record)
+            try:
+                with bamcols.BamColumnReader(temp_file) as reader:
+                    if tables is None:
+                        tables = reader.build_tables(None)
+                    else:
+                        reader.set_tables(tables)
+                    if cp.track_ranges:
+                        reader.track_ranges(True)
+                    cols = reader.read_all(chunk=1 << 23)
+                    ret.all_alignments += reader.all_alignments
+                    if cp.track_ranges:
+                        lo, hi = reader.ranges()
+                        for tid in np.flatnonzero(lo <= hi).tolist():        # bam_utils.py:272-286: keys are str(tid)
+                            n, x = ret.tid_ranges.get(str(tid), (int(lo[tid]), int(hi[tid])))
+                            ret.tid_ranges[str(tid)] = (min(n, int(lo[tid])), max(x, int(hi[tid])))
+            finally:
+                utils.delete_file(temp_file)
+            n = len(cols["read_group"])
+            if n == 0:
+                LOG.error("Error: sequence item 0: expected str instance, NoneType found")   # what :348 logs
+                break
+            if builder is None:
+                builder = EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False, alignments_hint=0,
+                                    device=device)
+            builder.push(cols["read_group"], cols["target_idx"], cols["hap_idx"], order_base=pushed)
+            pushed += n
+            ret.valid_alignments += n
+        if builder is not None and pushed:
+            res = builder.finalize()
+            # EC row (main target, haplotype mask) -> the tids of the reference's key
+            tid_of = np.full((tables.num_targets, max(1, tables.num_haplotypes)), -1, dtype=np.int64)
+            tid_of[tables.tid_target, tables.tid_hap] = np.arange(len(tables.tid_target))
+            indptr, indices, data, counts = res["a_indptr"], res["a_indices"], res["a_data"], res["n_data"]
+            for e in range(int(res["n_ec"])):
+                tids = []
+                for j in range(int(indptr[e]), int(indptr[e + 1])):
+                    mask = int(data[j])
+                    for h in range(tables.num_haplotypes):
+                        if (mask >> h) & 1:
+                            tids.append(str(int(tid_of[indices[j], h])))
+                ret.ec[",".join(sorted(tids))] = int(counts[e])
+    finally:
+        if builder is not None:
+            builder.close()
+    return ret
+
+
+def wrapper_convert(args):
+    """As the reference's (bam_utils.py:490-498): unpack the argument tuple Pool.imap delivers."""
+    return process_convert_bam(*args)
 
 
 def _job_plan(num_chunks, number_processes):

@@ -1,6 +1,7 @@
 """Host-side helpers that mirror alntools/utils.py (logging, partition, parse_targets)."""
 from collections import OrderedDict
 import logging
+import os
 
 LOG = None
 
@@ -30,6 +31,14 @@ def format_time(start, end):
     hours, rem = divmod(end - start, 3600)
     minutes, seconds = divmod(rem, 60)
     return "{:0>2}:{:0>2}:{:05.2f}".format(int(hours), int(minutes), seconds)
+
+
+def delete_file(file_name):
+    """Remove a file if it is there (alntools/utils.py: same name, same silence)."""
+    try:
+        os.remove(file_name)
+    except OSError:
+        pass
 
 
 def partition(lst, n):
