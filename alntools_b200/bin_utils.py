@@ -121,3 +121,18 @@ def ecload_arrays(ec_filename):
         raise ValueError("trailing bytes in EC file")
     return {"haplotypes": haplotypes, "targets": targets, "lengths": lengths, "samples": samples,
             "a": mats[0], "n": mats[1]}
+
+
+def ec2emase(ec_filename, emase_filename):
+    """EC binary file -> EMASE (.h5) file (alntools/bin_utils.py:979-995: ecload, then APM.save with the title
+    'Converted from <ec file>' and the data arrays included).  Needs PyTables like every EMASE output."""
+    import os
+    from . import emase
+    ec = ecload_arrays(ec_filename)
+    try:
+        os.remove(emase_filename)
+    except OSError:
+        pass
+    shape = (len(ec["targets"]), len(ec["haplotypes"]), len(ec["a"][0]) - 1)
+    emase.save_emase(emase_filename, "Converted from {}".format(ec_filename), shape, ec["haplotypes"], ec["targets"],
+                     ec["lengths"], ec["samples"], ec["a"], ec["n"], incidence_only=False, as_ecload=True)

@@ -63,3 +63,13 @@ def bam2emase(bam_file, emase_file, chunks, directory, mincount, multisample, nu
                                       rangefile, targets)
     else:
         methods.bam2emase(bam_file, emase_file, chunks, directory, number_processes, rangefile, targets)
+
+
+@cli.command('ec2emase', options_metavar='<options>', short_help='convert a binary EC file to EMASE format')
+@click.argument('ec_file', metavar='ec_file', type=click.Path(exists=True, resolve_path=True, dir_okay=False))
+@click.argument('emase_file', metavar='emase_file', type=click.Path(resolve_path=True, dir_okay=False))
+@click.option('-v', '--verbose', count=True, help='enables verbose mode')
+def ec2emase(ec_file, emase_file, verbose):
+    """Convert a binary EC format file (ec_file) to EMASE format (emase_file)"""
+    utils.configure_logging(verbose)
+    methods.ec2emase(ec_file, emase_file)

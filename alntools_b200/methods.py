@@ -36,3 +36,9 @@ def bam2emase_multisample(bam_filename, emase_filename, chunks=0, minimum_count=
                                   minimum_count=minimum_count, number_processes=number_processes,
                                   temp_dir=directory, range_filename=range_filename,
                                   target_filename=target_filename)
+
+
+def ec2emase(ec_file, emase_file):
+    """alntools/methods.py:205-206."""
+    from . import bin_utils
+    bin_utils.ec2emase(ec_file, emase_file)

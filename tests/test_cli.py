@@ -30,7 +30,7 @@ def test_commands_have_the_reference_surface():
         pytest.skip("the reference tree is not on this machine")
     run_reference._import_reference()
     from alntools import cli as ref                     # the reference package
-    for name in ("bam2ec", "bam2emase"):
+    for name in ("bam2ec", "bam2emase", "ec2emase"):
         assert _surface(ours.cli.commands[name]) == _surface(ref.cli.commands[name]), name
     # the facade and the converters below it: same parameter names, order and defaults
     # (methods.py:32-58, bam_utils.py:512, bam_utils_multisample.py:357); ours may add trailing keywords

@@ -93,3 +93,39 @@ def test_reference_reproduces_the_committed_records():
         assert len(got) == len(want), case["name"]
         for i, (g, w) in enumerate(zip(got, want)):
             _same_event(g, w, "%s event %d" % (case["name"], i))
+
+
+def test_ec2emase_hands_pytables_what_the_reference_does(tmp_path, monkeypatch):
+    """`ec2emase` (bin_utils.py:979-995): the reference reads the EC file back and saves it with the data arrays
+    included; ours must leave the same PyTables record for the same file."""
+    sys.path.insert(0, ROOT)
+    from oracle import run_reference
+    if not run_reference.available():
+        pytest.skip("the reference tree is not on this machine")
+    run_reference._import_reference()
+    from alntools import bin_utils as ref_bin_utils          # the reference package
+    import tables as shim                                     # the recording shim the reference imported
+    strip = lambda events: [e for e in events if e["op"] not in ("open", "close")]
+    for case in CASES[:2] + CASES[5:7]:
+        ec_file = os.path.join(GOLDEN, case["ec"])
+        rec = shim.start_recording()
+        ref_h5 = str(tmp_path / (case["name"] + ".ref.h5"))
+        try:
+            ref_bin_utils.ec2emase(ec_file, ref_h5)
+        finally:
+            shim.stop_recording()
+        want = strip(rec.get(ref_h5, []))
+        assert want, "the reference wrote nothing for %s (its ecload failed?)" % case["name"]
+        mine = _recording_tables()
+        monkeypatch.setitem(sys.modules, "tables", mine)
+        rec2 = mine.start_recording()
+        our_h5 = str(tmp_path / (case["name"] + ".our.h5"))
+        try:
+            bin_utils.ec2emase(ec_file, our_h5)
+        finally:
+            mine.stop_recording()
+        monkeypatch.setitem(sys.modules, "tables", shim)
+        got = strip(rec2[our_h5])
+        assert [(e["op"], e.get("node"), e.get("name")) for e in got] == [(e["op"], e.get("node"), e.get("name")) for e in want]
+        for i, (g, w) in enumerate(zip(got, want)):
+            _same_event(g, w, "%s event %d %s %s" % (case["name"], i, w["op"], w.get("node")))
