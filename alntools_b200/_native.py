@@ -20,8 +20,7 @@ ECB_OPT_HOT_CACHE = 5
 ECB_OPT_VERIFY_KEYS = 6
 ECB_OPT_CHUNK_LEN = 7
 ECB_OPT_PAGEABLE_RESULTS = 8
-ECB_OPT_TWO_PHASE = 9
-ECB_OPT_STRIP_KERNEL = 10
+ECB_OPT_WINDOW_KERNEL = 9
 
 ECB_ERR_EMPTY = -5
 
@@ -189,7 +188,7 @@ class EcBuilder(object):
                 "pair_slots": ECB_OPT_PAIR_SLOTS, "grid_ctas": ECB_OPT_GRID_CTAS,
                 "hot_cache": ECB_OPT_HOT_CACHE, "verify_keys": ECB_OPT_VERIFY_KEYS,
                 "chunk_len": ECB_OPT_CHUNK_LEN, "pageable_results": ECB_OPT_PAGEABLE_RESULTS,
-                "two_phase": ECB_OPT_TWO_PHASE, "strip_kernel": ECB_OPT_STRIP_KERNEL}
+                "window_kernel": ECB_OPT_WINDOW_KERNEL}
 
     def _check(self, rc):
         if rc != 0:

@@ -11,7 +11,7 @@
 #include "ecb_common.cuh"
 #include "ecb_scan.cuh"
 #include "ecb_group.cuh"
-#include "ecb_strip.cuh"
+#include "ecb_tile.cuh"
 #include "ecb_harvest.cuh"
 #include "ecb_finalize.cuh"
 #include "ecb_sort.cuh"
@@ -41,11 +41,7 @@ struct ecb_ctx {
   int use_cache = 1;
   int verify_keys = 0;
   int pageable_results = 0;
-  int two_phase = 0;
-  int strip_kernel = 0;   // ECB_OPT_STRIP_KERNEL (initial value from the environment variable ECB_STRIP_KERNEL)
-  int strip_warps = 32;   // warps per CTA of the strip kernel: 32, or 24 (environment variable ECB_STRIP_WARPS)
-  int strip_dense = 0;    // 24 warps + closed reads parked and looked up 32 at a time (value 124)
-  DevBuf plog, pcur;
+  int window_kernel = 0;  // ECB_OPT_WINDOW_KERNEL: the single-sample path runs the window kernel instead of the tile kernel
   // EC table
   DevBuf table;
   u32 table_slots = 0;
@@ -320,8 +316,8 @@ int allow_group_smem(ecb_ctx* c, K kernel) {
 int group_prepare_launch(ecb_ctx* c) {
   if (!c->group_attr_set) {
     CKR(allow_group_smem(c, ecb_group_insert_kernel<true>));
-    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true>));
     CKR(allow_group_smem(c, ecb_group_insert_kernel<false>));
+    CK(cudaFuncSetAttribute(ecb_group_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ECB_T_SMEM));
     c->group_attr_set = true;
   }
   return ECB_OK;
@@ -329,13 +325,14 @@ int group_prepare_launch(ecb_ctx* c) {
 
 // Launch geometry of the grouping kernel: one persistent CTA per SM, every warp takes chunks of
 // `chunk_len` alignments from a shared counter.
-void group_geometry(ecb_ctx* c, int64_t n, int* grid, int* chunk_len) {
-  const int64_t warps = (int64_t)c->sm_count * ECB_GWARPS;
+void group_geometry(ecb_ctx* c, int64_t n, bool tile, int* grid, int* chunk_len) {
+  const int wpc = tile ? ECB_T_WARPS : ECB_GWARPS;
+  const int64_t warps = (int64_t)c->sm_count * wpc;
   int64_t cl = c->opt_chunk_len > 0 ? c->opt_chunk_len : std::min<int64_t>(4096, std::max<int64_t>(256, n / (warps * 4)));
   cl = (cl + 31) / 32 * 32;
-  if (c->strip_kernel) cl = (cl + ECB_TILE - 1) / ECB_TILE * ECB_TILE;   // whole tiles of 32 strips
+  if (tile) cl = std::min<int64_t>(ECB_T_MAX_CHUNK, (cl + ECB_T_BLOCK - 1) / ECB_T_BLOCK * ECB_T_BLOCK);   // whole blocks
   const int64_t chunks = (n + cl - 1) / cl;
-  int64_t g = c->opt_grid > 0 ? c->opt_grid : std::min<int64_t>(c->sm_count, (chunks + ECB_GWARPS - 1) / ECB_GWARPS);
+  int64_t g = c->opt_grid > 0 ? c->opt_grid : std::min<int64_t>(c->sm_count, (chunks + wpc - 1) / wpc);
   *grid = (int)std::max<int64_t>(1, g);
   *chunk_len = (int)cl;
 }
@@ -581,11 +578,7 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   c->n_haps = n_haps;
   c->with_cells = with_cells ? 1 : 0;
   c->hint = std::max<int64_t>(alignments_hint, 0);
-  if (const char* e = getenv("ECB_STRIP_KERNEL")) c->strip_kernel = atoi(e) ? 1 : 0;
-  if (const char* e = getenv("ECB_STRIP_WARPS")) {
-    c->strip_warps = (atoi(e) == 24 || atoi(e) == 124) ? 24 : 32;
-    c->strip_dense = atoi(e) == 124;
-  }
+  if (const char* e = getenv("ECB_WINDOW_KERNEL")) c->window_kernel = atoi(e) ? 1 : 0;
   auto bail = [&](int code) {
     g_create_error = c->err;
     ecb_destroy(c);
@@ -627,12 +620,7 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
-    case ECB_OPT_TWO_PHASE: c->two_phase = (value == 2 || value == 3) ? (int)value : (value ? 1 : 0); break;
-    case ECB_OPT_STRIP_KERNEL:
-      c->strip_kernel = value ? 1 : 0;
-      if (value == 24 || value == 32) { c->strip_warps = (int)value; c->strip_dense = 0; }
-      if (value == 124) { c->strip_warps = 24; c->strip_dense = 1; }
-      break;
+    case ECB_OPT_WINDOW_KERNEL: c->window_kernel = value ? 1 : 0; break;
     case ECB_OPT_PAGEABLE_RESULTS:
       if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
       c->pageable_results = value ? 1 : 0; break;
@@ -701,93 +689,18 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
 
   const u32 e_before = c->n_ec;
   CKR(group_prepare_launch(c));
+  const bool tile = !c->with_cells && !c->window_kernel;
   int grid = 1, chunk_len = 32;
-  group_geometry(c, n, &grid, &chunk_len);
+  group_geometry(c, n, tile, &grid, &chunk_len);
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
-  const bool flat_log = (c->two_phase == 2 || c->two_phase == 3) && !c->strip_kernel && !c->with_cells;
-  const bool two_phase = c->two_phase == 1 && !c->strip_kernel && !c->with_cells && c->table_slots >= 1024u * ECB_LOG_PARTS;
-  if (two_phase) {
-    // logs sized from the push: misses are at most one per read, reads at most one per alignment
-    const u32 cap = (u32)std::min<int64_t>(0x7FFFFFFF / ECB_LOG_PARTS, n / ECB_LOG_PARTS * 3 / 4 + 4096);
-    CKR(ensure(c, c->plog, (size_t)cap * ECB_LOG_PARTS * sizeof(EcbLogEntry)));
-    CKR(ensure(c, c->pcur, ECB_LOG_PARTS * 4));
-    CK(cudaMemsetAsync(c->pcur.p, 0, ECB_LOG_PARTS * 4, c->stream));
-    P.plog = (EcbLogEntry*)c->plog.p;
-    P.pcur = (u32*)c->pcur.p;
-    P.plog_cap = cap;
-    u32 bits = 0;
-    while ((1u << bits) < c->table_slots) ++bits;
-    P.plog_shift = bits - ECB_LOG_PARTS_LOG2;   // partition = the top bits of the slot index
-    P.use_log = 1;
-    CKR(ensure(c, c->spill, ((size_t)grid * ECB_CACHE + 1024) * sizeof(EcbSpill)));
-    P.spill = (EcbSpill*)c->spill.p;
-  }
-  if (flat_log) {
-    // one flat log: three quarters of an entry per alignment (misses <= reads <= alignments; what does not
-    // fit is inserted directly) plus one block per warp for the padding
-    const int64_t cap64 = n / 4 * 3 + (int64_t)grid * ECB_GWARPS * ECB_LOG_BLOCK + ECB_LOG_BLOCK;
-    const u32 cap = (u32)std::min<int64_t>(0x7FFFFF00, cap64);
-    CKR(ensure(c, c->plog, (size_t)cap * sizeof(EcbLogEntry)));
-    CKR(ensure(c, c->pcur, ECB_LOG_PARTS * 4));
-    CK(cudaMemsetAsync(c->pcur.p, 0, 4, c->stream));
-    P.plog = (EcbLogEntry*)c->plog.p;
-    P.pcur = (u32*)c->pcur.p;
-    P.plog_cap = cap;
-    P.plog_shift = 0;
-    P.use_log = 1;
-  }
-  // experimental variants: opt-in shared memory of the one that is about to run (outside the timed interval)
-  if (c->strip_kernel && c->strip_dense) {
-    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 24, true>) : allow_group_smem(c, ecb_group_strip_kernel<false, 24, true>));
-  } else if (c->strip_kernel && c->strip_warps == 24) {
-    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 24>) : allow_group_smem(c, ecb_group_strip_kernel<false, 24>));
-  } else if (c->strip_kernel) {
-    CKR(c->with_cells ? allow_group_smem(c, ecb_group_strip_kernel<true, 32>) : allow_group_smem(c, ecb_group_strip_kernel<false, 32>));
-  } else if (flat_log && c->two_phase == 3) {
-    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true, true, true>));
-  } else if (flat_log) {
-    CKR(allow_group_smem(c, ecb_group_insert_kernel<false, true, true>));
-  }
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (c->strip_kernel && c->strip_dense) {
-    if (c->with_cells) {
-      ecb_group_strip_kernel<true, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    } else {
-      ecb_group_strip_kernel<false, 24, true><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    }
-  } else if (c->strip_kernel && c->strip_warps == 24) {
-    if (c->with_cells) {
-      ecb_group_strip_kernel<true, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    } else {
-      ecb_group_strip_kernel<false, 24><<<grid, 32 * 24, sizeof(GroupSmem), c->stream>>>(P);
-    }
-  } else if (c->strip_kernel) {
-    if (c->with_cells) {
-      ecb_group_strip_kernel<true, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
-    } else {
-      ecb_group_strip_kernel<false, 32><<<grid, 32 * 32, sizeof(GroupSmem), c->stream>>>(P);
-    }
-  }
+  if (tile) ecb_group_tile_kernel<<<grid, ECB_T_THREADS, ECB_T_SMEM, c->stream>>>(P);
   else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
-  else if (flat_log && c->two_phase == 3) {
-    ecb_group_insert_kernel<false, true, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
-  } else if (flat_log) {
-    ecb_group_insert_kernel<false, true, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
-  }
-  else if (two_phase) ecb_group_insert_kernel<false, true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
-  if (two_phase) {
-    ecb_log_insert_kernel<<<c->sm_count, 1024, 0, c->stream>>>(P);
-    LAUNCH_CHECK("log_insert");
-  }
-  if (flat_log) {
-    ecb_log_insert_flat_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P);
-    LAUNCH_CHECK("log_insert_flat");
-  }
   CK(cudaEventRecord(c->ev[2], c->stream));
   CKR(sync_counters(c));
   CKR(check_device_error(c));
@@ -821,6 +734,11 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   c->n_ec = c->h_ctr->n_ec;
   c->n_triples = c->h_ctr->n_triples;
   CK(cudaEventRecord(c->ev[3], c->stream));
+  if (tile && c->n_ec > e_before) {   // the tile kernel records where a representative read starts, not how long it is
+    ecb_rep_len_kernel<<<grid_for(c->n_ec - e_before, 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        rg, (int)n, (const u32*)c->ec_rep.p, (u32*)c->ec_len.p, e_before, c->n_ec);
+    LAUNCH_CHECK("rep_len");
+  }
   CKR(harvest_new_rows(c, rg, tg, hp, n, e_before, c->n_ec));
   CK(cudaEventRecord(c->ev[4], c->stream));
   if (c->verify_keys) {
@@ -1506,7 +1424,7 @@ int ecb_destroy(ecb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   DevBuf* bufs[] = {&c->table, &c->ec_slot, &c->ec_rep, &c->ec_len, &c->spill, &c->row_len, &c->row_off, &c->arena, &c->long_list, &c->mid_list, &c->big_list, &c->count_of,
-                    &c->ttable, &c->plog, &c->pcur, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell,
+                    &c->ttable, &c->st_rg, &c->st_tg, &c->st_hp, &c->st_cell, &c->st2_rg, &c->st2_tg, &c->st2_hp, &c->st2_cell,
                     &c->overflow_bits,
                     &c->scan_partials, &c->bitmap, &c->word_rank, &c->first_rel, &c->ecid_of, &c->ec_keep,
                     &c->r_a_indptr, &c->r_a_indices, &c->r_a_data, &c->r_n_indptr, &c->r_n_indices,

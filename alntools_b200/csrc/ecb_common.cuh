@@ -83,18 +83,9 @@ struct Mix4 {
   u32 a, b, c, d;
 };
 // multiply-fold: low ^ high half of a 32x32 -> 64 bit product (one IMAD.WIDE + one LOP3)
-#ifndef ECB_MUM_PTX
-#define ECB_MUM_PTX 0   // 1: spell the 32x32->64 multiply out in PTX (experiment: the compiler's version carries
-#endif                  // dead add-with-zero instructions in the grouping kernel)
 __host__ __device__ __forceinline__ u32 mum32(u32 x, u32 k) {
-#if ECB_MUM_PTX && defined(__CUDA_ARCH__)
-  u32 lo, hi;
-  asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(k));
-  return lo ^ hi;
-#else
   const u64 p = (u64)x * k;
   return (u32)p ^ (u32)(p >> 32);
-#endif
 }
 __host__ __device__ __forceinline__ Mix4 ecb_mix(u32 code) {
   Mix4 m;
@@ -109,18 +100,11 @@ __host__ __device__ __forceinline__ void mix_add(Mix4& x, const Mix4& y) {
 }
 __host__ __device__ __forceinline__ Mix4 mix_zero() { return Mix4{0u, 0u, 0u, 0u}; }
 
-#ifndef ECB_KEY127
-#define ECB_KEY127 0   // 1 (experiment, to be measured): the top bit of every key is cleared, so the all-ones empty
-#endif                 // marker cannot occur and the per-read test for it (6 instructions per window) goes away
 __host__ __device__ __forceinline__ Key128 mix_to_key(const Mix4& m) {
   Key128 k;
   k.lo = ((u64)m.b << 32) | m.a;
-#if ECB_KEY127
-  k.hi = ((u64)(m.d & 0x7FFFFFFFu) << 32) | m.c;
-#else
   k.hi = ((u64)m.d << 32) | m.c;
   if (key_empty(k)) k.lo = 0;  // all-ones is the empty marker
-#endif
   return k;
 }
 // Slot hash over all 128 key bits (EC keys are already uniform; (file, EC, cell) keys are not).

@@ -54,15 +54,6 @@ struct EcbSpill {
   u32 count, first, rep, len;
 };
 
-// One miss of the hot-EC cache (count 1, first == rep) or one flushed cache entry, 32 bytes.
-struct __align__(32) EcbLogEntry {
-  u64 lo, hi;
-  u32 first, count, rep, len;
-};
-#define ECB_LOG_PARTS 1024  // many partitions: the cursor atomics of a launch spread over that many addresses
-#define ECB_LOG_PARTS_LOG2 10
-#define ECB_LOG_BLOCK 256   // ECB_OPT_TWO_PHASE = 2: entries a warp takes from the flat log at a time (4 batches)
-
 struct GroupParams {
   const int32_t* rg;
   const int32_t* tg;
@@ -83,12 +74,6 @@ struct GroupParams {
   EcbCounters* ctr;
   u32* overflow_bits;  // [ceil(n/32)] reads that must be replayed after a table growth
   EcbSpill* spill;     // [grid * ECB_CACHE] cache entries that must be replayed after a table growth
-  // two-phase insert (ECB_OPT_TWO_PHASE): misses go to per-partition logs, a second kernel inserts them
-  EcbLogEntry* plog;   // [ECB_LOG_PARTS * plog_cap]
-  u32* pcur;           // [ECB_LOG_PARTS] entries appended so far (beyond plog_cap: inserted directly instead)
-  u32 plog_cap;
-  u32 plog_shift;      // partition = (slot hash & mask) >> plog_shift: a contiguous range of table slots
-  int use_log;
   EcbEntry* ttable;    // (file, EC slot, cell) table, with cells only
   u32 tmask;
   u32 push_id;
@@ -122,50 +107,6 @@ __device__ __forceinline__ u32 table_probe_from(EcbEntry* table, u32 mask, const
   return ECB_NONE;
 }
 
-#ifndef ECB_SMEM_BASE_ASM
-#define ECB_SMEM_BASE_ASM 0   // 1 (experiment, to be measured): shared-window base of the grouping kernel from one opaque asm
-#endif
-#ifndef ECB_WARP_PROBE
-#define ECB_WARP_PROBE 0   // 1 (experiment, to be measured): probe continuation of the batched insert as a warp-uniform loop
-#endif
-
-// Warp-uniform form of table_probe_from for code that the whole warp executes together: every lane stays in
-// the loop until the last one is done (lanes without work idle), so the loop has ONE exit, decided by a
-// vote.  With the per-lane exits of table_probe_from inlined into the window loop, ptxas can no longer
-// prove that loop convergent and guards every shuffle / vote in it with a BRA.DIV check: 25 of them, 28
-// warp instructions per window (10 %).  With this form the kernel has none (3040 -> 2880 instructions).
-__device__ __forceinline__ u32 table_probe_warp(EcbEntry* table, u32 mask, const Key128& key, u32 slot,
-                                                int max_probe, bool need, bool& claimed, u64& first_seen) {
-  u32 result = ECB_NONE;
-  bool active = need;
-  for (int p = 0; p < max_probe; ++p) {
-    if (!__any_sync(ECB_FULL, active)) break;
-    if (active) {
-      EcbEntry* e = table + slot;
-      Key128 k;
-      u64 first;
-      u32 cm1, aux;
-      load_entry_cg(e, k, first, cm1, aux);
-      if (key_eq(k, key)) {
-        first_seen = first;
-        result = slot;
-        active = false;
-      } else if (key_empty(k)) {
-        Key128 old = atomic_cas128(e, Key128{~0ull, ~0ull}, key);
-        if (key_empty(old)) {
-          claimed = true;
-          result = slot;
-          active = false;
-        } else if (key_eq(old, key)) {
-          result = slot;
-          active = false;
-        }
-      }
-      slot = (slot + 1) & mask;
-    }
-  }
-  return result;
-}
 
 // Find `key` or claim an empty slot for it.  EC selects the EC table's slot hash.
 template <bool EC = false>
@@ -275,17 +216,6 @@ __device__ __forceinline__ void global_upsert2(const GroupParams& P, const Key12
   if (casB) fB = ~0ull;
   slotA = (eqA || clA || (casA && key_eq(kA, keyA))) ? hA : ECB_NONE;
   slotB = (eqB || clB || (casB && key_eq(kB, keyB))) ? hB : ECB_NONE;
-#if ECB_WARP_PROBE
-  {  // the home slot holds another key: walk on - the whole warp together (see table_probe_warp)
-    const bool moreA = hasA && slotA == ECB_NONE, moreB = hasB && slotB == ECB_NONE;
-    if (moreA) fA = ~0ull;
-    if (moreB) fB = ~0ull;
-    const u32 wa = table_probe_warp(P.table, P.mask, keyA, (hA + 1) & P.mask, ECB_MAX_PROBE - 1, moreA, clA, fA);
-    const u32 wb = table_probe_warp(P.table, P.mask, keyB, (hB + 1) & P.mask, ECB_MAX_PROBE - 1, moreB, clB, fB);
-    if (moreA) slotA = wa;
-    if (moreB) slotB = wb;
-  }
-#else
   if (hasA && slotA == ECB_NONE) {  // the home slot holds another key: walk on
     fA = ~0ull;
     slotA = table_probe_from(P.table, P.mask, keyA, (hA + 1) & P.mask, ECB_MAX_PROBE - 1, clA, fA);
@@ -294,7 +224,6 @@ __device__ __forceinline__ void global_upsert2(const GroupParams& P, const Key12
     fB = ~0ull;
     slotB = table_probe_from(P.table, P.mask, keyB, (hB + 1) & P.mask, ECB_MAX_PROBE - 1, clB, fB);
   }
-#endif
   if (slotA != ECB_NONE) {
     EcbEntry* e = P.table + slotA;
     atomicAdd(&e->countm1, 1u);
@@ -390,13 +319,9 @@ __device__ __forceinline__ Key128 key_of(const uint4& k) {
   return Key128{((u64)k.y << 32) | k.x, ((u64)k.w << 32) | k.z};
 }
 __host__ __device__ __forceinline__ uint4 key_words(const Mix4& m) {
-#if ECB_KEY127
-  return make_uint4(m.a, m.b, m.c, m.d & 0x7FFFFFFFu);   // as mix_to_key
-#else
   uint4 k = make_uint4(m.a, m.b, m.c, m.d);
   if ((k.x & k.y & k.z & k.w) == 0xFFFFFFFFu) k.x = k.y = 0u;  // all-ones is the empty marker (as mix_to_key)
   return k;
-#endif
 }
 // Column loads: read once (twice by overlapping windows, which L1 absorbs), so they are marked
 // evict-first in L2 and leave the cache to the EC table.
@@ -453,104 +378,6 @@ __device__ __forceinline__ void insert_misses(const GroupParams& P, u32 qk, u32 
   }
 }
 
-// Two-phase insert, phase A: the misses are appended to the log of their table partition.  The two
-// appends of a lane are in flight together; the only round trip is the cursor atomic.  A full log
-// (never in practice: the logs are sized from the push) falls back to the direct insert.
-__device__ __forceinline__ bool log_append(const GroupParams& P, const Key128& key, u32 first, u32 count, u32 rep,
-                                           u32 len, u32 pos, u32 part) {
-  if (pos >= P.plog_cap) return false;
-  uint4* dst = reinterpret_cast<uint4*>(P.plog + (size_t)part * P.plog_cap + pos);
-  dst[0] = make_uint4((u32)key.lo, (u32)(key.lo >> 32), (u32)key.hi, (u32)(key.hi >> 32));
-  dst[1] = make_uint4(first, count, rep, len);
-  return true;
-}
-
-template <bool WITH_CELLS>
-__device__ __forceinline__ void log_misses(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb, bool hasB) {
-  uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
-  uint2 rA = make_uint2(0u, 0u), rB = rA;
-  if (hasA) {
-    kA = lds128(qk + qa * 16u);
-    rA = lds64(qr + qa * 8u);
-  }
-  if (hasB) {
-    kB = lds128(qk + qb * 16u);
-    rB = lds64(qr + qb * 8u);
-  }
-  const Key128 keyA = key_of(kA), keyB = key_of(kB);
-  const u32 pA = (ec_slot_hash(keyA) & P.mask) >> P.plog_shift, pB = (ec_slot_hash(keyB) & P.mask) >> P.plog_shift;
-  u32 posA = 0, posB = 0;
-  if (hasA) posA = atomicAdd(&P.pcur[pA], 1u);
-  if (hasB) posB = atomicAdd(&P.pcur[pB], 1u);
-  const bool okA = hasA && log_append(P, keyA, rA.x, 1u, rA.x, rA.y, posA, pA);
-  const bool okB = hasB && log_append(P, keyB, rB.x, 1u, rB.x, rB.y, posB, pB);
-  const bool redoA = hasA && !okA, redoB = hasB && !okB;
-#if ECB_WARP_PROBE
-  if (__any_sync(ECB_FULL, redoA || redoB)) {   // global_upsert2 is a whole-warp routine in this build
-#else
-  if (redoA || redoB) {
-#endif
-    u32 slotA, slotB;
-    global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
-    if (redoA && slotA == ECB_NONE) {
-      atomicOr(&P.overflow_bits[rA.x >> 5], 1u << (rA.x & 31));
-      atomicAdd(&P.ctr->n_overflow, 1u);
-    }
-    if (redoB && slotB == ECB_NONE) {
-      atomicOr(&P.overflow_bits[rB.x >> 5], 1u << (rB.x & 31));
-      atomicAdd(&P.ctr->n_overflow, 1u);
-    }
-  }
-}
-
-// Two-phase insert, second form (ECB_OPT_TWO_PHASE = 2), phase A: ONE flat log; a warp takes blocks of
-// ECB_LOG_BLOCK entries from it (one atomic with return value per 256 misses instead of one per miss) and
-// fills them with whole batches of 64 - two coalesced 1 KB stores, no round trip.  Entries that are absent
-// in the last, partial batch of a warp are written as empty entries (count 0) so that a block has no holes;
-// lb / lu = base and fill of the warp's current block.
-__device__ __forceinline__ void log_misses_priv(const GroupParams& P, u32 qk, u32 qr, u32 qa, bool hasA, u32 qb,
-                                                bool hasB, u32& lb, u32& lu, const bool pair = true) {
-  const int lane = threadIdx.x & 31;
-  uint4 kA = make_uint4(0u, 0u, 0u, 0u), kB = kA;
-  uint2 rA = make_uint2(0u, 0u), rB = rA;
-  if (hasA) {
-    kA = lds128(qk + qa * 16u);
-    rA = lds64(qr + qa * 8u);
-  }
-  if (hasB) {
-    kB = lds128(qk + qb * 16u);
-    rB = lds64(qr + qb * 8u);
-  }
-  if (lu >= ECB_LOG_BLOCK) {   // warp-uniform: the block is full (or there is none yet)
-    u32 b = 0;
-    if (lane == 0) b = atomicAdd(&P.pcur[0], (u32)ECB_LOG_BLOCK);
-    lb = __shfl_sync(ECB_FULL, b, 0);
-    lu = 0u;
-  }
-  const Key128 keyA = key_of(kA), keyB = key_of(kB);
-  // pair = false: a batch of 32 (entry qa of every lane only)
-  const bool okA = log_append(P, keyA, rA.x, hasA ? 1u : 0u, rA.x, rA.y, lb + lu + (u32)lane, 0u);
-  const bool okB = pair ? log_append(P, keyB, rB.x, hasB ? 1u : 0u, rB.x, rB.y, lb + lu + 32u + (u32)lane, 0u) : true;
-  lu += pair ? 64u : 32u;
-  const bool redoA = hasA && !okA, redoB = hasB && !okB;   // the log is full: insert directly
-#if ECB_WARP_PROBE
-  if (__any_sync(ECB_FULL, redoA || redoB)) {   // global_upsert2 is a whole-warp routine in this build
-#else
-  if (redoA || redoB) {
-#endif
-    u32 slotA, slotB;
-    global_upsert2(P, keyA, rA.x, rA.y, redoA, keyB, rB.x, rB.y, redoB, slotA, slotB);
-    if (redoA && slotA == ECB_NONE) {
-      atomicOr(&P.overflow_bits[rA.x >> 5], 1u << (rA.x & 31));
-      atomicAdd(&P.ctr->n_overflow, 1u);
-    }
-    if (redoB && slotB == ECB_NONE) {
-      atomicOr(&P.overflow_bits[rB.x >> 5], 1u << (rB.x & 31));
-      atomicAdd(&P.ctr->n_overflow, 1u);
-    }
-  }
-}
-
 struct LongRead {
   uint4 key;
   int len;
@@ -603,71 +430,7 @@ __device__ __noinline__ LongRead ecb_long_read(const int32_t* __restrict__ rg, c
   return r;
 }
 
-// DENSEQ: cache look-up of up to 32 parked reads (entry idx of every lane that `has` one), misses to the
-// lower end of the warp's queue and from there to the flat log, 32 at a time.  The whole warp calls it.
-struct DenseAddr {
-  u32 qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen;
-};
-__device__ __forceinline__ void dense_commit(const GroupParams& P, const DenseAddr& A, bool use_cache, bool has, u32 idx,
-                                             u32 lt_mask, int lane, u32& qn, u32& lb, u32& lu) {
-  const u32 qk = A.qk, qr = A.qr, a_key = A.a_key, a_lock = A.a_lock, a_cnt = A.a_cnt, a_first = A.a_first,
-            a_rep = A.a_rep, a_seen = A.a_seen;
-  uint4 k2 = make_uint4(0u, 0u, 0u, 0u);
-  uint2 r2 = make_uint2(0u, 0u);
-  if (has) {
-    k2 = lds128(qk + idx * 16u);
-    r2 = lds64(qr + idx * 8u);
-  }
-  __syncwarp();
-  bool miss2 = has;
-  if (use_cache && has) {
-    const u32 cidx = (k2.y >> 7) & (ECB_CACHE - 1);
-    const uint4 ck = lds128(a_key + cidx * 16u);
-    const u32 cf = lds32(a_first + cidx * 4u);
-    bool hit = ck.x == k2.x && ck.y == k2.y && ck.z == k2.z && ck.w == k2.w;
-    if (!hit && (ck.x & ck.y & ck.z & ck.w) == 0xFFFFFFFFu) {
-#if ECB_ADMIT_SECOND
-      const u32 sbit = 1u << (k2.z & 31u);
-      const bool again = (atoms_or(a_seen + ((k2.z >> 5) & (ECB_SEEN_WORDS - 1)) * 4u, sbit) & sbit) != 0u;
-#else
-      const bool again = true;
-#endif
-      if (again && atoms_cas(a_lock + cidx * 4u, 0u, 1u) == 0u) {
-        sts64(a_rep + cidx * 8u, r2.x, r2.y);
-        sts128(a_key + cidx * 16u, k2);
-        hit = true;
-      }
-    }
-    if (hit) {
-      reds_add(a_cnt + cidx * 4u, 1u);
-      if (r2.x < cf) reds_min(a_first + cidx * 4u, r2.x);
-      miss2 = false;
-    }
-  }
-  const u32 mm2 = __ballot_sync(ECB_FULL, miss2);
-  if (mm2) {
-    if (miss2) {
-      const u32 q = qn + __popc(mm2 & lt_mask);
-      sts128(qk + q * 16u, k2);
-      sts64(qr + q * 8u, r2.x, r2.y);
-    }
-    qn += __popc(mm2);
-    __syncwarp();
-    if (qn >= 32u) {
-      qn -= 32u;
-      log_misses_priv(P, qk, qr, qn + lane, true, 0u, false, lb, lu, false);
-      __syncwarp();
-    }
-  }
-}
-
-// LOGGED: the experimental two-phase insert (ECB_OPT_TWO_PHASE); a template parameter so that the
-// default kernel carries none of it.
-// PRIVLOG (with LOGGED): the flat log with per-warp blocks instead of the per-partition logs.
-// DENSEQ (with PRIVLOG, ECB_OPT_TWO_PHASE = 3): closed reads are parked in the upper end of the warp's queue
-// and looked up in the cache 32 at a time with every lane busy (in the plain form about 14 of 32 lanes are,
-// once per window); misses grow from the lower end and go to the log in batches of 32.
-template <bool WITH_CELLS, bool LOGGED = false, bool PRIVLOG = false, bool DENSEQ = false>
+template <bool WITH_CELLS>
 __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const GroupParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GroupSmem& S = *reinterpret_cast<GroupSmem*>(smem_raw);
@@ -697,26 +460,12 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
   __syncthreads();
 
-#if ECB_SMEM_BASE_ASM
-  // one opaque base: the compiler keeps it (in a uniform register) instead of re-deriving the shared window
-  // from SR_CgaCtaId in every window (S2R + MOV + LEA + 2 adds in front of the cache look-up)
-  u32 sbase;
-  asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(sbase) : "l"(smem_raw));
-  const u32 qk = sbase + (u32)offsetof(GroupSmem, q_key) + (u32)warp * ECB_MQ * 16u;   // this warp's miss queue
-  const u32 qr = sbase + (u32)offsetof(GroupSmem, q_rep) + (u32)warp * ECB_MQ * 8u;
-  const u32 a_key = sbase + (u32)offsetof(GroupSmem, c_key), a_lock = sbase + (u32)offsetof(GroupSmem, c_lock);
-  const u32 a_cnt = sbase + (u32)offsetof(GroupSmem, c_cnt), a_first = sbase + (u32)offsetof(GroupSmem, c_first);
-  const u32 a_rep = sbase + (u32)offsetof(GroupSmem, c_rep), a_seen = sbase + (u32)offsetof(GroupSmem, seen);
-#else
   const u32 qk = smem_u32(S.q_key[warp]);  // this warp's miss queue (shared-window addresses)
   const u32 qr = smem_u32(S.q_rep[warp]);
   const u32 a_key = smem_u32(S.c_key), a_lock = smem_u32(S.c_lock), a_cnt = smem_u32(S.c_cnt);
   const u32 a_first = smem_u32(S.c_first), a_rep = smem_u32(S.c_rep), a_seen = smem_u32(S.seen);
-#endif
   u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
   u32 reads_counted = 0;  // per lane
-  u32 lb = 0u, lu = ECB_LOG_BLOCK;   // PRIVLOG: base and fill of this warp's block of the flat log (none yet)
-  [[maybe_unused]] u32 cn = 0u;      // DENSEQ: closed reads parked at the upper end of the queue (warp-uniform)
 
   for (;;) {
     // ---- next chunk of the stream (dynamic: whichever warp is free takes it) -------------------------
@@ -859,26 +608,6 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       }
       w = wnext;
 
-      if constexpr (DENSEQ) {
-        // ---- closed reads are parked; 32 of them at a time go through the cache ----------------------
-        const u32 cm = __ballot_sync(ECB_FULL, ins);
-        if (cm) {
-          if (lane == 0) reads_counted += __popc(cm);   // the count of the vote is there anyway
-          if (ins) {
-            const u32 j = (ECB_MQ - 1u) - (cn + __popc(cm & lt_mask));
-            sts128(qk + j * 16u, key);
-            sts64(qr + j * 8u, s, len);
-          }
-          cn += __popc(cm);
-          __syncwarp();
-          if (cn >= 32u) {
-            cn -= 32u;
-            dense_commit(P, DenseAddr{qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen}, use_cache, true,
-                         (ECB_MQ - 1u) - (cn + (u32)lane), lt_mask, lane, qn, lb, lu);
-          }
-        }
-        continue;
-      }
       // ---- closed reads: hot-EC cache first --------------------------------------------------------
       bool miss = ins;
       if (ins) ++reads_counted;
@@ -917,15 +646,13 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
           const u32 q = qn + __popc(mm & lt_mask);
           sts128(qk + q * 16u, key);
           sts64(qr + q * 8u, s, len);
-          if (!LOGGED) prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
+          prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
         }
         qn += __popc(mm);
         __syncwarp();
         if (qn >= 64u) {
           qn -= 64u;
-          if (PRIVLOG) log_misses_priv(P, qk, qr, qn + lane, true, qn + 32 + lane, true, lb, lu);
-          else if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
-          else insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
+          insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           __syncwarp();
         }
       }
@@ -933,21 +660,8 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   }
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
-  if constexpr (DENSEQ) {   // the parked reads that are left, then the misses that are left, in batches of 32
-    if (cn) dense_commit(P, DenseAddr{qk, qr, a_key, a_lock, a_cnt, a_first, a_rep, a_seen}, use_cache, (u32)lane < cn,
-                         (ECB_MQ - 1u) - (u32)lane, lt_mask, lane, qn, lb, lu);
-    if (qn) log_misses_priv(P, qk, qr, lane, (u32)lane < qn, 0u, false, lb, lu, false);
-    if (qn > 32u) log_misses_priv(P, qk, qr, lane + 32, (u32)lane + 32u < qn, 0u, false, lb, lu, false);
-    qn = 0u;
-  }
   if (qn) {
-    if (PRIVLOG) log_misses_priv(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn, lb, lu);
-    else if (LOGGED) log_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
-    else insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
-  }
-  if (PRIVLOG) {   // the rest of the warp's last block: empty entries
-    for (u32 i = lu + (u32)lane; i < ECB_LOG_BLOCK; i += 32u)
-      log_append(P, Key128{0ull, 0ull}, 0u, 0u, 0u, 0u, lb + i, 0u);
+    insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
   }
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);
@@ -959,10 +673,6 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         const Key128 key = key_of(S.c_key[i]);
         const u32 first = S.c_first[i];
         const uint2 rep = S.c_rep[i];
-        if (LOGGED && !PRIVLOG) {
-          const u32 part = (ec_slot_hash(key) & P.mask) >> P.plog_shift;
-          if (log_append(P, key, first, cnt, rep.x, rep.y, atomicAdd(&P.pcur[part], 1u), part)) continue;
-        }
         const u32 slot = global_upsert(P, key, cnt, first, rep.x, rep.y);
         if (slot == ECB_NONE) {  // table too full: park the entry, the host grows the table and replays it
           const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
@@ -1000,48 +710,6 @@ __device__ inline Key128 ecb_serial_read_key(const int32_t* rg, const int32_t* t
   }
   if (len_out) *len_out = j - s;
   return mix_to_key(sum);
-}
-
-// Two-phase insert, phase B: the logs go into the table, one partition per CTA at a time.  A partition
-// is a contiguous 1/1024 of the slots, so the slices the resident CTAs work on (148 x a few hundred KB)
-// stay in L2: probes, compare-and-swap and counters do not go to HBM.
-__global__ void __launch_bounds__(1024, 1) ecb_log_insert_kernel(const GroupParams P) {
-  for (u32 part = blockIdx.x; part < ECB_LOG_PARTS; part += gridDim.x) {
-    const u32 cnt = min(P.pcur[part], P.plog_cap);
-    const uint4* log = reinterpret_cast<const uint4*>(P.plog + (size_t)part * P.plog_cap);
-    for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const uint4 k = log[2 * (size_t)i], v = log[2 * (size_t)i + 1];
-      const Key128 key = key_of(k);
-      const u32 slot = global_upsert(P, key, v.y, v.x, v.z, v.w);
-      if (slot == ECB_NONE) {
-        if (v.y == 1u && v.x == v.z) {  // one read: flag it for the replay after the table has grown
-          atomicOr(&P.overflow_bits[v.z >> 5], 1u << (v.z & 31));
-          atomicAdd(&P.ctr->n_overflow, 1u);
-        } else {
-          const u32 si = atomicAdd(&P.ctr->n_spill, 1u);
-          P.spill[si] = EcbSpill{key.lo, key.hi, v.y, v.x, v.z, v.w};
-        }
-      }
-    }
-  }
-}
-
-// Two-phase insert, second form, phase B: the flat log goes into the table, one entry per thread, with as
-// many threads resident as the SMs take (the probes are independent chains of round trips; there is
-// nothing else to wait for here).  Empty entries (count 0) pad the blocks.
-__global__ void __launch_bounds__(256) ecb_log_insert_flat_kernel(const GroupParams P) {
-  const u32 cnt = min(P.pcur[0], P.plog_cap);
-  const uint4* log = reinterpret_cast<const uint4*>(P.plog);
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-    const uint4 k = log[2 * (size_t)i], v = log[2 * (size_t)i + 1];
-    if (v.y == 0u) continue;
-    const Key128 key = key_of(k);
-    const u32 slot = global_upsert(P, key, v.y, v.x, v.z, v.w);
-    if (slot == ECB_NONE) {   // one read: flag it for the replay after the table has grown
-      atomicOr(&P.overflow_bits[v.z >> 5], 1u << (v.z & 31));
-      atomicAdd(&P.ctr->n_overflow, 1u);
-    }
-  }
 }
 
 // ECB_OPT_VERIFY_KEYS: prove that no two different reads of this push were merged by the 128-bit key.

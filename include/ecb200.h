@@ -65,17 +65,10 @@ enum ecb_option {
   ECB_OPT_CHUNK_LEN = 7,        /* alignments per work chunk of the grouping kernel (0 = automatic) */
   ECB_OPT_PAGEABLE_RESULTS = 8, /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
                                    cheaper for a context that finalizes once, slower when reused */
-  ECB_OPT_TWO_PHASE = 9,        /* 1: the grouping kernel appends cache misses to per-partition logs and a second
-                                   kernel inserts them partition by partition (table slice resident in L2);
-                                   2: one flat log filled in per-warp blocks of 256 entries (no atomic with a
-                                   return value in the streaming loop), inserted by a second kernel with one
-                                   entry per thread; 3: as 2, with the cache look-ups of the grouping kernel
-                                   batched 32 at a time on full warps.  Experimental, single-sample path only */
-  ECB_OPT_STRIP_KERNEL = 10     /* 1: the strip form of the grouping kernel (a lane walks 8 consecutive alignments
-                                   in registers instead of one alignment per lane; same table protocol, same
-                                   results); 24 or 32 also select that many warps per CTA, 124 = 24 warps with the
-                                   cache look-ups batched 32 at a time.  Initial value:
-                                   environment variables ECB_STRIP_KERNEL (0/1) and ECB_STRIP_WARPS (24/32) */
+  ECB_OPT_WINDOW_KERNEL = 9     /* 1: the single-sample path runs the window form of the grouping kernel (one
+                                   alignment per lane; it always serves the per-cell path) instead of the tile
+                                   form (one read per lane).  Same results; kept as the cross-check of the
+                                   default.  Initial value: environment variable ECB_WINDOW_KERNEL (0/1) */
 };
 
 typedef struct ecb_result {

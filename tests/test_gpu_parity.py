@@ -448,91 +448,20 @@ def test_key_verification_option_finds_no_collision(native):
         _assert_same(got, _oracle(cols))
 
 
-STRIP_READY = os.environ.get("ECB_TEST_STRIP") == "1"
-
-
-@pytest.mark.skipif(not STRIP_READY, reason="strip kernel (experimental, off by default): this test and the whole GPU "
-                    "suite under ECB_STRIP_KERNEL=1 ECB_STRIP_WARPS=124 passed on a B200 (profiles/r1_strip_eval.log); the "
-                    "address-space fix of its out-of-line insert came after the last GPU minute of round 1, so the "
-                    "test stays opt-in (ECB_TEST_STRIP=1) until it has run again")
-@pytest.mark.parametrize("warps", [32, 24, 124])
-def test_strip_kernel_gives_the_same_result(native, warps):
-    """ECB_OPT_STRIP_KERNEL: a lane walks 8 consecutive alignments in registers.  Same matrices as the
-    oracle over short reads, reads around the 8-alignment limit of a lane, long reads, duplicates, sizes
-    around the 256-alignment tile, tiny grids, small tables (growth + replay) and the per-cell path."""
+@pytest.mark.parametrize("case", ["diploid", "heavy", "dups", "tiny"])
+def test_window_kernel_cross_check(native, case):
+    """ECB_OPT_WINDOW_KERNEL: the window form of the grouping kernel (one alignment per lane; it serves the
+    per-cell path) must give the matrices of the default tile form (one read per lane) and of the oracle."""
     from alntools_b200 import synth
-    for n_reads, n_targets, n_haps, mode, dup in ((1, 5, 2, "light", 0.0), (7, 5, 2, "light", 0.5),
-                                                  (1000, 50, 2, "light", 0.05), (200000, 2000, 2, "diploid", 0.02),
-                                                  (30000, 1500, 8, "heavy", 0.01), (4000, 1000, 8, 64, 0.0),
-                                                  (20000, 300, 4, 3, 0.3), (300000, 100000, 2, "diploid", 0.0)):
-        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=n_reads % 89 + 2, mode=mode, dup_rate=dup)
-        want = _oracle(cols)
-        for opts in ({}, {"hot_cache": 0}, {"grid_ctas": 1, "chunk_len": 256}, {"table_slots": 1024}):
-            got, _ = _run(native, cols, n_targets, n_haps, strip_kernel=warps, **opts)
-            _assert_same(got, want)
-    for n_reads in (60, 120, 127, 128, 129, 250, 255, 256, 257, 511, 513, 1100):   # around one and two tiles
-        cols = synth.make_columns(n_reads, 40, 3, seed=n_reads, mode="diploid", dup_rate=0.1)
-        got, _ = _run(native, cols, 40, 3, strip_kernel=warps, grid_ctas=2)
-        _assert_same(got, _oracle(cols))
-    for n in (255, 256, 257, 264, 2048):                                          # one alignment per read
-        rg = np.arange(n, dtype=np.int32)
-        cols = {"read_group": rg, "target_idx": (rg % 7).astype(np.int32), "hap_idx": (rg % 2).astype(np.int32)}
-        got, _ = _run(native, cols, 7, 2, strip_kernel=warps)
-        _assert_same(got, _oracle(cols))
-    cols = synth.make_columns(5000, 200, 2, seed=4, mode="diploid")              # the dropped last read
-    with native.EcBuilder(200, 2, strip_kernel=warps) as b:
-        b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"], drop_last_group=True)
-        got = b.finalize()
-    _assert_same(got, _oracle(cols, drop_last=True))
-
-
-@pytest.mark.skipif(os.environ.get("ECB_TEST_FLATLOG") != "1", reason="ECB_OPT_TWO_PHASE = 2 (flat log, per-warp blocks) was "
-                    "written after the last GPU minute of round 1; first run pending (ECB_TEST_FLATLOG=1)")
-@pytest.mark.parametrize("form", [2, 3])
-def test_flat_log_two_phase_insert_gives_the_same_result(native, form):
-    """ECB_OPT_TWO_PHASE = 2 (3: with the cache look-ups batched on full warps): misses appended to one flat log in per-warp blocks, inserted by a second kernel -
-    same matrices as the direct insert, with and without the cache, with a table that has to grow, with a
-    log too small for the misses (alignments that are all their own read) and across several pushes."""
-    from alntools_b200 import synth
-    for n_reads, n_targets, n_haps, mode, dup, slots in ((200000, 2000, 2, "diploid", 0.02, 1 << 20),
-                                                         (3000000, 100000, 2, "diploid", 0.0, 1 << 20),
-                                                         (30000, 1500, 8, "heavy", 0.01, 1 << 20),
-                                                         (400000, 50000, 2, "light", 0.0, 1 << 21),
-                                                         (50000, 40000, 2, 1, 0.0, 1 << 12)):
-        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=5, mode=mode, dup_rate=dup)
-        want = _oracle(cols)
-        for cache in (1, 0):
-            got, stats = _run(native, cols, n_targets, n_haps, two_phase=form, table_slots=slots, hot_cache=cache)
-            _assert_same(got, want)
-    # more misses than the log holds (every alignment its own read, no cache): the rest is inserted directly
-    cols = synth.make_columns(8000000, 2000000, 1, seed=3, mode=1)
-    got, _ = _run(native, cols, 2000000, 1, two_phase=form, hot_cache=0)
-    _assert_same(got, _oracle(cols))
-    for n_reads in (1, 31, 64, 65, 300, 5000):
-        cols = synth.make_columns(n_reads, 50, 2, seed=n_reads, mode="diploid", dup_rate=0.1)
-        got, _ = _run(native, cols, 50, 2, two_phase=form, grid_ctas=2, chunk_len=64)
-        _assert_same(got, _oracle(cols))
-    cols = synth.make_columns(120000, 3000, 2, seed=8, mode="diploid")
-    rg = cols["read_group"]
-    cut = int(np.flatnonzero(rg[1:] != rg[:-1])[len(rg) // 5] + 1)
-    with native.EcBuilder(3000, 2, two_phase=form) as b:
-        b.push(rg[:cut], cols["target_idx"][:cut], cols["hap_idx"][:cut])
-        b.push(rg[cut:], cols["target_idx"][cut:], cols["hap_idx"][cut:], order_base=cut)
-        got = b.finalize()
-    _assert_same(got, _oracle(cols))
-
-
-def test_two_phase_insert_gives_the_same_result(native):
-    """ECB_OPT_TWO_PHASE: cache misses logged per table partition and inserted by a second kernel -
-    same matrices as the direct insert, also when the table is too small and the logged reads have to
-    be replayed after a growth."""
-    from alntools_b200 import synth
-    for n_reads, n_targets, n_haps, mode, dup, slots in ((200000, 2000, 2, "diploid", 0.02, 1 << 20),
-                                                         (3000000, 100000, 2, "diploid", 0.0, 1 << 20),
-                                                         (30000, 1500, 8, "heavy", 0.01, 1 << 20),
-                                                         (400000, 50000, 2, "light", 0.0, 1 << 21)):
-        cols = synth.make_columns(n_reads, n_targets, n_haps, seed=5, mode=mode, dup_rate=dup)
-        want = _oracle(cols)
-        for cache in (1, 0):
-            got, stats = _run(native, cols, n_targets, n_haps, two_phase=1, table_slots=slots, hot_cache=cache)
-            _assert_same(got, want)
+    if case == "diploid":
+        cols, nt, nh = synth.make_columns(300000, 5000, 2, seed=31, mode="diploid", dup_rate=0.03), 5000, 2
+    elif case == "heavy":
+        cols, nt, nh = synth.make_columns(20000, 3000, 8, seed=32, mode="heavy", dup_rate=0.02), 3000, 8
+    elif case == "dups":
+        cols, nt, nh = synth.make_columns(100000, 50, 3, seed=33, mode="light", dup_rate=0.4), 50, 3
+    else:
+        cols, nt, nh = synth.make_columns(7, 5, 2, seed=34, mode="light"), 5, 2
+    want = _oracle(cols)
+    for window in (0, 1):
+        got, _ = _run(native, cols, nt, nh, window_kernel=window)
+        _assert_same(got, want)
