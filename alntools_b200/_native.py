@@ -20,7 +20,6 @@ ECB_OPT_HOT_CACHE = 5
 ECB_OPT_VERIFY_KEYS = 6
 ECB_OPT_CHUNK_LEN = 7
 ECB_OPT_PAGEABLE_RESULTS = 8
-ECB_OPT_WINDOW_KERNEL = 9
 
 ECB_ERR_EMPTY = -5
 
@@ -187,8 +186,7 @@ class EcBuilder(object):
     _OPTIONS = {"result_on_device": ECB_OPT_RESULT_ON_DEVICE, "table_slots": ECB_OPT_TABLE_SLOTS,
                 "pair_slots": ECB_OPT_PAIR_SLOTS, "grid_ctas": ECB_OPT_GRID_CTAS,
                 "hot_cache": ECB_OPT_HOT_CACHE, "verify_keys": ECB_OPT_VERIFY_KEYS,
-                "chunk_len": ECB_OPT_CHUNK_LEN, "pageable_results": ECB_OPT_PAGEABLE_RESULTS,
-                "window_kernel": ECB_OPT_WINDOW_KERNEL}
+                "chunk_len": ECB_OPT_CHUNK_LEN, "pageable_results": ECB_OPT_PAGEABLE_RESULTS}
 
     def _check(self, rc):
         if rc != 0:

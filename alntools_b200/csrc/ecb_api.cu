@@ -11,7 +11,6 @@
 #include "ecb_common.cuh"
 #include "ecb_scan.cuh"
 #include "ecb_group.cuh"
-#include "ecb_tile.cuh"
 #include "ecb_harvest.cuh"
 #include "ecb_finalize.cuh"
 #include "ecb_sort.cuh"
@@ -41,7 +40,6 @@ struct ecb_ctx {
   int use_cache = 1;
   int verify_keys = 0;
   int pageable_results = 0;
-  int window_kernel = 0;  // ECB_OPT_WINDOW_KERNEL: the single-sample path runs the window kernel instead of the tile kernel
   // EC table
   DevBuf table;
   u32 table_slots = 0;
@@ -317,7 +315,6 @@ int group_prepare_launch(ecb_ctx* c) {
   if (!c->group_attr_set) {
     CKR(allow_group_smem(c, ecb_group_insert_kernel<true>));
     CKR(allow_group_smem(c, ecb_group_insert_kernel<false>));
-    CK(cudaFuncSetAttribute(ecb_group_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ECB_T_SMEM));
     c->group_attr_set = true;
   }
   return ECB_OK;
@@ -325,12 +322,11 @@ int group_prepare_launch(ecb_ctx* c) {
 
 // Launch geometry of the grouping kernel: one persistent CTA per SM, every warp takes chunks of
 // `chunk_len` alignments from a shared counter.
-void group_geometry(ecb_ctx* c, int64_t n, bool tile, int* grid, int* chunk_len) {
-  const int wpc = tile ? ECB_T_WARPS : ECB_GWARPS;
+void group_geometry(ecb_ctx* c, int64_t n, int* grid, int* chunk_len) {
+  const int wpc = ECB_GWARPS;
   const int64_t warps = (int64_t)c->sm_count * wpc;
   int64_t cl = c->opt_chunk_len > 0 ? c->opt_chunk_len : std::min<int64_t>(4096, std::max<int64_t>(256, n / (warps * 4)));
   cl = (cl + 31) / 32 * 32;
-  if (tile) cl = std::min<int64_t>(ECB_T_MAX_CHUNK, (cl + ECB_T_BLOCK - 1) / ECB_T_BLOCK * ECB_T_BLOCK);   // whole blocks
   const int64_t chunks = (n + cl - 1) / cl;
   int64_t g = c->opt_grid > 0 ? c->opt_grid : std::min<int64_t>(c->sm_count, (chunks + wpc - 1) / wpc);
   *grid = (int)std::max<int64_t>(1, g);
@@ -578,7 +574,6 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   c->n_haps = n_haps;
   c->with_cells = with_cells ? 1 : 0;
   c->hint = std::max<int64_t>(alignments_hint, 0);
-  if (const char* e = getenv("ECB_WINDOW_KERNEL")) c->window_kernel = atoi(e) ? 1 : 0;
   auto bail = [&](int code) {
     g_create_error = c->err;
     ecb_destroy(c);
@@ -620,7 +615,6 @@ int ecb_set_option(ecb_ctx* c, int option, int64_t value) {
     case ECB_OPT_HOT_CACHE: c->use_cache = value ? 1 : 0; break;
     case ECB_OPT_VERIFY_KEYS: c->verify_keys = value ? 1 : 0; break;
     case ECB_OPT_CHUNK_LEN: c->opt_chunk_len = value; break;
-    case ECB_OPT_WINDOW_KERNEL: c->window_kernel = value ? 1 : 0; break;
     case ECB_OPT_PAGEABLE_RESULTS:
       if (c->h_res) return fail(c, ECB_ERR_STATE, "result buffers already allocated");
       c->pageable_results = value ? 1 : 0; break;
@@ -689,16 +683,14 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
 
   const u32 e_before = c->n_ec;
   CKR(group_prepare_launch(c));
-  const bool tile = !c->with_cells && !c->window_kernel;
   int grid = 1, chunk_len = 32;
-  group_geometry(c, n, tile, &grid, &chunk_len);
+  group_geometry(c, n, &grid, &chunk_len);
   CKR(ensure(c, c->spill, (size_t)grid * ECB_CACHE * sizeof(EcbSpill)));
   GroupParams P = make_group_params(c, rg, tg, hp, cell, n, order_base, drop_last_group, push_id);
   P.chunk_len = chunk_len;
   CK(cudaMemsetAsync(&c->d_ctr->chunk_next, 0, sizeof(u32), c->stream));
   CK(cudaEventRecord(c->ev[1], c->stream));
-  if (tile) ecb_group_tile_kernel<<<grid, ECB_T_THREADS, ECB_T_SMEM, c->stream>>>(P);
-  else if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
+  if (c->with_cells) ecb_group_insert_kernel<true><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   else ecb_group_insert_kernel<false><<<grid, ECB_GTHREADS, sizeof(GroupSmem), c->stream>>>(P);
   LAUNCH_CHECK("group_insert");
   CK(cudaEventRecord(c->ev[2], c->stream));
@@ -734,11 +726,6 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
   c->n_ec = c->h_ctr->n_ec;
   c->n_triples = c->h_ctr->n_triples;
   CK(cudaEventRecord(c->ev[3], c->stream));
-  if (tile && c->n_ec > e_before) {   // the tile kernel records where a representative read starts, not how long it is
-    ecb_rep_len_kernel<<<grid_for(c->n_ec - e_before, 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        rg, (int)n, (const u32*)c->ec_rep.p, (u32*)c->ec_len.p, e_before, c->n_ec);
-    LAUNCH_CHECK("rep_len");
-  }
   CKR(harvest_new_rows(c, rg, tg, hp, n, e_before, c->n_ec));
   CK(cudaEventRecord(c->ev[4], c->stream));
   if (c->verify_keys) {

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
   const u32 qr = smem_u32(S.q_rep[warp]);
   const u32 a_key = smem_u32(S.c_key), a_lock = smem_u32(S.c_lock), a_cnt = smem_u32(S.c_cnt);
   const u32 a_first = smem_u32(S.c_first), a_rep = smem_u32(S.c_rep), a_seen = smem_u32(S.seen);
-  u32 qn = 0;             // reads parked in this warp's miss queue (warp-uniform)
+  u32 qn = 0, qh = 0;     // reads parked in this warp's miss queue (a ring of ECB_MQ) and index of the oldest (warp-uniform)
   u32 reads_counted = 0;  // per lane
 
   for (;;) {
@@ -643,7 +643,8 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
       const u32 mm = __ballot_sync(ECB_FULL, miss);
       if (mm) {
         if (miss) {
-          const u32 q = qn + __popc(mm & lt_mask);
+          u32 q = qh + qn + __popc(mm & lt_mask);
+          if (q >= ECB_MQ) q -= ECB_MQ;
           sts128(qk + q * 16u, key);
           sts64(qr + q * 8u, s, len);
           prefetch_l2(P.table + (ec_slot_hash(key_of(key)) & P.mask));
@@ -651,8 +652,14 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
         qn += __popc(mm);
         __syncwarp();
         if (qn >= 64u) {
+          // the OLDEST 64 go: the home slots of the newest are still on their way into L2
+          u32 qa = qh + lane, qb = qh + 32 + lane;
+          if (qa >= ECB_MQ) qa -= ECB_MQ;
+          if (qb >= ECB_MQ) qb -= ECB_MQ;
+          insert_misses<WITH_CELLS>(P, qk, qr, qa, true, qb, true);
+          qh += 64u;
+          if (qh >= ECB_MQ) qh -= ECB_MQ;
           qn -= 64u;
-          insert_misses<WITH_CELLS>(P, qk, qr, qn + lane, true, qn + 32 + lane, true);
           __syncwarp();
         }
       }
@@ -661,7 +668,10 @@ __global__ void __launch_bounds__(ECB_GTHREADS, 1) ecb_group_insert_kernel(const
 
   // ---- leftovers of the miss queue, then the cache goes into the HBM table ---------------------------
   if (qn) {
-    insert_misses<WITH_CELLS>(P, qk, qr, lane, (u32)lane < qn, lane + 32, (u32)lane + 32u < qn);
+    u32 qa = qh + lane, qb = qh + 32 + lane;
+    if (qa >= ECB_MQ) qa -= ECB_MQ;
+    if (qb >= ECB_MQ) qb -= ECB_MQ;
+    insert_misses<WITH_CELLS>(P, qk, qr, qa, (u32)lane < qn, qb, (u32)lane + 32u < qn);
   }
   reads_counted = __reduce_add_sync(ECB_FULL, reads_counted);
   if (lane == 0 && reads_counted) atomicAdd(&P.ctr->n_reads, (u64)reads_counted);

@@ -255,7 +255,6 @@ def main():
     ap.add_argument("--grid-ctas", type=int, default=0)
     ap.add_argument("--hot-cache", type=int, default=1)
     ap.add_argument("--chunk-len", type=int, default=0)
-    ap.add_argument("--window-kernel", type=int, default=0, help="1: window form of the grouping kernel (cross-check of the default tile form)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries exactly one JSON line: anything libraries print on fd 1 meanwhile (NCCL announces its
@@ -346,8 +345,6 @@ def main():
     opts["hot_cache"] = args.hot_cache
     if args.chunk_len:
         opts["chunk_len"] = args.chunk_len
-    if args.window_kernel:
-        opts["window_kernel"] = 1
     stream = torch.cuda.current_stream()
 
     def barrier():

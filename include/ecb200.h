@@ -65,10 +65,6 @@ enum ecb_option {
   ECB_OPT_CHUNK_LEN = 7,        /* alignments per work chunk of the grouping kernel (0 = automatic) */
   ECB_OPT_PAGEABLE_RESULTS = 8, /* 1: host results go to ordinary (malloc) memory instead of pinned memory:
                                    cheaper for a context that finalizes once, slower when reused */
-  ECB_OPT_WINDOW_KERNEL = 9     /* 1: the single-sample path runs the window form of the grouping kernel (one
-                                   alignment per lane; it always serves the per-cell path) instead of the tile
-                                   form (one read per lane).  Same results; kept as the cross-check of the
-                                   default.  Initial value: environment variable ECB_WINDOW_KERNEL (0/1) */
 };
 
 typedef struct ecb_result {

@@ -446,22 +446,3 @@ def test_key_verification_option_finds_no_collision(native):
         cols = synth.make_columns(n_reads, n_targets, n_haps, seed=9, mode=mode, dup_rate=dup)
         got, _ = _run(native, cols, n_targets, n_haps, verify_keys=1)
         _assert_same(got, _oracle(cols))
-
-
-@pytest.mark.parametrize("case", ["diploid", "heavy", "dups", "tiny"])
-def test_window_kernel_cross_check(native, case):
-    """ECB_OPT_WINDOW_KERNEL: the window form of the grouping kernel (one alignment per lane; it serves the
-    per-cell path) must give the matrices of the default tile form (one read per lane) and of the oracle."""
-    from alntools_b200 import synth
-    if case == "diploid":
-        cols, nt, nh = synth.make_columns(300000, 5000, 2, seed=31, mode="diploid", dup_rate=0.03), 5000, 2
-    elif case == "heavy":
-        cols, nt, nh = synth.make_columns(20000, 3000, 8, seed=32, mode="heavy", dup_rate=0.02), 3000, 8
-    elif case == "dups":
-        cols, nt, nh = synth.make_columns(100000, 50, 3, seed=33, mode="light", dup_rate=0.4), 50, 3
-    else:
-        cols, nt, nh = synth.make_columns(7, 5, 2, seed=34, mode="light"), 5, 2
-    want = _oracle(cols)
-    for window in (0, 1):
-        got, _ = _run(native, cols, nt, nh, window_kernel=window)
-        _assert_same(got, want)

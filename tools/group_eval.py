@@ -1,4 +1,4 @@
-"""cfg2 (or another workload) on one GPU through the default (tile) and the window form of the grouping kernel:
+"""cfg2 (or another workload) on one GPU through the default library and any variant builds given:
 parity of one against the other and the kernel / step times.
 usage: python tools/group_eval.py [workload] [lib.so ...]   -> prints a table, appends to gpurun_out/group_eval.json"""
 import json, os, sys, time
@@ -19,7 +19,7 @@ n = len(cols["read_group"])
 print("columns ready %.1f s, %d alignments" % (time.time() - t0, n), flush=True)
 KEYS = ("a_indptr", "a_indices", "a_data", "n_data")
 default_lib = _native.load_library()
-runs = [("window", None, {"window_kernel": 1}), ("tile", None, {})] + [(os.path.basename(l), l, {}) for l in libs]
+runs = [("default", None, {})] + [(os.path.basename(l), l, {}) for l in libs]
 base, out = None, {}
 for name, lib, opts in runs:
     try:
