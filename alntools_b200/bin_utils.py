@@ -20,6 +20,13 @@ def _i32(arr):
     return a.data if a.size else b""
 
 
+def _name_bytes(name):
+    """The bytes ecsave2 writes for a name: pack('<{len(name)}s', name.encode()) keeps len(name) BYTES, so a
+    non-ASCII name is cut inside its UTF-8 encoding (bin_utils.py:131-135,153-159,177-180).  Same here, so the
+    file stays byte-identical and the length prefix always matches what follows."""
+    return name.encode("utf-8")[:len(name)]
+
+
 def _target_section(target_names, lengths, n_haps):
     """T x [len(name), name bytes, H x length] (bin_utils.py:153-159).  ASCII names (every aligner
     index) are laid out with numpy scatters; anything else takes the per-name loop."""
@@ -31,7 +38,7 @@ def _target_section(target_names, lengths, n_haps):
         parts = []
         for idx, name in enumerate(target_names):
             parts.append(struct.pack("<i", len(name)))
-            parts.append(name.encode("utf-8"))
+            parts.append(_name_bytes(name))
             parts.append(_i32(lengths[idx, :n_haps]))
         return b"".join(parts)
     nb = np.fromiter(map(len, target_names), dtype=np.int64, count=n)
@@ -58,7 +65,7 @@ def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names,
         fh.write(struct.pack("<i", len(haplotypes)))
         for hap in haplotypes:
             fh.write(struct.pack("<i", len(hap)))
-            fh.write(hap.encode("utf-8"))
+            fh.write(_name_bytes(hap))
         if target_section is not None:
             fh.write(struct.pack("<i", int(n_targets)))
             fh.write(target_section)
@@ -70,7 +77,7 @@ def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names,
         parts = []
         for sample in sample_names:
             parts.append(struct.pack("<i", len(sample)))
-            parts.append(sample.encode("utf-8"))
+            parts.append(_name_bytes(sample))
         fh.write(b"".join(parts))
         for indptr, indices, data in (a_csr, n_csc):
             fh.write(struct.pack("<i", len(indptr)))
@@ -93,7 +100,7 @@ def ecload_arrays(ec_filename):
 
     def text():
         n = i32()
-        s = buf[pos[0]:pos[0] + n].decode("utf-8")
+        s = buf[pos[0]:pos[0] + n].decode("utf-8", errors="replace")   # (a cut non-ASCII name: see _name_bytes)
         pos[0] += n
         return s
 

@@ -32,6 +32,7 @@ struct ecb_ctx {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaMemPool_t pool = nullptr;   // private stream-ordered pool: nothing this context does changes the device's default pool
   int n_targets = 0, n_haps = 0, with_cells = 0;
   int64_t hint = 0;
   // options
@@ -127,15 +128,15 @@ int fail(ecb_ctx* c, int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(c, ECB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
   } while (0)
 
-// Device memory comes from the stream-ordered allocator (cudaMallocAsync on the context's stream):
-// growing a buffer costs no device-wide synchronisation and memory released by one context is
-// reused by the next one in the process (ecb_create raises the pool's release threshold).
+// Device memory comes from the stream-ordered allocator (a private pool per context, on the context's
+// stream): growing a buffer costs no device-wide synchronisation, released blocks stay in the pool for the
+// next buffer of this context, and ecb_destroy hands everything back to the driver.
 int ensure(ecb_ctx* c, DevBuf& b, size_t bytes, bool preserve = false) {
   if (bytes <= b.bytes) return ECB_OK;
   size_t want = std::max(bytes, b.bytes + b.bytes / 2);
   want = (want + 255) & ~(size_t)255;
   void* np = nullptr;
-  CK(cudaMallocAsync(&np, want, c->stream));
+  CK(cudaMallocFromPoolAsync(&np, want, c->pool, c->stream));
   if (preserve && b.p && b.bytes) CK(cudaMemcpyAsync(np, b.p, b.bytes, cudaMemcpyDeviceToDevice, c->stream));
   if (b.p) CK(cudaFreeAsync(b.p, c->stream));
   b.p = np;
@@ -581,12 +582,17 @@ int ecb_create(ecb_ctx** out, int device, int n_targets, int n_haps, int with_ce
   };
   if (cudaSetDevice(device) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaSetDevice failed"); return bail(ECB_ERR_CUDA); }
   {
-    // keep released device memory in the pool instead of handing it back to the driver on every sync
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+    // a pool of this context's own, with released memory kept (the default pool would hand it back to the
+    // driver at every synchronisation); the device's default pool - which torch and NCCL may share - is
+    // left as it is
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaMemPoolCreate failed"); return bail(ECB_ERR_CUDA); }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { fail(c, ECB_ERR_CUDA, "cudaStreamCreate failed"); return bail(ECB_ERR_CUDA); }
   c->stream = c->own_stream;
@@ -1435,7 +1441,11 @@ int ecb_destroy(ecb_ctx* c) {
   }
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
-  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->own_stream) {
+    cudaStreamSynchronize(c->own_stream);
+    cudaStreamDestroy(c->own_stream);
+  }
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   delete c;
   return ECB_OK;
 }

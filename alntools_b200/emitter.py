@@ -126,22 +126,41 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
     import threading
     free, full = queue.Queue(), queue.Queue()
     allocated = [0]
+    stop = threading.Event()
+    rows = [int(chunk_rows)]
 
     def next_buffers():
         """A free buffer set; a new one is pinned only when all existing ones are in flight."""
-        try:
-            return free.get_nowait()
-        except queue.Empty:
-            if allocated[0] < depth:
-                allocated[0] += 1
-                return _column_buffers(chunk_rows, False, pinned)
-            return free.get()
+        while not stop.is_set():
+            try:
+                bufs = free.get_nowait()
+            except queue.Empty:
+                if allocated[0] < depth:
+                    allocated[0] += 1
+                    return _column_buffers(rows[0], False, pinned)
+                try:
+                    bufs = free.get(timeout=0.05)
+                except queue.Empty:
+                    continue
+            if int(bufs[0].shape[0]) >= rows[0]:
+                return bufs
+            allocated[0] -= 1                             # a set from before the buffers grew: let it go
+        return None
 
     def produce():
         try:
-            while True:
+            while not stop.is_set():
                 bufs = next_buffers()
-                n, done = reader.emit(bufs[0], bufs[1], bufs[2])
+                if bufs is None:
+                    return
+                try:
+                    n, done = reader.emit(bufs[0], bufs[1], bufs[2])
+                except ValueError as exc:                 # a read longer than the buffers hold: grow and retry
+                    if "buffers hold" in str(exc) and rows[0] < (1 << 28):   # (as BamColumnReader.read_all does)
+                        rows[0] *= 4
+                        allocated[0] -= 1
+                        continue
+                    raise
                 full.put((bufs, n, done, None))
                 if done:
                     return
@@ -151,17 +170,22 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
     worker = threading.Thread(target=produce, daemon=True)
     worker.start()
     pushed = 0
-    while True:
-        bufs, n, done, exc = full.get()
-        if exc is not None:
-            raise exc
-        if n:
-            builder.push(bufs[0], bufs[1], bufs[2], order_base=pushed, n=n)
-            pushed += n
-        free.put(bufs)
-        if done:
-            break
-    worker.join()
+    try:
+        while True:
+            bufs, n, done, exc = full.get()
+            if exc is not None:
+                raise exc
+            if n:
+                builder.push(bufs[0], bufs[1], bufs[2], order_base=pushed, n=n)
+                pushed += n
+            free.put(bufs)
+            if done:
+                break
+    finally:
+        # whatever happened, the producer has left native code before the caller may close the reader:
+        # bamcols_close frees what bamcols_emit is working on
+        stop.set()
+        worker.join()
     return pushed
 
 

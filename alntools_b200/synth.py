@@ -24,12 +24,28 @@ def _reads_per_k(rng, n_reads, mode):
     raise ValueError(mode)
 
 
+def make_columns_fixed_degree(n_reads, n_targets, n_haps, seed, degree):
+    """The multimapping-degree sweep (BASELINE.json configs[4]): every read has exactly `degree` alignments,
+    each on a Zipf(1.3) transcript and a uniformly random haplotype (duplicates inside a read are possible
+    and collapse, as in the reference)."""
+    rng = np.random.default_rng(seed)
+    n = int(n_reads) * int(degree)
+    return {
+        "read_group": np.repeat(np.arange(n_reads, dtype=np.int32), degree),
+        "target_idx": (rng.zipf(1.3, n) % n_targets).astype(np.int32),
+        "hap_idx": rng.integers(0, n_haps, n, dtype=np.int32),
+        "n_reads": int(n_reads),
+    }
+
+
 def make_columns(n_reads, n_targets, n_haps, seed, mode="light", n_cells=0, dup_rate=0.0):
     """Return dict(read_group, target_idx, hap_idx[, cell_idx]) int32 arrays plus n_reads.
 
     dup_rate: fraction of alignments duplicated verbatim inside their read (same transcript hit at a
     second position), which the reference collapses (bam_utils.py:322-325).
     """
+    if isinstance(mode, str) and mode.startswith("aln"):           # "aln<k>": exactly k alignments per read
+        return make_columns_fixed_degree(n_reads, n_targets, n_haps, seed, int(mode[3:]))
     rng = np.random.default_rng(seed)
     k = _reads_per_k(rng, n_reads, mode)
     n_hits = int(k.sum())

@@ -475,3 +475,48 @@ def test_native_target_section_equals_the_python_one(tmp_path):
         t = r.build_tables(None)
         assert t.target_section() is None
         assert list(t.main_targets.keys()) == ["tr\u00e4", "t2"]
+
+
+class _StubBuilder(object):
+    """Stands in for EcBuilder: collects what stream_single pushes (host logic only, no GPU)."""
+
+    def __init__(self, fail_at=None):
+        self.parts, self.bases, self.fail_at = [], [], fail_at
+
+    def push(self, rg, tg, hp, order_base=0, n=None):
+        if self.fail_at is not None and len(self.parts) >= self.fail_at:
+            raise RuntimeError("push failed")
+        self.parts.append([np.array(x[:n]) for x in (rg, tg, hp)])
+        self.bases.append(order_base)
+
+
+def test_stream_single_pipeline(tmp_path):
+    """emitter.stream_single: the pieces it pushes add up to the file; a read longer than the buffers makes
+    them grow (as read_all does) instead of failing; when the consumer fails the decode thread has left the
+    native library before the exception reaches the caller, so closing the reader is safe."""
+    import threading
+    rng = np.random.default_rng(12)
+    alns = []
+    for read in range(2000):
+        k = 40 if read == 700 else int(rng.integers(1, 5))
+        for _ in range(k):
+            alns.append(("read%05d" % read, 0, int(rng.integers(0, len(REFS)))))
+    path = _write(tmp_path, alns)
+    want, _ = _python_single(path)
+    for rows in (1 << 16, 64, 16):                                  # 16 < the 40-alignment read: buffers grow
+        with bamcols.BamColumnReader(path) as r:
+            r.set_tables(TargetTables(r.references, r.lengths, None))
+            stub = _StubBuilder()
+            n = emitter.stream_single(r, stub, chunk_rows=rows, pinned=False)
+        assert n == len(want.read_group)
+        assert stub.bases == list(np.cumsum([0] + [len(p[0]) for p in stub.parts[:-1]]))
+        assert np.array_equal(np.concatenate([p[1] for p in stub.parts]), want.target_idx)
+        assert np.array_equal(np.concatenate([p[2] for p in stub.parts]), want.hap_idx)
+        starts = np.concatenate([p[0][1:] != p[0][:-1] for p in stub.parts if len(p[0]) > 1])
+        assert int(starts.sum()) + len(stub.parts) == want.n_groups   # no read is split between pushes
+    before = threading.active_count()
+    with bamcols.BamColumnReader(path) as r:
+        r.set_tables(TargetTables(r.references, r.lengths, None))
+        with pytest.raises(RuntimeError, match="push failed"):
+            emitter.stream_single(r, _StubBuilder(fail_at=3), chunk_rows=64, pinned=False)
+        assert threading.active_count() == before                   # the producer was joined

@@ -193,3 +193,30 @@ def test_reference_writers_accept_our_output_object(tmp_path):
         ref_bin_utils.ecsave2(out, apm)
         with open(src, "rb") as a, open(out, "rb") as b:
             assert a.read() == b.read(), case["name"]
+
+
+def test_non_ascii_names_are_written_as_the_reference_writes_them(tmp_path):
+    """ecsave2 packs '<{len(name)}s': len(name) BYTES of the UTF-8 encoding, i.e. a non-ASCII name is cut.  Our
+    writer must produce the same bytes (checked against the unmodified reference when it is here) and our
+    reader must be able to read its own file back."""
+    from alntools_b200 import bin_utils
+    from alntools_b200.apm import ApmArrays
+    haps, targets, samples = ["A", "Bé"], ["tränscript1", "t2", "ターゲット"], ["sämple"]
+    lengths = np.array([[100, 101], [200, 0], [300, 301]], dtype=np.int32)
+    a = (np.array([0, 2, 3], dtype=np.int32), np.array([0, 2, 1], dtype=np.int32), np.array([3, 1, 2], dtype=np.int32))
+    n = (np.array([0, 2], dtype=np.int32), np.array([0, 1], dtype=np.int32), np.array([5, 7], dtype=np.int32))
+    ours = str(tmp_path / "ours.bin")
+    bin_utils.ecsave2_arrays(ours, haps, targets, lengths, samples, a, n)
+    back = bin_utils.ecload_arrays(ours)
+    assert [len(x) for x in back["targets"]] <= [len(x) for x in targets] and back["haplotypes"][0] == "A"
+    assert np.array_equal(back["a"][2], a[2]) and np.array_equal(back["n"][2], n[2])
+    assert np.array_equal(back["lengths"], lengths)
+    from oracle import run_reference
+    if not run_reference.available():
+        return
+    run_reference._import_reference()
+    from alntools import bin_utils as ref_bin_utils
+    ref = str(tmp_path / "ref.bin")
+    ref_bin_utils.ecsave2(ref, ApmArrays(haps, targets, lengths.copy(), samples, a, n))
+    with open(ours, "rb") as x, open(ref, "rb") as y:
+        assert x.read() == y.read()
