@@ -276,11 +276,22 @@ def test_cells_match_oracle(native, n_files, reads, n_cells, mincount):
 
 
 # ---------------------------------------------------------------- full-size properties (BASELINE configs)
+_CFG2 = {}
+
+
+def _cfg2():
+    """cfg2's columns and the C oracle's result on them, made once for the tests that use them."""
+    if not _CFG2:
+        from alntools_b200 import synth
+        _CFG2["cols"] = synth.make_columns(30_000_000, 100_000, 2, seed=2, mode="diploid")
+        _CFG2["want"] = _oracle(_CFG2["cols"])
+    return _CFG2["cols"], _CFG2["want"]
+
+
 def test_full_size_cfg2_properties_and_oracle(native):
     """cfg2 shape at full size (30 M reads, 2 haplotypes x 100 k transcripts): size-independent
     properties on the GPU result, then the C oracle on the same columns."""
-    from alntools_b200 import synth
-    cols = synth.make_columns(30_000_000, 100_000, 2, seed=2, mode="diploid")
+    cols, want = _cfg2()
     got, stats = _run(native, cols, 100_000, 2)
     n_aln = len(cols["read_group"])
     assert got["n_reads"] == cols["n_reads"] and got["n_alignments"] == n_aln
@@ -294,7 +305,65 @@ def test_full_size_cfg2_properties_and_oracle(native):
     again, _ = _run(native, cols, 100_000, 2)
     for k in ("a_indptr", "a_indices", "a_data", "n_data"):
         assert np.array_equal(got[k], again[k])
+    _assert_same(got, want)
+
+
+def test_full_size_cfg2_key_verification(native):
+    """EC identity on the device is the 128-bit set hash.  ECB_OPT_VERIFY_KEYS re-derives
+    every read's set of (target, haplotype) pairs and compares it with the row of the EC it was counted in: at
+    cfg2's full size (30 M reads, 4 M ECs) no two different sets may share a key, and the result is the oracle's."""
+    cols, want = _cfg2()
+    got, _ = _run(native, cols, 100_000, 2, verify_keys=1)      # a collision raises EcbError(ECB_ERR_LIMIT)
+    _assert_same(got, want)
+    _CFG2.clear()
+
+
+def test_full_size_cfg3_heavy_with_key_verification(native):
+    """cfg3 shape at the size the bench runs per GPU (8 haplotypes x 140 k transcripts, heavy multimapping,
+    100 M alignments): key verification on, result against the C oracle."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(3_000_000, 140_000, 8, seed=3, mode="heavy")
+    assert len(cols["read_group"]) > 90_000_000
+    got, _ = _run(native, cols, 140_000, 8, verify_keys=1)
+    assert int(got["n_data"].astype(np.int64).sum()) == cols["n_reads"]
     _assert_same(got, _oracle(cols))
+
+
+@pytest.mark.parametrize("degree", [1, 64])
+def test_full_size_cfg5_sweep_ends(native, degree):
+    """cfg5, the two ends of the multimapping-degree sweep at the bench's size (64 M alignments, exactly
+    `degree` alignments per read, 8 haplotypes x 140 k transcripts) against the C oracle."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(64_000_000 // degree, 140_000, 8, seed=5, mode="aln%d" % degree)
+    got, _ = _run(native, cols, 140_000, 8)
+    _assert_same(got, _oracle(cols))
+
+
+def test_full_size_cfg4_cells_50k(native):
+    """cfg4 at the bench's size on one GPU: 20 M reads, 50 000 cells (Zipf sizes), 4 files with their last
+    read dropped, cells below 1000 reads filtered - against the C statement of the per-cell merge
+    (oracle/ec_oracle.c: ec_oracle_build_cells, itself pinned to the Python statement on small cases)."""
+    from alntools_b200 import synth
+    from oracle import c_oracle
+    cols = synth.make_columns(20_000_000, 140_000, 8, seed=4, mode="diploid", n_cells=50_000)
+    n = len(cols["read_group"])
+    cuts = [0]
+    for k in range(1, 4):
+        c = n * k // 4
+        while c < n and cols["read_group"][c] == cols["read_group"][c - 1]:
+            c += 1
+        cuts.append(c)
+    cuts.append(n)
+    pushes = [(cols["read_group"][a:b], cols["target_idx"][a:b], cols["hap_idx"][a:b], cols["cell_idx"][a:b], True)
+              for a, b in zip(cuts[:-1], cuts[1:])]
+    with native.EcBuilder(140_000, 8, with_cells=True, alignments_hint=n) as b:
+        for (rg, tg, hp, cell, drop), base in zip(pushes, cuts[:-1]):
+            b.push(rg, tg, hp, cell, order_base=base, drop_last_group=drop)
+        got = b.finalize(1000)
+    want = c_oracle.ec_from_columns_cells(pushes, 1000)
+    assert got["n_reads"] == want["n_reads"]
+    for k in ("a_indptr", "a_indices", "a_data", "n_indptr", "n_indices", "n_data", "cell_order"):
+        assert np.array_equal(got[k], want[k]), k
 
 
 # ---------------------------------------------------------------- multi-GPU exchange (needs >= 2 GPUs)

@@ -220,3 +220,29 @@ def test_non_ascii_names_are_written_as_the_reference_writes_them(tmp_path):
     ref_bin_utils.ecsave2(ref, ApmArrays(haps, targets, lengths.copy(), samples, a, n))
     with open(ours, "rb") as x, open(ref, "rb") as y:
         assert x.read() == y.read()
+
+
+def test_c_per_cell_oracle_equals_the_python_statement():
+    """oracle/ec_oracle.c: ec_oracle_build_cells (used at sizes the Python statement cannot finish) against
+    oracle/ec_oracle.py: ec_from_columns_cells, which follows bam_utils_multisample.py:503-636,702-791 and is
+    pinned by the multisample goldens: random files, cells, minimum counts, dropped last reads."""
+    from oracle import c_oracle, ec_oracle
+    from alntools_b200 import synth
+    rng = np.random.default_rng(3)
+    for case in range(40):
+        pushes = []
+        for f in range(int(rng.integers(1, 5))):
+            cols = synth.make_columns(int(rng.integers(1, 200)), int(rng.integers(2, 30)), int(rng.integers(1, 4)),
+                                      seed=int(rng.integers(0, 1 << 30)), mode=["light", "diploid", "heavy"][int(rng.integers(0, 3))],
+                                      n_cells=int(rng.integers(1, 12)), dup_rate=0.1)
+            pushes.append((cols["read_group"], cols["target_idx"], cols["hap_idx"], cols["cell_idx"], bool(rng.integers(0, 2))))
+        minimum = int(rng.choice([-1, 0, 1, 2, 5, 20]))
+        try:
+            want = ec_oracle.ec_from_columns_cells(pushes, minimum)
+        except ValueError:
+            with pytest.raises(ValueError):
+                c_oracle.ec_from_columns_cells(pushes, minimum)
+            continue
+        got = c_oracle.ec_from_columns_cells(pushes, minimum)
+        for k in want:
+            assert np.array_equal(want[k], got[k]), (case, k)
