@@ -77,6 +77,7 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "ecb_arena_open_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ecb_arena_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "ecb_rebase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "ecb_export_to_arenas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                             ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
                                             ctypes.POINTER(ctypes.c_int64)]),
@@ -287,6 +288,10 @@ class EcBuilder(object):
 
     def arena_reset(self):
         self._check(self._lib.ecb_arena_reset(self._ctx))
+
+    def rebase(self, delta):
+        """Shift the order key of everything pushed so far by `delta` (see ecb_rebase in include/ecb200.h)."""
+        self._check(self._lib.ecb_rebase(self._ctx, int(delta)))
 
     def export_to_arenas(self, bases, cap_records, cap_rows):
         """Partition this LOCAL context's ECs by owner and store them into the owners' arenas.

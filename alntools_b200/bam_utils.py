@@ -171,15 +171,186 @@ def _convert_python_emitter(bam_filename, target_filename, device, start_time):
     return res, tables, cols.valid_alignments
 
 
+def _requested_gpus(devices):
+    """How many GPUs the caller asked for: the `devices` keyword, else the environment variable ALNTOOLS_GPUS
+    (the CLI keeps the reference's options, so the environment is its only way to say it), else one."""
+    if devices is not None:
+        return max(1, int(devices))
+    try:
+        return max(1, int(os.environ.get("ALNTOOLS_GPUS", "1") or 1))
+    except ValueError:
+        raise ValueError("ALNTOOLS_GPUS must be a number of GPUs, found %r" % os.environ.get("ALNTOOLS_GPUS"))
+
+
+def _under_launcher():
+    """True inside a one-process-per-GPU job (torchrun sets RANK / WORLD_SIZE / LOCAL_RANK)."""
+    return int(os.environ.get("WORLD_SIZE", "1") or 1) > 1 and "RANK" in os.environ
+
+
+def _spawn_ranks(n_gpus, kwargs):
+    """convert() on `n_gpus` GPUs from an ordinary call: one worker process per GPU (the contract of the
+    multi-GPU path), each running convert_rank on its shard of the file; rank 0 reports the totals."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    import tempfile
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    with tempfile.TemporaryDirectory(prefix="alntools_b200_") as tmp:
+        job = os.path.join(tmp, "job.json")
+        with open(job, "w") as fh:
+            json.dump(kwargs, fh)
+        procs = []
+        for rank in range(n_gpus):
+            env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(n_gpus),
+                       MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ALNTOOLS_B200_SUMMARY=os.path.join(tmp, "summary.json"),
+                       ALNTOOLS_B200_VERBOSE="1" if LOG.isEnabledFor(20) else "0")
+            procs.append(subprocess.Popen([sys.executable, "-m", "alntools_b200._rank_worker", job], env=env))
+        codes = [p.wait() for p in procs]
+        if any(codes):
+            raise RuntimeError("multi-GPU bam2ec failed: worker exit codes %s" % codes)
+        with open(os.path.join(tmp, "summary.json")) as fh:
+            return json.load(fh)
+
+
+def convert_rank(bam_filename, ec_filename, emase_filename, num_chunks=0, number_processes=-1, temp_dir=None,
+                 range_filename=None, sample=None, target_filename=None):
+    """One rank of the multi-GPU convert (one process per GPU; RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* in
+    the environment, as torchrun sets them).  What the reference does with a process pool over chunk BAMs
+    merged in chunk order (alntools/bam_utils.py:642-724) happens here as: every rank plans the same shards of
+    the ONE file (virtual offsets at read boundaries, no temporary BAMs: bamcols_plan_shards), decodes and
+    groups its own on its GPU, is moved to its global position in read order (ecb_rebase: the position is
+    known once every rank has counted its alignments), and the ranks merge through the exchange of
+    multi_gpu.distributed_finalize.  The final matrices stay partitioned by EC-id range; every rank writes its
+    byte ranges of the EC file.  Returns the totals on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import multi_gpu
+    start_time = time.time()
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", device_id=device)
+    try:
+        _, num_processes = _job_plan(num_chunks, number_processes)
+        num_processes = max(1, num_processes // world)          # the host threads are shared by the ranks
+        if sample is None:
+            sample = os.path.basename(bam_filename)
+        with bamcols.BamColumnReader(bam_filename, n_threads=num_processes) as reader:
+            tables = reader.build_tables(target_filename)
+            plan = reader.plan_shards(world)
+            reader.set_range(plan[rank], plan[rank + 1])
+            if range_filename is not None:
+                reader.track_ranges(True)
+            opts = dict(with_cells=False, alignments_hint=0, device=local_rank, result_on_device=1)
+            with EcBuilder(tables.num_targets, tables.num_haplotypes, **opts) as builder, \
+                    EcBuilder(tables.num_targets, tables.num_haplotypes, **opts) as owner:
+                chunk_rows = int(min(1 << 23, max(1 << 16, os.path.getsize(bam_filename) // 2)))
+                valid = emitter.stream_single(reader, builder, chunk_rows=chunk_rows, pinned=True)
+                mine = torch.tensor([valid, reader.all_alignments], dtype=torch.int64, device=device)
+                every = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(every, mine)
+                every = torch.stack(every).tolist()
+                total_valid = sum(r[0] for r in every)
+                if total_valid == 0:                              # as the single-GPU path (Sparse3DMatrix.py:45-46)
+                    raise RuntimeError("The shape must be a tuple of three positive integers.")
+                builder.rebase(sum(r[0] for r in every[:rank]))
+                out = multi_gpu.distributed_finalize(builder, lambda: owner, device, result_on="slices")
+                n_ec, id_base, n_local, nnz_local = int(out["n_ec"]), int(out["id_base"]), int(out["n_ec_local"]), int(out["nnz_local"])
+                sizes = [torch.empty(2, dtype=torch.int64, device=device) for _ in range(world)]
+                dist.all_gather(sizes, torch.tensor([n_local, nnz_local], dtype=torch.int64, device=device))
+                sizes = torch.stack(sizes).tolist()
+                nnz_base, nnz_total = sum(r[1] for r in sizes[:rank]), sum(r[1] for r in sizes)
+                a_indptr = out["a_indptr"][:n_local + 1].cpu().numpy()
+                a_indices = out["a_indices"][:nnz_local].cpu().numpy()
+                a_data = out["a_data"][:nnz_local].cpu().numpy()
+                counts = out["n_data"][:n_local].cpu().numpy()
+                reads = torch.tensor([int(counts.astype(np.int64).sum())], dtype=torch.int64, device=device)
+                dist.all_reduce(reads)
+            section = tables.target_section()
+            target_names = list(tables.main_targets.keys()) if (emase_filename or section is None) else None
+            if ec_filename:
+                header = bin_utils.ec_header_bytes(tables.haplotypes, target_names, tables.lengths, [sample],
+                                                   target_section=section, n_targets=tables.num_targets)
+                args = (ec_filename, header, n_ec, nnz_total, id_base, nnz_base, a_indptr, a_indices, a_data, counts)
+                if rank == 0:
+                    try:
+                        os.remove(ec_filename)
+                    except OSError:
+                        pass
+                    bin_utils.ecsave2_slice(*args, create=True)
+                dist.barrier()                                    # the file is laid out
+                if rank != 0:
+                    bin_utils.ecsave2_slice(*args, create=False)
+                dist.barrier()
+            if emase_filename:                                    # one writer: the slices travel to rank 0
+                parts = [None] * world
+                dist.all_gather_object(parts, (a_indptr, a_indices, a_data, counts))
+                if rank == 0:
+                    indptr = np.concatenate([[0]] + [p[0][1:].astype(np.int64) + sum(len(q[1]) for q in parts[:i])
+                                                     for i, p in enumerate(parts)]).astype(np.int32)
+                    a_csr = (indptr, np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts]))
+                    n_counts = np.concatenate([p[3] for p in parts])
+                    n_csc = (np.array([0, n_ec], dtype=np.int32), np.arange(n_ec, dtype=np.int32), n_counts)
+                    try:
+                        os.remove(emase_filename)
+                    except OSError:
+                        pass
+                    emase.save_emase(emase_filename, "bam2ec", (tables.num_targets, tables.num_haplotypes, n_ec),
+                                     tables.haplotypes, target_names, tables.lengths, [sample], a_csr, n_csc,
+                                     incidence_only=True)
+            if range_filename is not None:                        # bam_utils.py:735-766, over all shards
+                lo, hi = reader.ranges()
+                lo_t, hi_t = torch.from_numpy(lo.copy()).to(device), torch.from_numpy(hi.copy()).to(device)
+                dist.all_reduce(lo_t, op=dist.ReduceOp.MIN)
+                dist.all_reduce(hi_t, op=dist.ReduceOp.MAX)
+                if rank == 0:
+                    utils.write_range_file(range_filename, list(tables.main_targets.keys()), tables.haplotypes,
+                                           reader.references, lo_t.cpu().numpy(), hi_t.cpu().numpy())
+        if rank != 0:
+            return None
+        LOG.info("# Valid Alignments: {:,}".format(total_valid))
+        LOG.info("# Main Targets: {:,}".format(tables.num_targets))
+        LOG.info("# Haplotypes: {:,}".format(tables.num_haplotypes))
+        LOG.info("# Equivalence Classes: {:,}".format(n_ec))
+        LOG.info("# Unique Reads: {:,}".format(int(reads.item())))
+        LOG.info("{} GPUs, total time: {}".format(world, utils.format_time(start_time, time.time())))
+        return {"n_ec": n_ec, "nnz_a": nnz_total, "n_samples": 1, "nnz_n": n_ec, "n_reads": int(reads.item()),
+                "n_alignments": total_valid, "n_gpus": world,
+                "alignments_per_gpu": [r[0] for r in every]}
+    finally:
+        if own_group and dist.is_initialized():
+            dist.destroy_process_group()
+
+
 def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_processes=-1, temp_dir=None,
-            range_filename=None, sample=None, target_filename=None, device=0):
+            range_filename=None, sample=None, target_filename=None, device=0, devices=None):
     """Convert a name-grouped BAM file into an EC binary file and/or an EMASE file.
 
     Arguments keep the reference's meaning.  num_chunks / number_processes only shape the host decode
     (the EC file does not depend on them, as in the reference); temp_dir is unused because no
-    temporary BAM is written.  `device` selects the GPU.
+    temporary BAM is written.  `device` selects the GPU.  devices=N (or the environment variable
+    ALNTOOLS_GPUS=N) shards the file over N GPUs of this machine, one worker process per GPU (convert_rank);
+    the same happens without either when the call is made inside a one-process-per-GPU job (torchrun).
+    The EC file does not depend on the number of GPUs.
     """
     start_time = time.time()
+    job = dict(bam_filename=bam_filename, ec_filename=ec_filename, emase_filename=emase_filename, num_chunks=num_chunks,
+               number_processes=number_processes, temp_dir=temp_dir, range_filename=range_filename, sample=sample,
+               target_filename=target_filename)
+    if _under_launcher():
+        if emitter.use_python_emitter():
+            raise NotImplementedError("the multi-GPU path needs the native emitter (unset ALNTOOLS_B200_EMITTER)")
+        return convert_rank(**job)
+    if _requested_gpus(devices) > 1:
+        if emitter.use_python_emitter():
+            raise NotImplementedError("the multi-GPU path needs the native emitter (unset ALNTOOLS_B200_EMITTER)")
+        return _spawn_ranks(_requested_gpus(devices), job)
     if range_filename is not None and emitter.use_python_emitter():
         raise NotImplementedError("--rangefile needs the native emitter (unset ALNTOOLS_B200_EMITTER)")
     num_chunks, num_processes = _job_plan(num_chunks, number_processes)
@@ -253,3 +424,4 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
             utils.write_range_file(range_filename, list(tables.main_targets.keys()), tables.haplotypes,
                                    reader.references, lo, hi)
     return summary
+

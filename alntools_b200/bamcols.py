@@ -39,6 +39,8 @@ SIGNATURES = {
                                       ctypes.POINTER(ctypes.c_int)]),
     "bamcols_all_alignments": (ctypes.c_int64, [ctypes.c_void_p]),
     "bamcols_n_groups": (ctypes.c_int64, [ctypes.c_void_p]),
+    "bamcols_plan_shards": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]),
+    "bamcols_set_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]),
     "bamcols_track_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "bamcols_ranges": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p)]),
     "bamcols_phase_seconds": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]),
@@ -245,6 +247,23 @@ class BamColumnReader(object):
     @property
     def all_alignments(self):
         return int(self._lib.bamcols_all_alignments(self._h))
+
+    def plan_shards(self, n_shards):
+        """n_shards + 1 BGZF virtual offsets: shard k holds the records of [v[k], v[k + 1]); every shard starts
+        at a read boundary, v[0] is the first record of the file, -1 stands for the end of the file.  What the
+        reference's calculate_chunks (bam_utils.py:1174-1304) plans - without the temporary BAM files."""
+        v = (ctypes.c_int64 * (int(n_shards) + 1))()
+        rc = self._lib.bamcols_plan_shards(self._h, int(n_shards), v)
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(self._h).decode())
+        return [int(x) for x in v]
+
+    def set_range(self, vbegin, vend=-1):
+        """Confine this reader to the records of [vbegin, vend) (virtual offsets of plan_shards); before the
+        first emit()."""
+        rc = self._lib.bamcols_set_range(self._h, int(vbegin), int(vend))
+        if rc != 0:
+            _raise(rc, self._lib.bamcols_last_error(self._h).decode())
 
     def track_ranges(self, enable=True):
         rc = self._lib.bamcols_track_ranges(self._h, 1 if enable else 0)

@@ -8,6 +8,7 @@ strings raw UTF-8 with an int32 length prefix, no padding:
 The reference packs every array with struct.pack('<{n}i', *arr) (one Python int per element);
 ndarray.astype('<i4').tobytes() yields the same bytes.
 """
+import os
 import struct
 
 import numpy as np
@@ -85,6 +86,67 @@ def ecsave2_arrays(ec_filename, haplotypes, target_names, lengths, sample_names,
             fh.write(_i32(indptr))
             fh.write(_i32(indices))
             fh.write(_i32(data))
+
+
+def ec_header_bytes(haplotypes, target_names, lengths, sample_names, target_section=None, n_targets=None):
+    """The sections of an EC file in front of the matrices (format tag, haplotypes, targets, samples), as
+    ecsave2_arrays writes them."""
+    parts = [struct.pack("<i", 2), struct.pack("<i", len(haplotypes))]
+    for hap in haplotypes:
+        parts.append(struct.pack("<i", len(hap)))
+        parts.append(_name_bytes(hap))
+    if target_section is not None:
+        parts.append(struct.pack("<i", int(n_targets)))
+        parts.append(bytes(target_section))
+    else:
+        parts.append(struct.pack("<i", len(target_names)))
+        parts.append(_target_section(target_names, np.asarray(lengths).astype(int), len(haplotypes)))
+    parts.append(struct.pack("<i", len(sample_names)))
+    for sample in sample_names:
+        parts.append(struct.pack("<i", len(sample)))
+        parts.append(_name_bytes(sample))
+    return b"".join(parts)
+
+
+def ecsave2_slice(ec_filename, header, n_ec_total, nnz_total, id_base, nnz_base, a_indptr_local, a_indices, a_data,
+                  counts, create):
+    """Single-sample EC file written by several processes, each holding the ECs [id_base, id_base + n) of the
+    final matrices (the multi-GPU build leaves them partitioned by EC-id range): every process writes its
+    own byte ranges of the A (CSR) and N (CSC, one sample) sections; the one with create=True also lays the
+    file out (header sections, the four size fields, indptr[0], N's indptr) and must run first.
+    a_indptr_local: [n + 1] offsets local to the slice (a_indptr_local[0] == 0); nnz_base = non-zeros of the
+    slices in front.  Same bytes as ecsave2_arrays on the assembled matrices (alntools/bin_utils.py:105-277)."""
+    E, Z = int(n_ec_total), int(nnz_total)
+    n = len(counts)
+    hdr = len(header)
+    a_at = hdr                                   # A: len(indptr), nnz, indptr[E + 1], indices[Z], data[Z]
+    a_indptr_at = a_at + 8
+    a_indices_at = a_indptr_at + 4 * (E + 1)
+    a_data_at = a_indices_at + 4 * Z
+    n_at = a_data_at + 4 * Z                     # N: 2, E, [0, E], indices[E] = 0..E-1, data[E] = counts
+    n_indices_at = n_at + 16
+    n_data_at = n_indices_at + 4 * E
+    total = n_data_at + 4 * E
+    if create:
+        with open(ec_filename, "wb") as fh:
+            fh.write(header)
+            fh.write(struct.pack("<ii", E + 1, Z))
+            fh.write(struct.pack("<i", 0))
+            fh.truncate(total)
+            fh.seek(n_at)
+            fh.write(struct.pack("<iiii", 2, E, 0, E))
+    fd = os.open(ec_filename, os.O_WRONLY)
+    try:
+        if n:
+            indptr = (np.asarray(a_indptr_local[1:], dtype=np.int64) + int(nnz_base)).astype("<i4")
+            os.pwrite(fd, _i32(indptr), a_indptr_at + 4 * (int(id_base) + 1))
+            os.pwrite(fd, _i32(np.arange(int(id_base), int(id_base) + n, dtype=np.int32)), n_indices_at + 4 * int(id_base))
+            os.pwrite(fd, _i32(counts), n_data_at + 4 * int(id_base))
+        if len(a_indices):
+            os.pwrite(fd, _i32(a_indices), a_indices_at + 4 * int(nnz_base))
+            os.pwrite(fd, _i32(a_data), a_data_at + 4 * int(nnz_base))
+    finally:
+        os.close(fd)
 
 
 def ecload_arrays(ec_filename):

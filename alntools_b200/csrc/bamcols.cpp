@@ -179,7 +179,14 @@ struct bamcols {
   const uint8_t* file = nullptr;
   size_t file_size = 0;
   size_t cpos = 0;               // compressed offset of the next BGZF block
-  bool file_done = false;        // every block has been inflated
+  bool file_done = false;        // every block (of the range) has been inflated
+  // a reader may be confined to a range of records [begin, end) given as BGZF virtual offsets (compressed
+  // offset of a block << 16 | offset inside the inflated block): one shard of a file that several readers
+  // share (bamcols_plan_shards / bamcols_set_range)
+  size_t end_c = SIZE_MAX;       // compressed offset of the block that holds the end of the range
+  uint32_t end_u = 0;            // ... and how many of its inflated bytes belong to the range
+  int64_t first_voffset = 0;     // virtual offset of the first record (set by bamcols_open)
+  size_t last_batch_c0 = 0, last_batch_keep = 0;   // where the latest refill started: file offset and window offset
   RawBuf<uint8_t> win;           // inflated window
   size_t wpos = 0, wend = 0;     // unread part of the window
   int n_threads = 1;
@@ -322,8 +329,14 @@ int refill(bamcols* r) {
   r->wend = keep;
   std::vector<BlockJob> jobs;
   jobs.reserve(r->batch_blocks);
-  size_t total = 0;
+  size_t total = 0, spill = 0;   // spill: inflated bytes of the last block that lie beyond the end of the range
+  r->last_batch_c0 = r->cpos;
+  r->last_batch_keep = keep;
   while (jobs.size() < r->batch_blocks) {
+    if (r->cpos > r->end_c || (r->cpos == r->end_c && r->end_u == 0)) {
+      r->file_done = true;
+      break;
+    }
     BlockJob job;
     size_t bsize = 0;
     const int rc = parse_block(r, r->cpos, &job, &bsize);
@@ -333,12 +346,21 @@ int refill(bamcols* r) {
       break;
     }
     job.dst_off = keep + total;
+    if (r->cpos == r->end_c) {   // the range ends inside this block (at a record boundary)
+      if (r->end_u > job.isize) return fail(r, BAMCOLS_ERR_INVALID, "range end lies beyond its block");
+      total += r->end_u;
+      spill = job.isize - r->end_u;
+      r->cpos += bsize;
+      jobs.push_back(job);
+      r->file_done = true;
+      break;
+    }
     total += job.isize;
     r->cpos += bsize;
     jobs.push_back(job);
   }
   if (jobs.empty()) return 0;
-  if (r->win.size() < keep + total) r->win.resize(keep + total);
+  if (r->win.size() < keep + total + spill) r->win.resize(keep + total + spill);
   uint8_t* base = r->win.data();
   const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)r->n_threads, (jobs.size() + 15) / 16));
   std::atomic<size_t> next(0);
@@ -1204,6 +1226,19 @@ int bamcols_open(bamcols** out, const char* path, int n_threads) {
   const int rc = read_header(r);
   r->batch_blocks = full_batch;
   if (rc < 0) return bail(rc);
+  {
+    // virtual offset of the first record: hop over the blocks of the batch that holds the window position
+    size_t c = r->last_batch_c0, w = r->last_batch_keep;
+    for (;;) {
+      BlockJob job;
+      size_t bsize = 0;
+      const int prc = parse_block(r, c, &job, &bsize);
+      if (prc != 0 || w + job.isize > r->wpos || (w + job.isize == r->wpos && c + bsize >= r->cpos)) break;
+      w += job.isize;
+      c += bsize;
+    }
+    r->first_voffset = (int64_t)((c << 16) | (r->wpos - w));
+  }
   r->prefetch = std::thread([r]() { r->prefetch_rc = refill(r); });
   *out = r;
   return BAMCOLS_OK;
@@ -1403,6 +1438,173 @@ int64_t bamcols_cells_count(const bamcols_cells* c) { return c ? (int64_t)c->nam
 const char* bamcols_cells_name(const bamcols_cells* c, int64_t idx) {
   if (!c || idx < 0 || (size_t)idx >= c->names.size()) return nullptr;
   return c->names[(size_t)idx].c_str();
+}
+
+// ---- shards of ONE file (what alntools/bam_utils.py:1174-1304 plans and :157-195 copies into
+// temporary BAM files is here a list of virtual offsets; nothing is copied) --------------------------------
+namespace {
+
+// First BGZF block boundary at or behind `from`: the magic bytes, a header that parses, and two more blocks
+// (or the end of the file) chained behind it.
+size_t find_block_boundary(bamcols* r, size_t from) {
+  const std::string keep_err = r->err;
+  for (size_t q = from; q + 18 <= r->file_size; ++q) {
+    const uint8_t* p = r->file + q;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) continue;
+    size_t c = q;
+    bool ok = true;
+    for (int k = 0; k < 3 && ok && c < r->file_size; ++k) {
+      BlockJob job;
+      size_t bsize = 0;
+      ok = parse_block(r, c, &job, &bsize) == 0;
+      c += bsize;
+    }
+    if (ok) {
+      r->err = keep_err;
+      return q;
+    }
+  }
+  r->err = keep_err;
+  return r->file_size;
+}
+
+// Inflated bytes from a block boundary on, with the table that maps them back to virtual offsets.
+struct PlanBuf {
+  std::vector<uint8_t> data;
+  std::vector<size_t> blk_c, blk_off;   // per block: compressed offset, offset of its first byte in `data`
+  size_t next_c = 0;
+  bool eof = false;
+  Inflater inf;
+};
+
+int plan_more(bamcols* r, PlanBuf& b, size_t want_blocks) {
+  for (size_t k = 0; k < want_blocks && !b.eof; ++k) {
+    BlockJob job;
+    size_t bsize = 0;
+    const int rc = parse_block(r, b.next_c, &job, &bsize);
+    if (rc < 0) return rc;
+    if (rc == 1) {
+      b.eof = true;
+      break;
+    }
+    const size_t at = b.data.size();
+    b.data.resize(at + job.isize);
+    if (!b.inf.run(job.src, job.src_len, b.data.data() + at, job.isize))
+      return fail(r, BAMCOLS_ERR_FORMAT, "corrupt BGZF block (inflate failed) at offset %zu", b.next_c);
+    b.blk_c.push_back(b.next_c);
+    b.blk_off.push_back(at);
+    b.next_c += bsize;
+  }
+  return 0;
+}
+
+int64_t plan_voffset(const PlanBuf& b, size_t pos) {
+  // the LAST block that starts at or before pos and is not empty there (a record that begins exactly where a
+  // block ends belongs to the next block)
+  size_t k = std::upper_bound(b.blk_off.begin(), b.blk_off.end(), pos) - b.blk_off.begin() - 1;
+  return (int64_t)((b.blk_c[k] << 16) | (pos - b.blk_off[k]));
+}
+
+}  // namespace
+
+int bamcols_plan_shards(bamcols* r, int n_shards, int64_t* voffsets) {
+  if (!r || !voffsets || n_shards < 1) return BAMCOLS_ERR_INVALID;
+  const int32_t n_ref = (int32_t)r->ref_names.size();
+  const size_t c_first = (size_t)(r->first_voffset >> 16);
+  voffsets[0] = r->first_voffset;
+  voffsets[n_shards] = -1;   // the end of the file
+  for (int k = 1; k < n_shards; ++k) {
+    voffsets[k] = -1;
+    const size_t target = c_first + (size_t)((double)(r->file_size - c_first) * (double)k / (double)n_shards);
+    const size_t q = find_block_boundary(r, std::max(target, c_first + 1));
+    if (q >= r->file_size) continue;   // nothing behind the target: an empty shard at the end
+    PlanBuf b;
+    b.next_c = q;
+    int rc = plan_more(r, b, 8);
+    if (rc < 0) return rc;
+    // a record start: eight plausible records in a row (samtools / htslib start every block with one)
+    size_t p = SIZE_MAX;
+    for (size_t cand = 0; cand + 36 <= b.data.size() && cand < (1u << 17); ++cand) {
+      size_t x = cand;
+      int good = 0;
+      while (good < 8) {
+        if (x + 36 > b.data.size()) {
+          if (b.eof) break;
+          rc = plan_more(r, b, 8);
+          if (rc < 0) return rc;
+          continue;
+        }
+        if (!plausible_record(b.data.data(), x, b.data.size(), n_ref)) break;
+        ++good;
+        x += 4 + le32(b.data.data() + x);
+        if (x == b.data.size() && b.eof) break;   // the chain ends with the file
+      }
+      if (good >= 8 || (good >= 1 && b.eof && x == b.data.size())) {
+        p = cand;
+        break;
+      }
+    }
+    if (p == SIZE_MAX) return fail(r, BAMCOLS_ERR_FORMAT, "no record boundary found behind offset %zu while planning shards", q);
+    // walk on to the first record whose trimmed name differs from its predecessor's: shards never split a read
+    std::string prev;
+    bool have_prev = false;
+    for (;;) {
+      while (p + 4 > b.data.size() || p + 4 + le32(b.data.data() + p) > b.data.size()) {
+        if (b.eof) break;
+        rc = plan_more(r, b, 16);
+        if (rc < 0) return rc;
+      }
+      if (p + 4 > b.data.size() || p + 4 + le32(b.data.data() + p) > b.data.size()) {
+        p = SIZE_MAX;   // the file ends inside this read: the shard is empty
+        break;
+      }
+      const uint8_t* c = b.data.data() + p + 4;
+      const size_t l_name = c[8];
+      const char* nm = (const char*)c + 32;
+      const size_t tl = trimmed_len(nm, l_name ? l_name - 1 : 0);
+      if (have_prev && (tl != prev.size() || memcmp(nm, prev.data(), tl) != 0)) break;
+      prev.assign(nm, tl);
+      have_prev = true;
+      p += 4 + le32(b.data.data() + p);
+    }
+    if (p != SIZE_MAX) voffsets[k] = plan_voffset(b, p);
+  }
+  // shards are contiguous and in order; a shard that would start before its predecessor's start (one read
+  // reaching over several targets) starts where that one does and the predecessor is empty
+  for (int k = n_shards - 1; k >= 1; --k)
+    if (voffsets[k] < 0) voffsets[k] = k + 1 < n_shards ? voffsets[k + 1] : -1;
+  for (int k = 1; k < n_shards; ++k)
+    if (voffsets[k] >= 0 && voffsets[k] < voffsets[k - 1]) voffsets[k] = voffsets[k - 1];
+  return BAMCOLS_OK;
+}
+
+int bamcols_set_range(bamcols* r, int64_t vbegin, int64_t vend) {
+  if (!r) return BAMCOLS_ERR_INVALID;
+  if (r->mode != 0) return fail(r, BAMCOLS_ERR_INVALID, "bamcols_set_range must come before the first bamcols_emit");
+  if (r->prefetch.joinable()) r->prefetch.join();   // whatever it inflated belongs to the unranged reader
+  if (vbegin < 0) {   // an empty shard at the end of the file
+    r->wpos = r->wend = 0;
+    r->file_done = true;
+    return BAMCOLS_OK;
+  }
+  if (vbegin < r->first_voffset) return fail(r, BAMCOLS_ERR_INVALID, "range begins inside the BAM header");
+  if (vend >= 0 && vend < vbegin) return fail(r, BAMCOLS_ERR_INVALID, "range ends before it begins");
+  r->end_c = vend < 0 ? SIZE_MAX : (size_t)(vend >> 16);
+  r->end_u = vend < 0 ? 0u : (uint32_t)(vend & 0xFFFF);
+  r->cpos = (size_t)(vbegin >> 16);
+  r->wpos = r->wend = 0;
+  r->file_done = false;
+  r->prefetch_rc = 0;
+  if (vend >= 0 && vend == vbegin) {
+    r->file_done = true;
+    return BAMCOLS_OK;
+  }
+  const int rc = refill(r);
+  if (rc < 0) return rc;
+  const size_t skip = (size_t)(vbegin & 0xFFFF);
+  if (skip > r->wend) return fail(r, BAMCOLS_ERR_INVALID, "range begins beyond its block");
+  r->wpos = skip;
+  return BAMCOLS_OK;
 }
 
 int bamcols_track_ranges(bamcols* r, int enable) {

@@ -1016,6 +1016,20 @@ int ecb_get_stats(const ecb_ctx* c, ecb_stats* out) {
   return ECB_OK;
 }
 
+int ecb_rebase(ecb_ctx* c, int64_t delta) {
+  if (!c) return ECB_ERR_INVALID;
+  if (delta < 0) return fail(c, ECB_ERR_INVALID, "negative delta");
+  if (c->with_cells) return fail(c, ECB_ERR_INVALID, "ecb_rebase covers the single-sample path only");
+  CK(cudaSetDevice(c->device));
+  if (delta == 0 || !c->table_slots || c->n_ec == 0) return ECB_OK;
+  ecb_rebase_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+      (EcbEntry*)c->table.p, (const u32*)c->ec_slot.p, c->n_ec, (u64)delta);
+  LAUNCH_CHECK("rebase");
+  c->min_base += (u64)delta;
+  c->max_end += (u64)delta;
+  return ECB_OK;
+}
+
 int ecb_export_partition(ecb_ctx* c, int world, ecb_export* out) {
   if (!c || !out) return ECB_ERR_INVALID;
   if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);

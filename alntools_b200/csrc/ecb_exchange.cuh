@@ -391,3 +391,11 @@ __global__ void __launch_bounds__(256) ecb_import_rows_kernel(const long long* _
     for (u32 j = 0; j < len; ++j) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
   }
 }
+
+// Shift the first-occurrence key of every EC of a context by `delta` (ecb_rebase): a rank that decodes one
+// shard of a file learns the global position of its shard only when all ranks have counted theirs.
+__global__ void __launch_bounds__(256) ecb_rebase_kernel(EcbEntry* table, const u32* __restrict__ ec_slot, u32 n_ec,
+                                                         u64 delta) {
+  for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_ec; e += gridDim.x * blockDim.x)
+    table[ec_slot[e]].first += delta;
+}

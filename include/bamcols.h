@@ -88,6 +88,18 @@ const char* bamcols_cells_name(const bamcols_cells* c, int64_t idx);
 int64_t bamcols_emit(bamcols* r, bamcols_cells* cells, int32_t* read_group, int32_t* target_idx, int32_t* hap_idx,
                      int32_t* cell_idx, int64_t capacity, int* done);
 
+/* Shards of ONE file for several readers (one per GPU / process), without temporary files.  The reference plans
+ * chunks as BGZF virtual offsets at read boundaries (alntools/bam_utils.py:1174-1304) and then copies every
+ * chunk into its own temporary BAM (:157-195); here every reader opens the same file and confines itself to
+ * its range.  bamcols_plan_shards: voffsets[n_shards + 1], voffsets[k] = virtual offset (compressed offset of
+ * a block << 16 | offset inside the inflated block) of the first record of shard k - a record whose trimmed
+ * name differs from its predecessor's, at or behind k/n of the compressed bytes; voffsets[0] = first record of
+ * the file, voffsets[n_shards] = -1 (end of file); -1 also marks an empty shard at the end.  The plan depends
+ * on the file only, so every process computes the same one.  bamcols_set_range (before the first
+ * bamcols_emit): the reader emits the records of [vbegin, vend) only (vend = -1: to the end of the file). */
+int bamcols_plan_shards(bamcols* r, int n_shards, int64_t* voffsets);
+int bamcols_set_range(bamcols* r, int64_t vbegin, int64_t vend);
+
 /* Counters so far: records seen (valid or not) and reads started. */
 int64_t bamcols_all_alignments(const bamcols* r);
 int64_t bamcols_n_groups(const bamcols* r);

@@ -166,6 +166,11 @@ const char* ecb_last_error(const ecb_ctx* ctx);
  *      so a SUM all-reduce assembles the final CSR A matrix and the counts on every rank.
  * All pointers marked "device" are device memory of the context's GPU owned by the caller.
  */
+/* Add `delta` (>= 0) to the order key of everything pushed so far: a rank that decodes one shard of a file
+ * pushes with order_base counted from its own first alignment and is moved to its global position once every
+ * rank knows how many alignments the shards in front of it hold.  Single-sample contexts, before the exchange. */
+int ecb_rebase(ecb_ctx* ctx, int64_t delta);
+
 #define ECB_EXPORT_META_WORDS 5
 typedef struct ecb_export {
   int64_t n_ec;                    /* local ECs exported                                           */

@@ -520,3 +520,47 @@ def test_stream_single_pipeline(tmp_path):
         with pytest.raises(RuntimeError, match="push failed"):
             emitter.stream_single(r, _StubBuilder(fail_at=3), chunk_rows=64, pinned=False)
         assert threading.active_count() == before                   # the producer was joined
+
+
+@pytest.mark.parametrize("payload,n_shards", [(300, 2), (300, 5), (4000, 3), (60000, 4), (70, 7)])
+def test_shards_of_one_file_add_up_to_the_file(tmp_path, payload, n_shards):
+    """bamcols_plan_shards / bamcols_set_range (chunks as virtual offsets, no temporary BAMs): the
+    shards are contiguous, start at read boundaries, and their columns concatenated are the file's columns -
+    with records that straddle BGZF blocks (tiny payloads), reads of many alignments around the cuts, names
+    with blanks, filtered records, and more shards than the file can feed."""
+    rng = np.random.default_rng(payload + n_shards)
+    alns = []
+    for read in range(1500):
+        k = 60 if read % 400 == 7 else int(rng.integers(1, 6))
+        name = "read%05d" % read + (" tail words" if read % 5 == 0 else "")
+        for _ in range(k):
+            flag = int(rng.choice([0, 16, 4, 1 | 2 | 64, 1 | 2 | 128]))
+            alns.append((name, flag, int(rng.integers(0, len(REFS)))))
+    path = _write(tmp_path, alns, block_payload=payload)
+    want, _ = _python_single(path)
+    with bamcols.BamColumnReader(path) as r:
+        plan = r.plan_shards(n_shards)
+        whole_all = None
+    assert len(plan) == n_shards + 1 and plan[-1] == -1 and plan[0] > 0
+    starts = [v for v in plan[:-1] if v >= 0]
+    assert starts == sorted(starts)
+    parts, seen_records = [], 0
+    for k in range(n_shards):
+        with bamcols.BamColumnReader(path) as r:
+            r.set_tables(TargetTables(r.references, r.lengths, None))
+            assert r.plan_shards(n_shards) == plan                  # the plan depends on the file only
+            r.set_range(plan[k], plan[k + 1])
+            cols = r.read_all(chunk=1 << 12)
+            seen_records += r.all_alignments
+            parts.append(cols)
+    assert seen_records == want.all_alignments
+    tg = np.concatenate([p["target_idx"] for p in parts])
+    hp = np.concatenate([p["hap_idx"] for p in parts])
+    assert np.array_equal(tg, want.target_idx) and np.array_equal(hp, want.hap_idx)
+    # read boundaries: inside a shard as in the file, and every non-empty shard begins a new read
+    heads = np.concatenate([np.concatenate(([True], p["read_group"][1:] != p["read_group"][:-1])) if len(p["read_group"]) else
+                            np.zeros(0, dtype=bool) for p in parts])
+    want_heads = np.concatenate(([True], want.read_group[1:] != want.read_group[:-1]))
+    assert np.array_equal(heads, want_heads)
+    if payload >= 4000 and n_shards <= 4:
+        assert sum(1 for p in parts if len(p["read_group"])) >= 2   # the work really is split

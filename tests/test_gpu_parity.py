@@ -384,6 +384,34 @@ def test_multigpu_exchange_matches_oracle(native):
     assert out.stdout.count("OK") == 4
 
 
+def test_multigpu_convert_writes_the_golden_files(native):
+    """convert() / the CLI sharded over GPUs (ALNTOOLS_GPUS; one worker process per GPU, shards of the one BAM
+    planned as virtual offsets): golden EC files and a 1.5 M-read file byte-identical at 2 and at all GPUs."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "multigpu_convert_check.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "multigpu convert check: ok" in out.stdout
+
+
+def test_rebase_moves_the_order_keys(native):
+    """ecb_rebase: pushes made with order_base counted from 0 and then moved by a delta give the result of
+    pushes made at their final positions (two contexts merged through the single-GPU exchange emulation would
+    need more plumbing; here: the EC order of ONE context must not change, and finalize must still work)."""
+    from alntools_b200 import synth
+    cols = synth.make_columns(50000, 900, 2, seed=61, mode="diploid", dup_rate=0.02)
+    want = _oracle(cols)
+    with native.EcBuilder(900, 2) as b:
+        b.push(cols["read_group"], cols["target_idx"], cols["hap_idx"], order_base=0)
+        b.rebase(123456789)
+        _assert_same(b.finalize(), want)
+
+
 def test_exchange_primitives_single_gpu(native):
     """The export -> import -> global id path with world = 1..3 emulated on ONE GPU: all partitions
     are imported into owner contexts on the same device and the bitmap 'all-reduce' is a local sum."""

@@ -151,3 +151,30 @@ def test_convert_writes_the_same_file_with_native_and_python_target_sections(tmp
     assert outputs["native"][0] == outputs["python"][0]
     assert outputs["native"][1] == outputs["python"][1]
     assert len(outputs["native"][0]) > 60 and len(outputs["native"][1]) > 60
+
+
+def test_sliced_ec_file_writer_reproduces_the_golden_bytes(tmp_path):
+    """bin_utils.ecsave2_slice: the EC file written in EC-id ranges by several writers (what the ranks of the
+    multi-GPU convert do) is the file ecsave2 writes, for 1, 2, 3 and 5 writers, empty slices included."""
+    import json
+    from conftest import GOLDEN
+    from alntools_b200 import bin_utils
+    with open(os.path.join(GOLDEN, "manifest.json")) as fh:
+        cases = [c for c in json.load(fh) if c["kind"] == "single"]
+    for case in cases:
+        src = os.path.join(GOLDEN, case["ec"])
+        ec = bin_utils.ecload_arrays(src)
+        header = bin_utils.ec_header_bytes(ec["haplotypes"], ec["targets"], ec["lengths"], ec["samples"])
+        indptr, indices, data = ec["a"]
+        counts = ec["n"][2]
+        n_ec, nnz = len(counts), len(indices)
+        for world in (1, 2, 3, 5, n_ec + 3):
+            out = str(tmp_path / ("%s.%d.bin" % (case["name"], world)))
+            per = (n_ec + world - 1) // world
+            for r in range(world):
+                a, b = min(n_ec, r * per), min(n_ec, (r + 1) * per)
+                lo, hi = int(indptr[a]), int(indptr[b])
+                bin_utils.ecsave2_slice(out, header, n_ec, nnz, a, lo, indptr[a:b + 1] - indptr[a], indices[lo:hi],
+                                        data[lo:hi], counts[a:b], create=(r == 0))
+            with open(out, "rb") as x, open(src, "rb") as y:
+                assert x.read() == y.read(), (case["name"], world)
