@@ -1522,6 +1522,11 @@ int bamcols_plan_shards(bamcols* r, int n_shards, int64_t* voffsets) {
     b.next_c = q;
     int rc = plan_more(r, b, 8);
     if (rc < 0) return rc;
+    while (b.data.empty() && !b.eof) {   // (empty blocks)
+      rc = plan_more(r, b, 8);
+      if (rc < 0) return rc;
+    }
+    if (b.data.empty()) continue;   // only the end-of-file marker lies behind the target: an empty shard
     // a record start: eight plausible records in a row (samtools / htslib start every block with one)
     size_t p = SIZE_MAX;
     for (size_t cand = 0; cand + 36 <= b.data.size() && cand < (1u << 17); ++cand) {
