@@ -165,6 +165,7 @@ int sync_counters(ecb_ctx* c) {
   CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(EcbCounters), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->stats.d2h_bytes += sizeof(EcbCounters);
+  c->arena_used = c->h_ctr->arena_used;   // rows reserved by the harvest kernels so far
   return ECB_OK;
 }
 
@@ -334,9 +335,16 @@ void group_geometry(ecb_ctx* c, int64_t n, int* grid, int* chunk_len) {
   *chunk_len = (int)cl;
 }
 
+// Rows of the ECs claimed in this push (ids e0..e1).  No host round trip: the kernels reserve their rows on
+// the device-side arena cursor, the lists of the longer reads are sized on the device, and all four kernels
+// are launched whether their lists turn out empty or not (an empty list costs a few microseconds).
 int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int32_t* hp, int64_t n, u32 e0,
                      u32 e1) {
   if (e1 <= e0) return ECB_OK;
+  // room for one row entry per alignment of this push: the rows of its new ECs come from distinct reads
+  const u64 bound = c->arena_used + (u64)n;
+  if (bound > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
+  CKR(ensure(c, c->arena, (size_t)bound * sizeof(uint2), true));
   HarvestParams H{};
   H.rg = rg; H.tg = tg; H.hp = hp; H.n = (int)n;
   H.n_targets = c->n_targets; H.n_haps = c->n_haps;
@@ -344,48 +352,29 @@ int harvest_new_rows(ecb_ctx* c, const int32_t* rg, const int32_t* tg, const int
   H.ec_len = (const u32*)c->ec_len.p;
   H.e0 = e0; H.e1 = e1;
   H.row_len = (u32*)c->row_len.p;
-  H.row_off = (const u32*)c->row_off.p;
+  H.row_off = (u32*)c->row_off.p;
   H.long_list = (u32*)c->long_list.p;
   H.mid_list = (u32*)c->mid_list.p;
   H.big_list = (u32*)c->big_list.p;
   H.ctr = c->d_ctr;
-  const u32 n_new = e1 - e0;
-  u64 total = 0;
-  if (c->arena_used > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
-  // row offsets from the read lengths (upper bound of the row length); rows never overlap
-  CKR(device_scan<false>(c, H.ec_len + e0, (u32*)c->row_off.p + e0, n_new, (u32)c->arena_used, &total));
-  if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
-  CKR(ensure(c, c->arena, (size_t)(c->arena_used + total) * sizeof(uint2), true));
   H.arena = (uint2*)c->arena.p;
+  const u32 n_new = e1 - e0;
   ecb_harvest_short_kernel<<<grid_for(n_new, 256, c->sm_count * 16), 256, 0, c->stream>>>(H);
   LAUNCH_CHECK("harvest_short");
-  CKR(sync_counters(c));
-  CKR(check_device_error(c));
-  if (c->h_ctr->scratch[1]) {
-    const u32 n_mid = c->h_ctr->scratch[1];
-    ecb_harvest_warp_kernel<<<grid_for((u64)n_mid * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(H, n_mid);
-    LAUNCH_CHECK("harvest_warp");
-    CK(cudaMemsetAsync(&c->d_ctr->scratch[1], 0, sizeof(u32), c->stream));
+  ecb_harvest_warp_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_warp");
+  ecb_harvest_wsort_kernel<<<c->sm_count * 6, 256, (size_t)8 * HARVEST_WSORT_MAX * 4, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_wsort");
+  if (!c->long_attr_set) {
+    CK(cudaFuncSetAttribute(ecb_harvest_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HARVEST_LONG_MAX * 4));
+    c->long_attr_set = true;
   }
-  if (c->h_ctr->scratch[3]) {
-    const u32 n_big = c->h_ctr->scratch[3];
-    const size_t smem = (size_t)8 * HARVEST_WSORT_MAX * 4;
-    ecb_harvest_wsort_kernel<<<grid_for((u64)n_big * 32, 256, c->sm_count * 6), 256, smem, c->stream>>>(H, n_big);
-    LAUNCH_CHECK("harvest_wsort");
-    CK(cudaMemsetAsync(&c->d_ctr->scratch[3], 0, sizeof(u32), c->stream));
-  }
-  const u32 n_long = c->h_ctr->n_long;
-  if (n_long) {
-    if (!c->long_attr_set) {
-      CK(cudaFuncSetAttribute(ecb_harvest_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              HARVEST_LONG_MAX * 4));
-      c->long_attr_set = true;
-    }
-    ecb_harvest_long_kernel<<<grid_for(n_long, 1, c->sm_count * 3), 256, HARVEST_LONG_MAX * 4, c->stream>>>(H, n_long);
-    LAUNCH_CHECK("harvest_long");
-    CK(cudaMemsetAsync(&c->d_ctr->n_long, 0, sizeof(u32), c->stream));
-  }
-  c->arena_used += total;
+  ecb_harvest_long_kernel<<<c->sm_count * 3, 256, HARVEST_LONG_MAX * 4, c->stream>>>(H);
+  LAUNCH_CHECK("harvest_long");
+  // the list counters go back to zero for the next push (the kernels above have read them by then)
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[1], 0, sizeof(u32), c->stream));
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[3], 0, sizeof(u32), c->stream));
+  CK(cudaMemsetAsync(&c->d_ctr->n_long, 0, sizeof(u32), c->stream));
   return ECB_OK;
 }
 
@@ -745,10 +734,11 @@ static int push_one(ecb_ctx* c, const int32_t* read_group, const int32_t* target
     V.ctr = c->d_ctr;
     ecb_verify_kernel<<<grid_for((u64)n, 256, c->sm_count * 16), 256, 0, c->stream>>>(V);
     LAUNCH_CHECK("verify");
-    CKR(sync_counters(c));
-    CKR(check_device_error(c));
   }
-  CK(cudaStreamSynchronize(c->stream));
+  // the push ends with its second (and last) host round trip: the caller's buffers are free again, the
+  // counters (arena cursor, device-side errors of the harvest / verification) are current on the host
+  CKR(sync_counters(c));
+  CKR(check_device_error(c));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); c->stats.group_ms = ms;
   CK(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->stats.harvest_ms = ms;
@@ -873,12 +863,17 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   const int g_ec = grid_for(n_prov, 256, c->sm_count * 8);
   ecb_fin_mark_kernel<<<g_ec, 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_mark");
-  u64 n_kept = 0;
-  CKR(device_scan<true>(c, F.bitmap, (u32*)c->word_rank.p, words, 0, &n_kept));
-  if (n_kept == 0) return fail(c, ECB_ERR_EMPTY, "no equivalence class survives the cell filter");
-  if (!c->with_cells && n_kept != n_prov)
-    return fail(c, ECB_ERR_INVALID, "order_base ranges of different pushes overlap (%llu first positions for %u ECs)",
-                (unsigned long long)n_kept, n_prov);
+  u64 n_kept = n_prov;
+  if (c->with_cells) {
+    CKR(device_scan<true>(c, F.bitmap, (u32*)c->word_rank.p, words, 0, &n_kept));   // the cell filter decides: host round trip
+    if (n_kept == 0) return fail(c, ECB_ERR_EMPTY, "no equivalence class survives the cell filter");
+  } else {
+    // single sample: every EC is kept, so E is known; the count of first-occurrence bits is checked against it
+    // when the one round trip of this call brings it back (it differs when order_base ranges overlapped)
+    CKR(device_scan<true>(c, F.bitmap, (u32*)c->word_rank.p, words, 0, nullptr));
+    const u32 n_blocks = (u32)((words + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    CK(cudaMemcpyAsync(c->h_total + 1, (const u64*)c->scan_partials.p + n_blocks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+  }
   const u64 E = n_kept;
   if (E + 1 > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "more than 2^31 equivalence classes");
 
@@ -895,37 +890,42 @@ int ecb_finalize(ecb_ctx* c, int64_t min_cell_count, ecb_result* out) {
   if (c->with_cells) ecb_fin_rank_kernel<false><<<g_ec, 256, 0, c->stream>>>(F);
   else ecb_fin_rank_kernel<true><<<g_ec, 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rank");
-  u64 Z = 0;
-  {  // row lengths -> indptr; its total and the counters (wide-row count) come back with ONE sync
-    CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, E + 1, 0, nullptr));
+  // row lengths -> indptr; the rows follow at once: the arena's fill (known on the host since the last push)
+  // bounds the number of non-zeros, so the result arrays need not wait for the exact figure
+  CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, E + 1, 0, nullptr));
+  {
     const u32 n_blocks = (u32)((E + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
     CK(cudaMemcpyAsync(c->h_total, (const u64*)c->scan_partials.p + n_blocks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
-    CKR(sync_counters(c));
-    c->stats.d2h_bytes += sizeof(u64);
-    Z = *c->h_total;
+    c->stats.d2h_bytes += 2 * sizeof(u64);
   }
-  if (Z > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix has more than 2^31-1 non-zeros");
-  CKR(ensure(c, c->r_a_indices, std::max<u64>(Z, 1) * 4));
-  CKR(ensure(c, c->r_a_data, std::max<u64>(Z, 1) * 4));
+  const u64 z_bound = std::max<u64>(c->arena_used, 1);
+  if (z_bound > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix may have more than 2^31-1 non-zeros");
+  CKR(ensure(c, c->r_a_indices, z_bound * 4));
+  CKR(ensure(c, c->r_a_data, z_bound * 4));
   F.a_indices = (int32_t*)c->r_a_indices.p;
   F.a_data = (int32_t*)c->r_a_data.p;
   ecb_fin_rows_kernel<<<grid_for(n_prov, 256, c->sm_count * 16), 256, 0, c->stream>>>(F);
   LAUNCH_CHECK("fin_rows");
-  if (c->h_ctr->scratch[2]) {
-    const u32 n_wide = c->h_ctr->scratch[2];
-    ecb_fin_rows_long_kernel<<<grid_for((u64)n_wide * 32, 256, c->sm_count * 8), 256, 0, c->stream>>>(
-        F, (const u32*)c->long_list.p, n_wide);
-    LAUNCH_CHECK("fin_rows_long");
+  ecb_fin_rows_long_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(F, (const u32*)c->long_list.p, 0xFFFFFFFFu);   // (count on the device)
+  LAUNCH_CHECK("fin_rows_long");
+  CellResult cr2 = cr;
+  if (c->with_cells) CKR(cells_emit(c, &cr2, (const u32*)c->ecid_of.p, E));   // N matrix as CSC
+  else {
+    ecb_set_pair_kernel<<<1, 1, 0, c->stream>>>((int32_t*)c->r_n_indptr.p, 0, (int32_t)E);
+    LAUNCH_CHECK("set_pair");
   }
+  CKR(sync_counters(c));   // the round trip of this call: non-zeros, first-occurrence bits, device-side errors
+  CKR(check_device_error(c));
+  const u64 Z = *c->h_total;
+  if (!c->with_cells && c->h_total[1] != n_prov)
+    return fail(c, ECB_ERR_INVALID, "order_base ranges of different pushes overlap (%llu first positions for %u ECs)",
+                (unsigned long long)c->h_total[1], n_prov);
+  if (Z > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "A matrix has more than 2^31-1 non-zeros");
 
   int64_t n_samples = 1, nnz_n = (int64_t)E;
   if (c->with_cells) {
-    CKR(cells_emit(c, &cr, (const u32*)c->ecid_of.p, E));   // N matrix as CSC
-    n_samples = cr.n_kept_cells;
-    nnz_n = cr.nnz_n;
-  } else {
-    ecb_set_pair_kernel<<<1, 1, 0, c->stream>>>((int32_t*)c->r_n_indptr.p, 0, (int32_t)E);
-    LAUNCH_CHECK("set_pair");
+    n_samples = cr2.n_kept_cells;
+    nnz_n = cr2.nnz_n;
   }
 
   out->n_ec = (int64_t)E;
@@ -1140,6 +1140,8 @@ int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* ro
         (const u32*)c->row_len.p, (const u32*)c->row_off.p, (uint2*)c->arena.p, e0, e1);
     LAUNCH_CHECK("import_rows");
     c->arena_used += total;
+    c->h_ctr->arena_used = c->arena_used;   // the device-side cursor follows (pushes reserve rows there)
+    CK(cudaMemcpyAsync(&c->d_ctr->arena_used, &c->h_ctr->arena_used, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;

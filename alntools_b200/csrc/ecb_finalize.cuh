@@ -94,12 +94,13 @@ __global__ void __launch_bounds__(256) ecb_fin_rows_kernel(const FinalizeParams 
   }
 }
 
-// Rows with more than 8 entries: one warp per row.  With a list (n_wide entries of P.wide_list) only
-// those rows are visited; without one (list == NULL) every EC is looked at.
+// Rows with more than 8 entries: one warp per row.  With a list (n_wide entries of P.wide_list; 0xFFFFFFFF =
+// as many as *P.wide_count says) only those rows are visited; without one (list == NULL) every EC is looked at.
 __global__ void __launch_bounds__(256) ecb_fin_rows_long_kernel(const FinalizeParams P, const u32* list, u32 n_wide) {
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
+  if (n_wide == 0xFFFFFFFFu) n_wide = *P.wide_count;   // the list was counted on the device (same stream, earlier launch)
   const u32 n_items = list ? n_wide : P.n_ec;
   for (u32 i = warp_global; i < n_items; i += n_warps) {
     const u32 e = list ? list[i] : i;

@@ -5,8 +5,10 @@
 // canonicalisation scipy performs in alntools/bin_utils.py:208-211 (sum of 2^h * data[h], tocsr()
 // with sorted column indices).  Runs at the end of every push, while the caller's columns are still
 // valid, over the ECs claimed in that push only (E rows, not R reads).  The grouping kernel recorded
-// for every new EC the offset and the length of one read with that key; row offsets come from an
-// exclusive scan of those lengths (an upper bound of the row length).
+// for every new EC the offset and the length of one read with that key.  A row's place in the arena is
+// reserved when its length is known, with one atomic per warp (short reads) or per row (the rare long
+// ones) on the arena cursor: no scan, no host round trip; the host only provides room for one row entry
+// per alignment of the push, which is an upper bound.
 //   k <= 8        one thread per EC: 8-element sorting network in registers
 //   8 < k <= 32   one warp per EC: __match_any_sync / __reduce_or_sync, rank by counting
 //   32 < k <= 1024  one warp per EC: warp-synchronous bitonic sort in shared memory (no CTA barrier)
@@ -24,15 +26,37 @@ struct HarvestParams {
   const u32* ec_len;
   u32 e0, e1;        // provisional ids claimed in this push
   u32* row_len;      // [capacity] out: row length
-  const u32* row_off;  // [capacity] absolute offsets inside the arena
+  u32* row_off;      // [capacity] out: absolute offset inside the arena (reserved here)
   uint2* arena;      // (target, mask) pairs
   int n_targets, n_haps;  // bounds of the column values (checked here, off the streaming path)
   u32* long_list;    // provisional ids whose read has more than 32 alignments
   u32* mid_list;     // provisional ids whose read has 9..32 alignments
   u32* big_list;     // provisional ids whose read has 33..HARVEST_WSORT_MAX alignments
   EcbCounters* ctr;  // scratch[1] = #ECs with 8 < k <= 32, scratch[3] = #ECs with 32 < k <= HARVEST_WSORT_MAX,
-                     // n_long = #ECs with more
+                     // n_long = #ECs with more; arena_used = the arena cursor
 };
+
+// Reserve `cnt` arena entries for every lane of the (fully converged) warp: one atomic per warp.
+__device__ __forceinline__ u32 harvest_warp_reserve(EcbCounters* ctr, u32 cnt) {
+  const int lane = threadIdx.x & 31;
+  u32 inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(ECB_FULL, inc, d);
+    if (lane >= d) inc += o;
+  }
+  const u32 total = __shfl_sync(ECB_FULL, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total) base = atomicAdd((unsigned long long*)&ctr->arena_used, (unsigned long long)total);
+  base = __shfl_sync(ECB_FULL, base, 31);
+  return (u32)base + inc - cnt;
+}
+// ... for one row, by one lane of a warp (the others get the value too).
+__device__ __forceinline__ u32 harvest_row_reserve(EcbCounters* ctr, u32 cnt, int lane) {
+  unsigned long long base = 0;
+  if (lane == 0 && cnt) base = atomicAdd((unsigned long long*)&ctr->arena_used, (unsigned long long)cnt);
+  return (u32)__shfl_sync(ECB_FULL, base, 0);
+}
 
 #define HARVEST_LONG_MAX 16384
 #define HARVEST_WSORT_MAX 1024   // longest read whose row one warp sorts on its own
@@ -59,24 +83,28 @@ __device__ __forceinline__ void warp_append(u32* list, u32* counter, bool take, 
 }
 
 __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestParams P) {
-  for (u32 e = P.e0 + blockIdx.x * blockDim.x + threadIdx.x; e < P.e1; e += gridDim.x * blockDim.x) {
-    const u32 k = P.ec_len[e];
-    warp_append(P.mid_list, &P.ctr->scratch[1], k > 8 && k <= 32, e);
-    warp_append(P.big_list, &P.ctr->scratch[3], k > 32 && k <= HARVEST_WSORT_MAX, e);
-    if (k > 8) {
-      if (k > HARVEST_WSORT_MAX) {
-        if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
-        P.long_list[atomicAdd(&P.ctr->n_long, 1u)] = e;
-      }
-      continue;
+  // whole warps walk the id range together (the reservation below is a warp-wide step)
+  const u32 n_new = P.e1 - P.e0;
+  const u32 stride = gridDim.x * blockDim.x;
+  for (u32 i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n_new; i0 += stride) {
+    const u32 i = i0 + (threadIdx.x & 31u);
+    const bool in = i < n_new;
+    const u32 e = P.e0 + (in ? i : 0u);
+    const u32 k = in ? P.ec_len[e] : 0u;
+    warp_append(P.mid_list, &P.ctr->scratch[1], in && k > 8 && k <= 32, e);
+    warp_append(P.big_list, &P.ctr->scratch[3], in && k > 32 && k <= HARVEST_WSORT_MAX, e);
+    if (in && k > HARVEST_WSORT_MAX) {
+      if (k > HARVEST_LONG_MAX) atomicOr(&P.ctr->error, ECB_DEVERR_READ_TOO_LONG);
+      P.long_list[atomicAdd(&P.ctr->n_long, 1u)] = e;
     }
-    const int s = (int)P.ec_rep[e];
+    const bool mine = in && k <= 8;
+    const int s = (int)(mine ? P.ec_rep[e] : 0u);
     u32 c[8];
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       c[j] = 0xFFFFFFFFu;
-      if ((u32)j < k) {
+      if (mine && (u32)j < k) {
         const int t = P.tg[s + j], h = P.hp[s + j];
         bad |= (u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps;
         c[j] = ecb_code(t, h);
@@ -90,29 +118,38 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
     ECB_CSWAP(c[0], c[4]) ECB_CSWAP(c[1], c[5]) ECB_CSWAP(c[2], c[6]) ECB_CSWAP(c[3], c[7])
     ECB_CSWAP(c[2], c[4]) ECB_CSWAP(c[3], c[5])
     ECB_CSWAP(c[1], c[2]) ECB_CSWAP(c[3], c[4]) ECB_CSWAP(c[5], c[6])
-    uint2* out = P.arena + P.row_off[e];
-    u32 cnt = 0, prev_t = 0xFFFFFFFFu, mask = 0;
+    // row length = distinct targets; then the row goes to the place reserved for it
+    u32 cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c[j] != 0xFFFFFFFFu && (j == 0 || (c[j] >> 5) != (c[j - 1] >> 5))) ++cnt;
+    const u32 off = harvest_warp_reserve(P.ctr, cnt);
+    if (!mine) continue;
+    uint2* out = P.arena + off;
+    u32 w = 0, prev_t = 0xFFFFFFFFu, mask = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (c[j] != 0xFFFFFFFFu) {
         const u32 t = c[j] >> 5;
         if (t != prev_t) {
-          if (cnt) out[cnt - 1] = make_uint2(prev_t, mask);
-          ++cnt;
+          if (w) out[w - 1] = make_uint2(prev_t, mask);
+          ++w;
           prev_t = t;
           mask = 0;
         }
         mask |= 1u << (c[j] & 31u);
       }
     }
-    if (cnt) out[cnt - 1] = make_uint2(prev_t, mask);
+    if (w) out[w - 1] = make_uint2(prev_t, mask);
     P.row_len[e] = cnt;
+    P.row_off[e] = off;
   }
 }
 
 // Rows of reads with 9..32 alignments (listed by the short kernel): one warp per EC, one alignment
 // per lane.
-__global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P, u32 n_mid) {
+__global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P) {
+  const u32 n_mid = P.ctr->scratch[1];   // listed by the short kernel (same stream, earlier launch)
   const int lane = threadIdx.x & 31;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -133,15 +170,20 @@ __global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestPara
       const int tj = __shfl_sync(ECB_FULL, t, j);
       rank += ((leaders >> j) & 1u) && tj < t;
     }
-    if (leader) P.arena[(size_t)P.row_off[e] + rank] = make_uint2((u32)t, mask);
-    if (lane == 0) P.row_len[e] = (u32)__popc(leaders);
+    const u32 off = harvest_row_reserve(P.ctr, (u32)__popc(leaders), lane);
+    if (leader) P.arena[(size_t)off + rank] = make_uint2((u32)t, mask);
+    if (lane == 0) {
+      P.row_len[e] = (u32)__popc(leaders);
+      P.row_off[e] = off;
+    }
   }
 }
 
 // Rows of reads with 33..HARVEST_WSORT_MAX alignments (heavy multimapping): one WARP per EC.  The
 // element codes are sorted with a bitonic network in the warp's own slice of shared memory, so the only
 // synchronisation is __syncwarp; then one entry per distinct target.
-__global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestParams P, u32 n_big) {
+__global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestParams P) {
+  const u32 n_big = P.ctr->scratch[3];
   extern __shared__ u32 sm_all[];
   const int lane = threadIdx.x & 31;
   u32* codes = sm_all + (threadIdx.x >> 5) * HARVEST_WSORT_MAX;
@@ -181,7 +223,15 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
         __syncwarp();
       }
     }
-    uint2* out = P.arena + (size_t)P.row_off[e];
+    // distinct targets first (the row's length), then the row at its reserved place
+    u32 n_rows = 0;
+    for (u32 base = 0; base < k; base += 32) {
+      const u32 i = base + lane;
+      const bool start = i < k && ((i == 0) || ((codes[i - 1] >> 5) != (codes[i] >> 5)));
+      n_rows += (u32)__popc(__ballot_sync(ECB_FULL, start));
+    }
+    const u32 off = harvest_row_reserve(P.ctr, n_rows, lane);
+    uint2* out = P.arena + (size_t)off;
     u32 run = 0;
     for (u32 base = 0; base < k; base += 32) {
       const u32 i = base + lane;
@@ -199,17 +249,22 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
       }
       run += (u32)__popc(m);
     }
-    if (lane == 0) P.row_len[e] = run;
+    if (lane == 0) {
+      P.row_len[e] = run;
+      P.row_off[e] = off;
+    }
     __syncwarp();
   }
 }
 
 // Rows of long reads (HARVEST_WSORT_MAX+1 .. HARVEST_LONG_MAX alignments): one CTA per EC, bitonic sort of the element
 // codes in shared memory, then one entry per distinct target.
-__global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestParams P, u32 n_long) {
+__global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestParams P) {
+  const u32 n_long = P.ctr->n_long;
   extern __shared__ u32 sm_codes[];
   __shared__ u32 s_scan[9];
   __shared__ u32 s_run;
+  __shared__ u32 s_off;
   for (u32 li = blockIdx.x; li < n_long; li += gridDim.x) {
     const u32 e = P.long_list[li];
     const int s = (int)P.ec_rep[e];
@@ -241,9 +296,22 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
         __syncthreads();
       }
     }
+    // distinct targets first (the row's length), then the row at its reserved place
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
-    const size_t out0 = (size_t)P.row_off[e];
+    {
+      u32 mine = 0;
+      for (u32 i = threadIdx.x; i < k; i += blockDim.x)
+        mine += ((i == 0) || ((sm_codes[i - 1] >> 5) != (sm_codes[i] >> 5))) ? 1u : 0u;
+      if (mine) atomicAdd(&s_run, mine);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_off = (u32)atomicAdd((unsigned long long*)&P.ctr->arena_used, (unsigned long long)s_run);
+      s_run = 0;
+    }
+    __syncthreads();
+    const size_t out0 = (size_t)s_off;
     for (u32 base = 0; base < k; base += blockDim.x) {
       const u32 i = base + threadIdx.x;
       bool start = false;
@@ -263,7 +331,10 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
       if (threadIdx.x == 0) s_run += total;
       __syncthreads();
     }
-    if (threadIdx.x == 0) P.row_len[e] = s_run;
+    if (threadIdx.x == 0) {
+      P.row_len[e] = s_run;
+      P.row_off[e] = s_off;
+    }
     __syncthreads();
   }
 }
