@@ -36,20 +36,17 @@ struct HarvestParams {
                      // n_long = #ECs with more; arena_used = the arena cursor
 };
 
-// Reserve `cnt` arena entries for every lane of the (fully converged) warp: one atomic per warp.
-__device__ __forceinline__ u32 harvest_warp_reserve(EcbCounters* ctr, u32 cnt) {
-  const int lane = threadIdx.x & 31;
-  u32 inc = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const u32 o = __shfl_up_sync(ECB_FULL, inc, d);
-    if (lane >= d) inc += o;
-  }
-  const u32 total = __shfl_sync(ECB_FULL, inc, 31);
-  unsigned long long base = 0;
-  if (lane == 31 && total) base = atomicAdd((unsigned long long*)&ctr->arena_used, (unsigned long long)total);
-  base = __shfl_sync(ECB_FULL, base, 31);
-  return (u32)base + inc - cnt;
+// Reserve `cnt` arena entries for every thread of the (fully converged) 256-thread CTA: ONE atomic per CTA
+// (all reservations hit the same cursor; one per warp - 127 k for 4 M ECs - serialise at the L2 and were
+// measured to cost more than the scan they replaced).  `smem` needs 10 u32.
+__device__ __forceinline__ u32 harvest_block_reserve(EcbCounters* ctr, u32 cnt, u32* smem) {
+  u32 total;
+  const u32 excl = block_excl_scan_u32(cnt, smem, total);
+  if (threadIdx.x == 0) smem[9] = total ? (u32)atomicAdd((unsigned long long*)&ctr->arena_used, (unsigned long long)total) : 0u;
+  __syncthreads();
+  const u32 base = smem[9];
+  __syncthreads();
+  return base + excl;
 }
 // ... for one row, by one lane of a warp (the others get the value too).
 __device__ __forceinline__ u32 harvest_row_reserve(EcbCounters* ctr, u32 cnt, int lane) {
@@ -83,11 +80,12 @@ __device__ __forceinline__ void warp_append(u32* list, u32* counter, bool take, 
 }
 
 __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestParams P) {
-  // whole warps walk the id range together (the reservation below is a warp-wide step)
+  // whole CTAs walk the id range together (the reservation below is a CTA-wide step)
+  __shared__ u32 s_scan[10];
   const u32 n_new = P.e1 - P.e0;
   const u32 stride = gridDim.x * blockDim.x;
-  for (u32 i0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n_new; i0 += stride) {
-    const u32 i = i0 + (threadIdx.x & 31u);
+  for (u32 i0 = blockIdx.x * blockDim.x; i0 < n_new; i0 += stride) {
+    const u32 i = i0 + threadIdx.x;
     const bool in = i < n_new;
     const u32 e = P.e0 + (in ? i : 0u);
     const u32 k = in ? P.ec_len[e] : 0u;
@@ -123,7 +121,7 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (c[j] != 0xFFFFFFFFu && (j == 0 || (c[j] >> 5) != (c[j - 1] >> 5))) ++cnt;
-    const u32 off = harvest_warp_reserve(P.ctr, cnt);
+    const u32 off = harvest_block_reserve(P.ctr, cnt, s_scan);
     if (!mine) continue;
     uint2* out = P.arena + off;
     u32 w = 0, prev_t = 0xFFFFFFFFu, mask = 0;
