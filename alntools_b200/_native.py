@@ -78,6 +78,9 @@ SIGNATURES = {
     "ecb_arena_open_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ecb_arena_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "ecb_rebase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
+    "ecb_order_dispatch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "ecb_order_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(EcbSlice)]),
     "ecb_export_to_arenas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                             ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
                                             ctypes.POINTER(ctypes.c_int64)]),
@@ -309,6 +312,26 @@ class EcBuilder(object):
         """After global_count: send every owned EC (id, count, row) to the rank that assembles its id range."""
         arr = (ctypes.c_void_p * len(bases))(*bases)
         self._check(self._lib.ecb_slice_dispatch(self._ctx, len(bases), arr, int(cap_records), int(cap_rows)))
+
+    def order_dispatch(self, bases, cap_records, cap_rows, shard_lo, shard_hi):
+        """Send every owned EC (position inside its shard, count, row) to the rank whose shard of the read
+        order holds its first occurrence (shard_lo / shard_hi: one entry per rank)."""
+        arr = (ctypes.c_void_p * len(bases))(*bases)
+        lo = (ctypes.c_int64 * len(bases))(*[int(x) for x in shard_lo])
+        hi = (ctypes.c_int64 * len(bases))(*[int(x) for x in shard_hi])
+        self._check(self._lib.ecb_order_dispatch(self._ctx, len(bases), arr, int(cap_records), int(cap_rows), lo, hi))
+
+    def order_build(self, shard_lo, shard_hi):
+        """-> dict(n_ec, nnz, a_indptr, a_indices, a_data, n_data): the ECs whose first occurrence lies in this
+        rank's shard, in id order, as torch views of library memory (valid until the next call)."""
+        import torch
+        sl = EcbSlice()
+        self._check(self._lib.ecb_order_build(self._ctx, int(shard_lo), int(shard_hi), ctypes.byref(sl)))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        view = lambda p, n: _device_view(ctypes.cast(p, ctypes.c_void_p).value, (n,), "<i4", torch.int32, dev)
+        return {"n_ec": int(sl.n_ec), "nnz": int(sl.nnz), "a_indptr": view(sl.a_indptr, sl.n_ec + 1),
+                "a_indices": view(sl.a_indices, max(sl.nnz, 1))[:sl.nnz], "a_data": view(sl.a_data, max(sl.nnz, 1))[:sl.nnz],
+                "n_data": view(sl.n_data, max(sl.n_ec, 1))[:sl.n_ec]}
 
     def slice_build(self, rank, world):
         """-> dict(id_base, n_ec, nnz, a_indptr, a_indices, a_data, n_data): this rank's EC-id range of the

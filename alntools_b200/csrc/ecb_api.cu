@@ -1182,7 +1182,9 @@ int ecb_arena_reset(ecb_ctx* c) {
   if (!c || !c->xa_base) return ECB_ERR_INVALID;
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(c->xa_base, 0, ECB_ARENA_HEADER_BYTES, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  // on a caller-provided stream (ecb_set_stream) the call is stream-ordered - a collective on that stream is the
+  // barrier in front of the peers' stores; a context on its own stream synchronises
+  if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;
 }
 
@@ -1216,7 +1218,10 @@ int ecb_export_to_arenas(ecb_ctx* c, int world, void* const* arena_bases, int64_
   A.cap_rows = (unsigned long long)cap_rows;
   ecb_export_to_arenas_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
   LAUNCH_CHECK("export_to_arenas");
-  CK(cudaStreamSynchronize(c->stream));   // remote stores are complete (and visible to the owner) when the kernel is
+  // remote stores are complete (and visible to the owner) when the kernel is.  On a caller-provided stream the
+  // caller's next collective on that stream is the barrier between the stores and the owner's merge - no host
+  // round trip here; a context on its own stream synchronises
+  if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;
 }
 
@@ -1325,6 +1330,101 @@ int ecb_slice_build(ecb_ctx* c, int rank, int world, ecb_slice* out) {
   }
   CK(cudaStreamSynchronize(c->stream));
   out->id_base = (int64_t)base;
+  out->n_ec = (int64_t)n_local;
+  out->nnz = (int64_t)nnz;
+  out->a_indptr = (const int32_t*)c->r_a_indptr.p;
+  out->a_indices = (const int32_t*)c->r_a_indices.p;
+  out->a_data = (const int32_t*)c->r_a_data.p;
+  out->n_data = (const int32_t*)c->r_n_data.p;
+  return ECB_OK;
+}
+
+int ecb_order_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
+                       const int64_t* shard_lo, const int64_t* shard_hi) {
+  if (!c || !arena_bases || !shard_lo || !shard_hi || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;
+  if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
+  if (cap_rows >= (1ll << 40)) return fail(c, ECB_ERR_LIMIT, "arena rows must stay below 2^40");
+  CK(cudaSetDevice(c->device));
+  if (c->n_ec == 0) return ECB_OK;
+  OrderDispatchParams P{};
+  P.table = (const EcbEntry*)c->table.p;
+  P.ec_slot = (const u32*)c->ec_slot.p;
+  P.row_len = (const u32*)c->row_len.p;
+  P.row_off = (const u32*)c->row_off.p;
+  P.arena = (const uint2*)c->arena.p;
+  P.n_ec = c->n_ec;
+  P.world = (u32)world;
+  // shards with alignments, by position; they must not overlap (one read order over all ranks)
+  std::vector<int> order;
+  for (int r = 0; r < world; ++r)
+    if (shard_hi[r] > shard_lo[r]) order.push_back(r);
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return shard_lo[a] < shard_lo[b]; });
+  if (order.empty()) return fail(c, ECB_ERR_STATE, "no rank has pushed alignments");
+  for (size_t k = 0; k < order.size(); ++k) {
+    if (k && shard_lo[order[k]] < shard_hi[order[k - 1]])
+      return fail(c, ECB_ERR_INVALID, "the ranks' order_base ranges overlap");
+    if (shard_hi[order[k]] - shard_lo[order[k]] > 0xFFFFFFFEll)
+      return fail(c, ECB_ERR_LIMIT, "a rank's alignments span more than 2^32 positions");
+    P.lo[k] = (u64)shard_lo[order[k]];
+    P.dest[k] = (u32)order[k];
+  }
+  P.n_shards = (u32)order.size();
+  ArenaTargets A{};
+  for (int r = 0; r < world; ++r)
+    if (!arena_bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
+  arena_targets(&A, world, arena_bases, cap_records, cap_rows);
+  ecb_order_dispatch_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
+  LAUNCH_CHECK("order_dispatch");
+  if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));   // (as ecb_export_to_arenas)
+  return ECB_OK;
+}
+
+int ecb_order_build(ecb_ctx* c, int64_t shard_lo, int64_t shard_hi, ecb_slice* out) {
+  if (!c || !out || !c->xa_base || shard_hi < shard_lo) return ECB_ERR_INVALID;
+  memset(out, 0, sizeof *out);
+  CK(cudaSetDevice(c->device));
+  unsigned long long hdr[3] = {0, 0, 0};
+  CK(cudaMemcpyAsync(hdr, c->xa_base, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (hdr[2]) return fail(c, ECB_ERR_LIMIT, "exchange arena too small for the ordering dispatch");
+  const u64 n_local = hdr[0], nnz = hdr[1];
+  const u64 span = (u64)(shard_hi - shard_lo);
+  if (span > 0xFFFFFFFEull) return fail(c, ECB_ERR_LIMIT, "a rank's alignments span more than 2^32 positions");
+  if (n_local > span) return fail(c, ECB_ERR_INVALID, "%llu ECs arrived for a shard of %llu positions", hdr[0], (unsigned long long)span);
+  if (nnz > 0x7FFFFFFFull || n_local + 1 > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "slice exceeds the int32 fields of the EC file");
+  const char* b = (const char*)c->xa_base;
+  const unsigned long long* rec = (const unsigned long long*)(b + ECB_ARENA_HEADER_BYTES);
+  const int2* rows = (const int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)c->xa_cap_ec * ECB_META_WORDS * 8);
+  const size_t words = (size_t)(span / 32) + 1;
+  CKR(ensure(c, c->bitmap, words * 4));
+  CKR(ensure(c, c->word_rank, words * 4));
+  CKR(ensure(c, c->r_a_indptr, (n_local + 1) * 4));
+  CKR(ensure(c, c->r_n_data, std::max<u64>(n_local, 1) * 4));
+  CKR(ensure(c, c->first_rel, std::max<u64>(n_local, 1) * 8));   // scratch: record index per id
+  CKR(ensure(c, c->r_a_indices, std::max<u64>(nnz, 1) * 4));
+  CKR(ensure(c, c->r_a_data, std::max<u64>(nnz, 1) * 4));
+  u32* rec_of = (u32*)c->first_rel.p;
+  CK(cudaMemsetAsync(c->bitmap.p, 0, words * 4, c->stream));
+  CK(cudaMemsetAsync(c->r_a_indptr.p, 0, (n_local + 1) * 4, c->stream));
+  CK(cudaMemsetAsync(&c->d_ctr->scratch[5], 0, sizeof(u32), c->stream));
+  if (n_local) {
+    const int g = grid_for(n_local, 256, c->sm_count * 8);
+    ecb_order_mark_kernel<<<g, 256, 0, c->stream>>>(rec, (u32)n_local, (u32)span, (u32*)c->bitmap.p, &c->d_ctr->scratch[5]);
+    LAUNCH_CHECK("order_mark");
+    CKR(device_scan<true>(c, (const u32*)c->bitmap.p, (u32*)c->word_rank.p, words, 0, nullptr));
+    ecb_order_lens_kernel<<<g, 256, 0, c->stream>>>(rec, (u32)n_local, (u32)span, (const u32*)c->bitmap.p,
+                                                    (const u32*)c->word_rank.p, (int32_t*)c->r_a_indptr.p,
+                                                    (int32_t*)c->r_n_data.p, rec_of);
+    LAUNCH_CHECK("order_lens");
+    CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, n_local + 1, 0, nullptr));
+    ecb_slice_rows_kernel<<<grid_for(n_local, 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        rec, rows, rec_of, (const int32_t*)c->r_a_indptr.p, (u32)n_local, (int32_t*)c->r_a_indices.p,
+        (int32_t*)c->r_a_data.p);
+    LAUNCH_CHECK("slice_rows");
+  }
+  CKR(sync_counters(c));
+  if (c->h_ctr->scratch[5]) return fail(c, ECB_ERR_INVALID, "a record outside the shard's positions arrived, or two ECs share a first read");
+  out->id_base = 0;   // the caller knows where this rank's id range starts (the ECs of the shards in front)
   out->n_ec = (int64_t)n_local;
   out->nnz = (int64_t)nnz;
   out->a_indptr = (const int32_t*)c->r_a_indptr.p;

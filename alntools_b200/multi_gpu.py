@@ -4,11 +4,16 @@ The reference's only parallelism is a process pool over contiguous BAM chunks wh
 merged in chunk order (alntools/bam_utils.py:647-724).  Here every rank builds a local EC table from
 its shard (order_base = global offset of the shard) and the merge becomes:
 
-  all-to-all   local ECs, hash-partitioned by owner rank (key, first, count, row)       [NCCL]
+  dispatch 1   local ECs (key, first, count, row) stored straight into the arena of their OWNER rank
+               (hash of the key) over peer memory by one kernel                          [NVLink]
   owner merge  equal keys: counts summed, smallest first-occurrence kept                [kernel]
-  all-reduce   first-occurrence bitmap, OR as SUM of disjoint bits -> global EC ids     [NCCL]
-  all-reduce   row lengths / counts / rows scattered at their global ids (disjoint      [NCCL]
-               supports, so SUM assembles the final CSR on every rank)
+  dispatch 2   every merged EC to the rank whose SHARD holds its first occurrence; there a bitmap over
+               the rank's own positions orders them: ids are ranks of first occurrences and the shards
+               partition the positions, so every rank ends up with one contiguous id range of the
+               final matrices (result_on="slices")                                       [NVLink]
+  The barriers between these steps are tiny collectives on the stream the kernels run on: nothing in
+  between waits for the host.  (result_on="all" / "rank0" and the NCCL / gloo path keep the first form:
+  all-to-all, first-occurrence bitmap OR-ed by an all-reduce, rows scattered at their global ids.)
 
 torch.distributed is the plumbing (process group, collectives on device tensors); every compute
 step is a libecb200 kernel behind the C ABI.  The same orchestration runs on gloo/CPU in the tests
@@ -39,6 +44,19 @@ class _Phases(object):
     def report(self):
         if _TIMING and dist.get_rank() == 0:
             print("distributed_finalize: " + ", ".join("%s %.2f ms" % r for r in self.rows), flush=True)
+
+
+_BARRIER_WORD = {}
+
+
+def _stream_barrier(device, group):
+    """A barrier among the ranks that lives on the CUDA stream: a one-word all-reduce.  Work a rank put on the
+    stream before it is complete (and its peer-memory stores visible) before any rank's work behind it starts;
+    the host does not wait."""
+    key = (device, id(group))
+    if key not in _BARRIER_WORD:
+        _BARRIER_WORD[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.all_reduce(_BARRIER_WORD[key], group=group)
 
 
 def _all_to_all_counts(counts, device, group):
@@ -81,37 +99,69 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
         # over NVLink by ONE kernel (peer memory mapped through CUDA IPC); no staging, no all-to-all
         owner = make_owner()
         owner.set_stream(cur)
-        st = local.stats()
         arena = getattr(owner, "_exchange_arena", None)
-        if arena is not None:
+        if arena is not None and result_on == "slices":
+            # the arenas exist (a later step of the same job): clear the header and put ONE small collective on
+            # the stream as the barrier between "every arena is clear" and "peers store" - no host round trip;
+            # whether everything fits is decided by the overflow flag in the arena header
             owner.arena_reset()
-        info = torch.tensor([st["table_used"], st["row_entries"], 0 if arena is None else arena["cap_ec"],
-                             0 if arena is None else arena["cap_rows"]], dtype=torch.int64, device=device)
-        gathered = [torch.empty_like(info) for _ in range(world)]
-        dist.all_gather(gathered, info, group=group)     # also the barrier between "reset" and "store"
-        g = torch.stack(gathered).tolist()
-        need_ec = 2 * max(r[0] for r in g) + 1024
-        need_rows = 2 * max(r[1] for r in g) + 1024
-        if any(r[2] < need_ec // 2 + 512 or r[3] < need_rows // 2 + 512 for r in g) or arena is None:
+            _stream_barrier(device, group)
+        else:
+            st = local.stats()
             if arena is not None:
-                raise RuntimeError("exchange arena too small for this input; create the owner context per job")
-            handle, base = owner.arena_create(need_ec, need_rows)
-            hs = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
-            dist.all_gather(hs, torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device), group=group)
-            bases = [base if r == me else owner.arena_open_peer(bytes(hs[r].cpu().tolist())) for r in range(world)]
-            arena = {"bases": bases, "cap_ec": need_ec, "cap_rows": need_rows}
-            owner._exchange_arena = arena
-            dist.barrier(group=group)                     # every arena exists and is zeroed
+                owner.arena_reset()
+            info = torch.tensor([st["table_used"], st["row_entries"], 0 if arena is None else arena["cap_ec"],
+                                 0 if arena is None else arena["cap_rows"]], dtype=torch.int64, device=device)
+            gathered = [torch.empty_like(info) for _ in range(world)]
+            dist.all_gather(gathered, info, group=group)     # also the barrier between "reset" and "store"
+            g = torch.stack(gathered).tolist()
+            need_ec = 2 * max(r[0] for r in g) + 1024
+            need_rows = 2 * max(r[1] for r in g) + 1024
+            if any(r[2] < need_ec // 2 + 512 or r[3] < need_rows // 2 + 512 for r in g) or arena is None:
+                if arena is not None:
+                    raise RuntimeError("exchange arena too small for this input; create the owner context per job")
+                handle, base = owner.arena_create(need_ec, need_rows)
+                hs = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+                dist.all_gather(hs, torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device), group=group)
+                bases = [base if r == me else owner.arena_open_peer(bytes(hs[r].cpu().tolist())) for r in range(world)]
+                arena = {"bases": bases, "cap_ec": need_ec, "cap_rows": need_rows}
+                owner._exchange_arena = arena
+                dist.barrier(group=group)                     # every arena exists and is zeroed
         ph.mark("setup")
         min_base, max_end = local.export_to_arenas(arena["bases"], arena["cap_ec"], arena["cap_rows"])
         ph.mark("export+store")
+        if result_on == "slices":
+            # every rank's shard of the read order; the all-gather is the barrier between "store" and "merge"
+            mine = torch.tensor([min_base, max_end], dtype=torch.int64, device=device)
+            spans = torch.empty(2 * world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(spans, mine, group=group)
+            owner.import_arena()
+            owner.arena_reset()              # reused by the second dispatch ...
+            _stream_barrier(device, group)   # ... once every rank has merged what it received
+            ph.mark("import")
+            spans = spans.tolist()           # (import_arena has synchronised already)
+            lo, hi = spans[0::2], spans[1::2]
+            if not any(h > l for l, h in zip(lo, hi)):
+                raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
+            owner.order_dispatch(arena["bases"], arena["cap_ec"], arena["cap_rows"], lo, hi)
+            _stream_barrier(device, group)   # every rank's ECs have landed
+            ph.mark("order dispatch")
+            sl = owner.order_build(lo[me], hi[me])
+            ph.mark("order build")
+            # the id range of a rank starts behind the ECs of the shards in front of it
+            sizes = torch.empty(world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(sizes, torch.tensor([sl["n_ec"]], dtype=torch.int64, device=device), group=group)
+            sizes = sizes.tolist()
+            id_base = sum(n for r, n in enumerate(sizes) if hi[r] > lo[r] and (lo[r], r) < (lo[me], me))
+            ph.report()
+            return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
+                    "n_data": sl["n_data"], "n_ec": sum(sizes), "id_base": id_base, "n_ec_local": sl["n_ec"],
+                    "nnz_local": sl["nnz"], "nnz_a": None}
         span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
         dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)   # the barrier between "store" and "merge"
         g_min, g_max = -int(span[0].item()), int(span[1].item())
         owner.import_arena()
-        if result_on == "slices":
-            owner.arena_reset()          # the arena is reused by the slice dispatch; the bitmap all-reduce
-        ph.mark("import")                # below orders this reset before any peer's second store
+        ph.mark("import")
     else:
         meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
         ph.mark("export")
@@ -149,18 +199,7 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     n_ec = owner.global_count(bitmap)
     ph.mark("count")
     if result_on == "slices":
-        if not p2p:
-            raise RuntimeError('result_on="slices" needs the peer-memory exchange')
-        owner.slice_dispatch(arena["bases"], arena["cap_ec"], arena["cap_rows"])
-        dist.barrier(group=group)        # every rank's rows have landed
-        ph.mark("slice dispatch")
-        sl = owner.slice_build(me, world)
-        ph.mark("slice build")
-        ph.report()
-        return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
-                "n_data": sl["n_data"], "n_ec": n_ec, "id_base": sl["id_base"], "n_ec_local": sl["n_ec"],
-                "nnz_local": sl["nnz"], "nnz_a": None}
-
+        raise RuntimeError('result_on="slices" needs the peer-memory exchange')
     lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=device)
     counts = torch.zeros(n_ec, dtype=torch.int32, device=device)
     owner.global_lens(lens, counts)

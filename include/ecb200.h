@@ -221,6 +221,18 @@ int ecb_slice_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, 
                        int64_t cap_rows);
 int ecb_slice_build(ecb_ctx* owner_ctx, int rank, int world, ecb_slice* out);
 
+/* ---- ordering form of the second dispatch (the default of the multi-GPU path): every merged EC goes to the
+ * rank whose shard [shard_lo[r], shard_hi[r]) of the global read order holds its first occurrence.  EC ids are
+ * ranks of first-occurrence positions and the shards partition the positions, so a rank receives one contiguous
+ * id range and orders it with a bitmap over its OWN positions: no global bitmap, no all-reduce, no
+ * ecb_global_* call.  ecb_order_dispatch on the OWNER context (after ecb_import_arena and ecb_arena_reset, behind
+ * a barrier); after another barrier ecb_order_build turns what arrived into this rank's slice (id_base is left
+ * 0: the slice starts after the ECs of the shards in front, which the caller learns from one all-gather).
+ * Both calls are stream-ordered on the context's stream; the barriers are collectives on the same stream. */
+int ecb_order_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
+                       const int64_t* shard_lo, const int64_t* shard_hi);
+int ecb_order_build(ecb_ctx* owner_ctx, int64_t shard_lo, int64_t shard_hi, ecb_slice* out);
+
 /* Set the first-occurrence bits of the ECs this context owns in bitmap[n_words] (bit i = order key
  * min_base + i).  The caller zero-fills the bitmap and all-reduces it afterwards. */
 int ecb_global_mark(ecb_ctx* ctx, int64_t min_base, uint32_t* bitmap_device, int64_t n_words);

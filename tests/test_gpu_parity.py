@@ -498,6 +498,22 @@ def test_exchange_primitives_single_gpu(native):
                 assert np.array_equal(sl["a_data"].cpu().numpy(), want[2][want[0][a]:want[0][b]])
                 assert np.array_equal(sl["n_data"].cpu().numpy(), want[3][a:b])
                 at = b
+            # ordering form: every EC to the rank whose shard holds its first occurrence; no global bitmap
+            for ob in owners:
+                ob.arena_reset()
+            lo, hi = cuts[:-1], cuts[1:]
+            for ob in owners:
+                ob.order_dispatch(bases, cap_ec, cap_rows, lo, hi)
+            at = 0
+            for r, ob in enumerate(owners):
+                sl = ob.order_build(lo[r], hi[r])
+                a, b = at, at + sl["n_ec"]
+                assert np.array_equal(sl["a_indptr"].cpu().numpy(), want[0][a:b + 1] - want[0][a])
+                assert np.array_equal(sl["a_indices"].cpu().numpy(), want[1][want[0][a]:want[0][b]])
+                assert np.array_equal(sl["a_data"].cpu().numpy(), want[2][want[0][a]:want[0][b]])
+                assert np.array_equal(sl["n_data"].cpu().numpy(), want[3][a:b])
+                at = b
+            assert at == n_ec
             assert at == n_ec
         for b in locals_ + owners:
             b.close()
