@@ -1114,36 +1114,27 @@ int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* ro
   // the owner table must be able to take every incoming record as a new EC without filling up
   const u64 need = ((u64)c->n_ec + n_rec) * 2;
   if (need > c->table_slots) CKR(grow_table(c, pow2_ceil(need)));
-  const u32 e0 = c->n_ec;
+  // room for every received row (each new EC brings one): the kernel reserves what it needs on the device
+  if (c->arena_used + n_rows > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
+  CKR(ensure(c, c->arena, std::max<u64>(c->arena_used + n_rows, 1) * sizeof(uint2), true));
   ImportParams P{};
   P.meta = (const long long*)meta_device;
+  P.rows = (const int2*)rows_device;
+  P.parts = parts;
   P.n_rec = (u32)n_rec;
   P.table = (EcbEntry*)c->table.p;
   P.mask = c->table_slots - 1;
   P.ec_slot = (u32*)c->ec_slot.p;
   P.ec_rep = (u32*)c->ec_rep.p;
   P.row_len = (u32*)c->row_len.p;
+  P.row_off = (u32*)c->row_off.p;
+  P.arena = (uint2*)c->arena.p;
   P.ctr = c->d_ctr;
   ecb_import_insert_kernel<<<grid_for(n_rec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P);
   LAUNCH_CHECK("import_insert");
-  CKR(sync_counters(c));
+  CKR(sync_counters(c));   // the one round trip of the merge: ECs and arena fill are known to the host again
   CKR(check_device_error(c));
   c->n_ec = c->h_ctr->n_ec;
-  const u32 e1 = c->n_ec;
-  if (e1 > e0) {
-    u64 total = 0;
-    CKR(device_scan<false>(c, (const u32*)c->row_len.p + e0, (u32*)c->row_off.p + e0, e1 - e0, (u32)c->arena_used, &total));
-    if (c->arena_used + total > 0xFFFFFFFFull) return fail(c, ECB_ERR_LIMIT, "row arena exceeds 2^32 entries");
-    CKR(ensure(c, c->arena, std::max<u64>(c->arena_used + total, 1) * sizeof(uint2), true));
-    ecb_import_rows_kernel<<<grid_for(e1 - e0, 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        (const long long*)meta_device, (const int2*)rows_device, parts, (const u32*)c->ec_rep.p,
-        (const u32*)c->row_len.p, (const u32*)c->row_off.p, (uint2*)c->arena.p, e0, e1);
-    LAUNCH_CHECK("import_rows");
-    c->arena_used += total;
-    c->h_ctr->arena_used = c->arena_used;   // the device-side cursor follows (pushes reserve rows there)
-    CK(cudaMemcpyAsync(&c->d_ctr->arena_used, &c->h_ctr->arena_used, sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-  }
-  CK(cudaStreamSynchronize(c->stream));
   return ECB_OK;
 }
 

@@ -462,67 +462,79 @@ __global__ void __launch_bounds__(256) ecb_slice_rows_kernel(const unsigned long
   }
 }
 
-struct ImportParams {
-  const long long* meta;
-  u32 n_rec;
-  EcbEntry* table;
-  u32 mask;
-  u32* ec_slot;
-  u32* ec_rep;     // provisional id -> record index of the import that created it
-  u32* row_len;
-  EcbCounters* ctr;
-};
-
-// Merge received records into the owner table: sum counts, min first (bam_utils.py:693-698).
-__global__ void __launch_bounds__(256) ecb_import_insert_kernel(const ImportParams P) {
-  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_rec; i += gridDim.x * blockDim.x) {
-    const long long* m = P.meta + (size_t)i * ECB_META_WORDS;
-    const Key128 key{(u64)m[0], (u64)m[1]};
-    const u64 first = (u64)m[2];
-    const u32 count = (u32)((u64)m[3] >> 32);
-    bool claimed;
-    u64 seen;
-    const u32 slot = table_find_or_claim<true>(P.table, P.mask, key, claimed, seen);
-    if (slot == ECB_NONE) {
-      atomicOr(&P.ctr->error, ECB_DEVERR_EC_CAPACITY);
-      continue;
-    }
-    EcbEntry* e = P.table + slot;
-    atomicAdd(&e->countm1, count);
-    if (first < seen) atomicMin(&e->first, first);
-    const u32 ecl = alloc_ec_ids(P.ctr, claimed);  // one atomic per warp, not per new EC
-    if (claimed) {
-      e->aux = ecl;
-      P.ec_slot[ecl] = slot;
-      P.ec_rep[ecl] = i;
-      P.row_len[ecl] = (u32)((u64)m[3] & 0xFFFFFFFFull);
-    }
-  }
-}
-
 struct PartTable {
   long long row_base[ECB_MAX_WORLD];  // first row of each source partition in the receive buffer
   long long ec_end[ECB_MAX_WORLD];    // cumulative record count after each source partition
   u32 n;
 };
 
-// Copy the rows of the ECs created by this import from the receive buffer into the arena.  One
-// thread per EC: rows are a few entries long and the chain record -> offset -> row is all latency, so
-// millions of independent threads beat a warp per EC.
-__global__ void __launch_bounds__(256) ecb_import_rows_kernel(const long long* __restrict__ meta,
-                                                              const int2* __restrict__ rows, const PartTable parts,
-                                                              const u32* __restrict__ ec_rep,
-                                                              const u32* __restrict__ row_len,
-                                                              const u32* __restrict__ row_off, uint2* arena, u32 e0,
-                                                              u32 e1) {
-  for (u32 e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
-    const u32 rec = ec_rep[e];
-    u32 part = 0;
-    while (part + 1 < parts.n && (long long)rec >= parts.ec_end[part]) ++part;
-    const int2* src = rows + parts.row_base[part] + meta[(size_t)rec * ECB_META_WORDS + 4];
-    uint2* dst = arena + row_off[e];
-    const u32 len = row_len[e];
-    for (u32 j = 0; j < len; ++j) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
+struct ImportParams {
+  const long long* meta;
+  const int2* rows;      // received rows
+  PartTable parts;
+  u32 n_rec;
+  EcbEntry* table;
+  u32 mask;
+  u32* ec_slot;
+  u32* ec_rep;     // provisional id -> record index of the import that created it
+  u32* row_len;
+  u32* row_off;
+  uint2* arena;
+  EcbCounters* ctr;
+};
+
+// Merge received records into the owner table: sum counts, min first (bam_utils.py:693-698); the records that
+// bring a NEW key also get their provisional id and their row's place in the arena here - ids and arena space
+// are reserved once per CTA tile (a reservation per warp would put a hundred thousand atomics on one address)
+// - and their row is copied on the spot: one kernel, no scan, no host round trip in between.
+__global__ void __launch_bounds__(256) ecb_import_insert_kernel(const ImportParams P) {
+  __shared__ u32 s_scan[10];
+  const u32 tiles = (P.n_rec + blockDim.x - 1) / blockDim.x;
+  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const u32 i = tile * blockDim.x + threadIdx.x;
+    const bool live = i < P.n_rec;
+    bool claimed = false;
+    u32 slot = ECB_NONE, len = 0;
+    const long long* m = P.meta + (size_t)(live ? i : 0u) * ECB_META_WORDS;
+    if (live) {
+      const Key128 key{(u64)m[0], (u64)m[1]};
+      const u64 first = (u64)m[2];
+      const u32 count = (u32)((u64)m[3] >> 32);
+      u64 seen;
+      slot = table_find_or_claim<true>(P.table, P.mask, key, claimed, seen);
+      if (slot == ECB_NONE) {
+        atomicOr(&P.ctr->error, ECB_DEVERR_EC_CAPACITY);
+        claimed = false;
+      } else {
+        EcbEntry* e = P.table + slot;
+        atomicAdd(&e->countm1, count);
+        if (first < seen) atomicMin(&e->first, first);
+      }
+      if (claimed) len = (u32)((u64)m[3] & 0xFFFFFFFFull);
+    }
+    // provisional ids and arena space of the tile's new ECs
+    u32 n_new, n_rows;
+    const u32 id_excl = block_excl_scan_u32(claimed ? 1u : 0u, s_scan, n_new);
+    const u32 row_excl = block_excl_scan_u32(len, s_scan, n_rows);
+    if (threadIdx.x == 0) {
+      s_scan[8] = n_new ? atomicAdd(&P.ctr->n_ec, n_new) : 0u;
+      s_scan[9] = n_rows ? (u32)atomicAdd((unsigned long long*)&P.ctr->arena_used, (unsigned long long)n_rows) : 0u;
+    }
+    __syncthreads();
+    const u32 id = s_scan[8] + id_excl, off = s_scan[9] + row_excl;
+    __syncthreads();
+    if (claimed) {
+      P.table[slot].aux = id;
+      P.ec_slot[id] = slot;
+      P.ec_rep[id] = i;
+      P.row_len[id] = len;
+      P.row_off[id] = off;
+      u32 part = 0;
+      while (part + 1 < P.parts.n && (long long)i >= P.parts.ec_end[part]) ++part;
+      const int2* src = P.rows + P.parts.row_base[part] + m[4];
+      uint2* dst = P.arena + off;
+      for (u32 j = 0; j < len; ++j) dst[j] = make_uint2((u32)src[j].x, (u32)src[j].y);
+    }
   }
 }
 
