@@ -231,6 +231,7 @@ def convert_rank(bam_filename, ec_filename, emase_filename, num_chunks=0, number
     start_time = time.time()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    utils.bind_to_gpu_numa_node(local_rank)          # pinned buffers next to this rank's GPU
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     own_group = not dist.is_initialized()

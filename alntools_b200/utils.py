@@ -90,3 +90,26 @@ def write_range_file(range_filename, main_targets, haplotypes, references, range
             fw.write("\t")
             fw.write("\t".join(vals))
             fw.write("\n")
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs next to GPU `device_index` (NVML's ideal affinity) BEFORE it allocates
+    pinned host buffers: first touch then places them in the GPU's own NUMA node.  With one process per GPU
+    and several GPUs copying at once, buffers on the far socket make every host-to-device copy cross the
+    socket interconnect.  Returns the CPU list, or None when NVML is not there / has nothing to say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpus]
+        if not cpus:
+            return None
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(set(cpus) & allowed) or None
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None

@@ -340,6 +340,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU path for the EC build")
+    numa_cpus = None
+    if world > 1:
+        from alntools_b200 import utils as _utils
+        numa_cpus = _utils.bind_to_gpu_numa_node(local_rank)   # before any pinned allocation
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -590,7 +594,9 @@ def main():
                        table_slots=stats_dev["table_slots"], table_grows=stats_dev["table_grows"]),
         "e2e": {"value": total_aln * args.steps / (ms_e2e * 1e-3), "unit": "alignments/s",
                 "h2d_bytes_per_step": stats_e2e["h2d_bytes"] * world, "d2h_bytes_per_step": d2h_e2e,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "host_binding": ("rank processes bound to the CPUs of their GPU's NUMA node (rank 0: %d CPUs)" % len(numa_cpus))
+                if numa_cpus else "none"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "ecb_group_insert_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source, "peak_source": peak_kind,
