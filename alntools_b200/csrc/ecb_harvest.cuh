@@ -48,13 +48,6 @@ __device__ __forceinline__ u32 harvest_block_reserve(EcbCounters* ctr, u32 cnt, 
   __syncthreads();
   return base + excl;
 }
-// ... for one row, by one lane of a warp (the others get the value too).
-__device__ __forceinline__ u32 harvest_row_reserve(EcbCounters* ctr, u32 cnt, int lane) {
-  unsigned long long base = 0;
-  if (lane == 0 && cnt) base = atomicAdd((unsigned long long*)&ctr->arena_used, (unsigned long long)cnt);
-  return (u32)__shfl_sync(ECB_FULL, base, 0);
-}
-
 #define HARVEST_LONG_MAX 16384
 #define HARVEST_WSORT_MAX 1024   // longest read whose row one warp sorts on its own
 
@@ -121,7 +114,13 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (c[j] != 0xFFFFFFFFu && (j == 0 || (c[j] >> 5) != (c[j - 1] >> 5))) ++cnt;
-    const u32 off = harvest_block_reserve(P.ctr, cnt, s_scan);
+    // the rows of longer reads are built by the kernels below; their place is reserved HERE, with the read
+    // length as the upper bound of the row length (rows need not be packed: row_off / row_len index them),
+    // so those kernels need no reservation of their own - one atomic per EC on the arena cursor was most of
+    // their time on heavily multimapping input
+    const u32 want = mine ? cnt : (in ? min(k, (u32)HARVEST_LONG_MAX) : 0u);
+    const u32 off = harvest_block_reserve(P.ctr, want, s_scan);
+    if (in && !mine) P.row_off[e] = off;
     if (!mine) continue;
     uint2* out = P.arena + off;
     u32 w = 0, prev_t = 0xFFFFFFFFu, mask = 0;
@@ -144,36 +143,68 @@ __global__ void __launch_bounds__(256) ecb_harvest_short_kernel(const HarvestPar
   }
 }
 
-// Rows of reads with 9..32 alignments (listed by the short kernel): one warp per EC, one alignment
-// per lane.
+// Rows of reads with 9..32 alignments (listed by the short kernel): one warp per EC, one alignment per lane.
+// The 32 element codes are sorted in registers (bitonic network over shuffles, 15 compare-exchange steps), the
+// haplotype bits of equal targets are OR-ed with a segmented suffix scan, and the first lane of every run
+// writes its (target, mask) at the run's rank.  (A first version grouped the lanes with match_any and reduced
+// every group with its own mask: both serialise over the distinct values - 3.4 ms for 4 M such reads.)
 __global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestParams P) {
   const u32 n_mid = P.ctr->scratch[1];   // listed by the short kernel (same stream, earlier launch)
   const int lane = threadIdx.x & 31;
+  const u32 lt = (1u << lane) - 1u;
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (u32 i = warp_global; i < n_mid; i += n_warps) {
-    const u32 e = P.mid_list[i];
+  // Every EC costs a chain of dependent loads (list -> start / length / row place -> codes) that is far longer
+  // than the sort: the chain of the NEXT two ECs is in flight while the current one is sorted.
+  auto load_code = [&](u32 e, int& k_out, u32& off_out) -> u32 {
     const int k = (int)P.ec_len[e];
     const int s = (int)P.ec_rep[e];
-    const int t = lane < k ? P.tg[s + lane] : -1 - lane;
-    const int h = lane < k ? P.hp[s + lane] : 0;
-    if (lane < k && ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps)) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
-    const u32 hbit = lane < k ? (1u << (h & 31)) : 0u;
-    const u32 grp = __match_any_sync(ECB_FULL, t);
-    const u32 mask = __reduce_or_sync(grp, hbit);
-    const bool leader = lane < k && lane == __ffs(grp) - 1;
-    const u32 leaders = __ballot_sync(ECB_FULL, leader);
-    u32 rank = 0;
-    for (int j = 0; j < k; ++j) {
-      const int tj = __shfl_sync(ECB_FULL, t, j);
-      rank += ((leaders >> j) & 1u) && tj < t;
+    k_out = k;
+    off_out = P.row_off[e];   // reserved by the short kernel
+    u32 c = 0xFFFFFFFFu;      // lanes beyond the read sort to the end
+    if (lane < k) {
+      const int t = P.tg[s + lane], h = P.hp[s + lane];
+      if ((u32)t >= (u32)P.n_targets || (u32)h >= (u32)P.n_haps) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
+      c = ecb_code(t, h);
     }
-    const u32 off = harvest_row_reserve(P.ctr, (u32)__popc(leaders), lane);
-    if (leader) P.arena[(size_t)off + rank] = make_uint2((u32)t, mask);
-    if (lane == 0) {
-      P.row_len[e] = (u32)__popc(leaders);
-      P.row_off[e] = off;
+    return c;
+  };
+  u32 e_cur = warp_global < n_mid ? P.mid_list[warp_global] : 0u;
+  u32 e_nxt = warp_global + n_warps < n_mid ? P.mid_list[warp_global + n_warps] : 0u;
+  int k_cur = 0;
+  u32 off_cur = 0;
+  u32 c_cur = warp_global < n_mid ? load_code(e_cur, k_cur, off_cur) : 0xFFFFFFFFu;
+  for (u32 i = warp_global; i < n_mid; i += n_warps) {
+    const u32 e = e_cur, off = off_cur;
+    u32 c = c_cur;
+    // the next EC's codes and the list entry after it
+    const u32 e_nn = i + 2 * n_warps < n_mid ? P.mid_list[i + 2 * n_warps] : 0u;
+    if (i + n_warps < n_mid) c_cur = load_code(e_nxt, k_cur, off_cur);
+    e_cur = e_nxt;
+    e_nxt = e_nn;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        const u32 o = __shfl_xor_sync(ECB_FULL, c, stride);
+        const bool keep_min = ((lane & size) == 0) == ((lane & stride) == 0);
+        c = keep_min ? min(c, o) : max(c, o);
+      }
     }
+    const bool valid = c != 0xFFFFFFFFu;
+    const u32 t = c >> 5;
+    const u32 prev = __shfl_up_sync(ECB_FULL, c, 1);
+    const bool head = lane == 0 || (prev >> 5) != t;            // (the first lane beyond the read is one too)
+    const u32 heads = __ballot_sync(ECB_FULL, head);
+    u32 m = valid ? (1u << (c & 31u)) : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {                           // OR over the rest of the run
+      const u32 o = __shfl_down_sync(ECB_FULL, m, d);
+      if (lane + d < 32 && ((heads >> (lane + 1)) & ((1u << d) - 1u)) == 0u) m |= o;
+    }
+    const u32 vheads = heads & __ballot_sync(ECB_FULL, valid);
+    if (head && valid) P.arena[(size_t)off + __popc(vheads & lt)] = make_uint2(t, m);
+    if (lane == 0) P.row_len[e] = (u32)__popc(vheads);
   }
 }
 
@@ -188,10 +219,27 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
   const u32 warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const u32 n_warps = (gridDim.x * blockDim.x) >> 5;
   const u32 lt = (1u << lane) - 1u;
+  // the list entry and the start / length / row place of the NEXT ECs are fetched while the current one is sorted
+  u32 e_cur = warp_global < n_big ? P.big_list[warp_global] : 0u;
+  u32 e_nxt = warp_global + n_warps < n_big ? P.big_list[warp_global + n_warps] : 0u;
+  int s_cur = 0;
+  u32 k_cur = 0, off_cur = 0;
+  if (warp_global < n_big) {
+    s_cur = (int)P.ec_rep[e_cur];
+    k_cur = P.ec_len[e_cur];
+    off_cur = P.row_off[e_cur];
+  }
   for (u32 li = warp_global; li < n_big; li += n_warps) {
-    const u32 e = P.big_list[li];
-    const int s = (int)P.ec_rep[e];
-    const u32 k = P.ec_len[e];
+    const u32 e = e_cur, k = k_cur, off = off_cur;
+    const int s = s_cur;
+    const u32 e_nn = li + 2 * n_warps < n_big ? P.big_list[li + 2 * n_warps] : 0u;
+    if (li + n_warps < n_big) {
+      s_cur = (int)P.ec_rep[e_nxt];
+      k_cur = P.ec_len[e_nxt];
+      off_cur = P.row_off[e_nxt];
+    }
+    e_cur = e_nxt;
+    e_nxt = e_nn;
     u32 np2 = 64;
     while (np2 < k) np2 <<= 1;
     bool bad = false;
@@ -221,14 +269,6 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
         __syncwarp();
       }
     }
-    // distinct targets first (the row's length), then the row at its reserved place
-    u32 n_rows = 0;
-    for (u32 base = 0; base < k; base += 32) {
-      const u32 i = base + lane;
-      const bool start = i < k && ((i == 0) || ((codes[i - 1] >> 5) != (codes[i] >> 5)));
-      n_rows += (u32)__popc(__ballot_sync(ECB_FULL, start));
-    }
-    const u32 off = harvest_row_reserve(P.ctr, n_rows, lane);
     uint2* out = P.arena + (size_t)off;
     u32 run = 0;
     for (u32 base = 0; base < k; base += 32) {
@@ -247,10 +287,7 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
       }
       run += (u32)__popc(m);
     }
-    if (lane == 0) {
-      P.row_len[e] = run;
-      P.row_off[e] = off;
-    }
+    if (lane == 0) P.row_len[e] = run;
     __syncwarp();
   }
 }
@@ -294,19 +331,9 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
         __syncthreads();
       }
     }
-    // distinct targets first (the row's length), then the row at its reserved place
-    if (threadIdx.x == 0) s_run = 0;
-    __syncthreads();
-    {
-      u32 mine = 0;
-      for (u32 i = threadIdx.x; i < k; i += blockDim.x)
-        mine += ((i == 0) || ((sm_codes[i - 1] >> 5) != (sm_codes[i] >> 5))) ? 1u : 0u;
-      if (mine) atomicAdd(&s_run, mine);
-    }
-    __syncthreads();
     if (threadIdx.x == 0) {
-      s_off = (u32)atomicAdd((unsigned long long*)&P.ctr->arena_used, (unsigned long long)s_run);
       s_run = 0;
+      s_off = P.row_off[e];   // reserved by the short kernel
     }
     __syncthreads();
     const size_t out0 = (size_t)s_off;
@@ -329,10 +356,7 @@ __global__ void __launch_bounds__(256) ecb_harvest_long_kernel(const HarvestPara
       if (threadIdx.x == 0) s_run += total;
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      P.row_len[e] = s_run;
-      P.row_off[e] = s_off;
-    }
+    if (threadIdx.x == 0) P.row_len[e] = s_run;
     __syncthreads();
   }
 }
