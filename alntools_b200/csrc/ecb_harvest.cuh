@@ -208,6 +208,38 @@ __global__ void __launch_bounds__(256) ecb_harvest_warp_kernel(const HarvestPara
   }
 }
 
+// Bitonic sort of 32 * R values held R per lane (value i of the sequence = register i / 32 of lane i % 32):
+// compare-exchange steps with a stride below 32 are shuffles, the others stay inside the lane.  For 64 and 128
+// values this takes about 40 % of the instructions of the shared-memory network below.
+template <int R>
+__device__ __forceinline__ void harvest_sort_regs(u32 (&v)[R], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * R; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int sr = stride >> 5;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r & sr) continue;
+          const bool up = ((r << 5) & size) == 0;
+          const u32 lo = min(v[r], v[r | sr]), hi = max(v[r], v[r | sr]);
+          v[r] = up ? lo : hi;
+          v[r | sr] = up ? hi : lo;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const u32 o = __shfl_xor_sync(ECB_FULL, v[r], stride);
+          const bool up = (((r << 5) | lane) & size) == 0;
+          const bool keep_min = up == ((lane & stride) == 0);
+          v[r] = keep_min ? min(v[r], o) : max(v[r], o);
+        }
+      }
+    }
+  }
+}
+
 // Rows of reads with 33..HARVEST_WSORT_MAX alignments (heavy multimapping): one WARP per EC.  The
 // element codes are sorted with a bitonic network in the warp's own slice of shared memory, so the only
 // synchronisation is __syncwarp; then one entry per distinct target.
@@ -254,6 +286,21 @@ __global__ void __launch_bounds__(256) ecb_harvest_wsort_kernel(const HarvestPar
     }
     if (bad) atomicOr(&P.ctr->error, ECB_DEVERR_VALUE_RANGE);
     __syncwarp();
+    if (np2 == 64u) {          // up to 128 codes are sorted in registers and go back sorted
+      u32 v[2] = {codes[lane], codes[32 + lane]};
+      harvest_sort_regs<2>(v, lane);
+      codes[lane] = v[0];
+      codes[32 + lane] = v[1];
+      __syncwarp();
+    } else if (np2 == 128u) {
+      u32 v[4] = {codes[lane], codes[32 + lane], codes[64 + lane], codes[96 + lane]};
+      harvest_sort_regs<4>(v, lane);
+      codes[lane] = v[0];
+      codes[32 + lane] = v[1];
+      codes[64 + lane] = v[2];
+      codes[96 + lane] = v[3];
+      __syncwarp();
+    } else
     for (u32 size = 2; size <= np2; size <<= 1) {
       for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
         for (u32 i = lane; i < (np2 >> 1); i += 32) {
