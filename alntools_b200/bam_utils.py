@@ -208,7 +208,26 @@ def _spawn_ranks(n_gpus, kwargs):
                        MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), ALNTOOLS_B200_SUMMARY=os.path.join(tmp, "summary.json"),
                        ALNTOOLS_B200_VERBOSE="1" if LOG.isEnabledFor(20) else "0")
             procs.append(subprocess.Popen([sys.executable, "-m", "alntools_b200._rank_worker", job], env=env))
-        codes = [p.wait() for p in procs]
+        # one worker that fails would leave the others waiting in a collective: when the first non-zero exit code
+        # shows up the remaining workers (exactly the processes started above) are terminated
+        codes = [None] * n_gpus
+        while any(c is None for c in codes):
+            for i, p in enumerate(procs):
+                if codes[i] is None:
+                    codes[i] = p.poll()
+            if any(c not in (None, 0) for c in codes):
+                for i, p in enumerate(procs):
+                    if codes[i] is None:
+                        p.terminate()
+                for i, p in enumerate(procs):
+                    if codes[i] is None:
+                        try:
+                            codes[i] = p.wait(timeout=20)
+                        except subprocess.TimeoutExpired:
+                            p.kill()
+                            codes[i] = p.wait()
+                break
+            time.sleep(0.02)
         if any(codes):
             raise RuntimeError("multi-GPU bam2ec failed: worker exit codes %s" % codes)
         with open(os.path.join(tmp, "summary.json")) as fh:

@@ -1527,9 +1527,16 @@ int bamcols_plan_shards(bamcols* r, int n_shards, int64_t* voffsets) {
       if (rc < 0) return rc;
     }
     if (b.data.empty()) continue;   // only the end-of-file marker lies behind the target: an empty shard
-    // a record start: eight plausible records in a row (samtools / htslib start every block with one)
+    // a record start: eight plausible records in a row (samtools / htslib start every block with one; a record
+    // of a long read can be megabytes, so the search may have to run on for a while)
     size_t p = SIZE_MAX;
-    for (size_t cand = 0; cand + 36 <= b.data.size() && cand < (1u << 17); ++cand) {
+    for (size_t cand = 0; cand < ((size_t)1 << 26); ++cand) {
+      if (cand + 36 > b.data.size()) {
+        if (b.eof) break;
+        rc = plan_more(r, b, 16);
+        if (rc < 0) return rc;
+        if (cand + 36 > b.data.size()) break;
+      }
       size_t x = cand;
       int good = 0;
       while (good < 8) {

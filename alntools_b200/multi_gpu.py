@@ -135,23 +135,40 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
             mine = torch.tensor([min_base, max_end], dtype=torch.int64, device=device)
             spans = torch.empty(2 * world, dtype=torch.int64, device=device)
             dist.all_gather_into_tensor(spans, mine, group=group)
-            owner.import_arena()
+            # a rank that fails here (an arena that turned out too small) must not leave its peers waiting in a
+            # collective: it carries on with what it has, the failure travels with the all-gather of the slice
+            # sizes below, and every rank raises
+            failure = None
+            try:
+                owner.import_arena()
+            except Exception as exc:         # noqa: BLE001 - re-raised on every rank below
+                failure = exc
             owner.arena_reset()              # reused by the second dispatch ...
             _stream_barrier(device, group)   # ... once every rank has merged what it received
             ph.mark("import")
-            spans = spans.tolist()           # (import_arena has synchronised already)
+            spans = spans.tolist()
             lo, hi = spans[0::2], spans[1::2]
             if not any(h > l for l, h in zip(lo, hi)):
                 raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
             owner.order_dispatch(arena["bases"], arena["cap_ec"], arena["cap_rows"], lo, hi)
             _stream_barrier(device, group)   # every rank's ECs have landed
             ph.mark("order dispatch")
-            sl = owner.order_build(lo[me], hi[me])
+            sl = None
+            try:
+                sl = owner.order_build(lo[me], hi[me])
+            except Exception as exc:         # noqa: BLE001
+                failure = failure or exc
             ph.mark("order build")
             # the id range of a rank starts behind the ECs of the shards in front of it
-            sizes = torch.empty(world, dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(sizes, torch.tensor([sl["n_ec"]], dtype=torch.int64, device=device), group=group)
+            sizes = torch.empty(2 * world, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(sizes, torch.tensor([sl["n_ec"] if sl else 0, 1 if failure else 0],
+                                                            dtype=torch.int64, device=device), group=group)
             sizes = sizes.tolist()
+            if failure is not None:
+                raise failure
+            if any(sizes[1::2]):
+                raise RuntimeError("the multi-GPU exchange failed on rank(s) %s" % [r for r in range(world) if sizes[2 * r + 1]])
+            sizes = sizes[0::2]
             id_base = sum(n for r, n in enumerate(sizes) if hi[r] > lo[r] and (lo[r], r) < (lo[me], me))
             ph.report()
             return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
