@@ -85,9 +85,6 @@ SIGNATURES = {
                                             ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
                                             ctypes.POINTER(ctypes.c_int64)]),
     "ecb_import_arena": (ctypes.c_int, [ctypes.c_void_p]),
-    "ecb_slice_dispatch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
-                                          ctypes.c_int64, ctypes.c_int64]),
-    "ecb_slice_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(EcbSlice)]),
     "ecb_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "ecb_finalize": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(EcbResult)]),
@@ -308,11 +305,6 @@ class EcBuilder(object):
     def import_arena(self):
         self._check(self._lib.ecb_import_arena(self._ctx))
 
-    def slice_dispatch(self, bases, cap_records, cap_rows):
-        """After global_count: send every owned EC (id, count, row) to the rank that assembles its id range."""
-        arr = (ctypes.c_void_p * len(bases))(*bases)
-        self._check(self._lib.ecb_slice_dispatch(self._ctx, len(bases), arr, int(cap_records), int(cap_rows)))
-
     def order_dispatch(self, bases, cap_records, cap_rows, shard_lo, shard_hi):
         """Send every owned EC (position inside its shard, count, row) to the rank whose shard of the read
         order holds its first occurrence (shard_lo / shard_hi: one entry per rank)."""
@@ -332,18 +324,6 @@ class EcBuilder(object):
         return {"n_ec": int(sl.n_ec), "nnz": int(sl.nnz), "a_indptr": view(sl.a_indptr, sl.n_ec + 1),
                 "a_indices": view(sl.a_indices, max(sl.nnz, 1))[:sl.nnz], "a_data": view(sl.a_data, max(sl.nnz, 1))[:sl.nnz],
                 "n_data": view(sl.n_data, max(sl.n_ec, 1))[:sl.n_ec]}
-
-    def slice_build(self, rank, world):
-        """-> dict(id_base, n_ec, nnz, a_indptr, a_indices, a_data, n_data): this rank's EC-id range of the
-        final matrices as torch views of library memory (valid until the next call on this context)."""
-        import torch
-        sl = EcbSlice()
-        self._check(self._lib.ecb_slice_build(self._ctx, int(rank), int(world), ctypes.byref(sl)))
-        dev = torch.device("cuda", torch.cuda.current_device())
-        view = lambda p, n: _device_view(ctypes.cast(p, ctypes.c_void_p).value, (n,), "<i4", torch.int32, dev)
-        return {"id_base": int(sl.id_base), "n_ec": int(sl.n_ec), "nnz": int(sl.nnz),
-                "a_indptr": view(sl.a_indptr, sl.n_ec + 1), "a_indices": view(sl.a_indices, sl.nnz),
-                "a_data": view(sl.a_data, sl.nnz), "n_data": view(sl.n_data, sl.n_ec)}
 
     def global_mark(self, min_base, bitmap):
         self._check(self._lib.ecb_global_mark(self._ctx, int(min_base), bitmap.data_ptr(), bitmap.numel()))

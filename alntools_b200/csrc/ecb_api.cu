@@ -1245,91 +1245,6 @@ static void arena_targets(ArenaTargets* A, int world, void* const* bases, int64_
   A->cap_rows = (unsigned long long)cap_rows;
 }
 
-int ecb_slice_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows) {
-  if (!c || !arena_bases || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;
-  if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
-  if (cap_rows >= (1ll << 40)) return fail(c, ECB_ERR_LIMIT, "arena rows must stay below 2^40");
-  CK(cudaSetDevice(c->device));
-  if (c->g_n_ec_total == 0) return fail(c, ECB_ERR_STATE, "ecb_global_count has not run");
-  if (c->n_ec == 0) return ECB_OK;
-  // global ids of the owned ECs (no global arrays)
-  FinalizeParams F = global_params(c);
-  F.bitmap = (u32*)c->bitmap.p;
-  F.word_rank = (const u32*)c->word_rank.p;
-  ecb_fin_rank_kernel<false><<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(F);
-  LAUNCH_CHECK("fin_rank");
-  SliceDispatchParams P{};
-  P.ecid_of = (const u32*)c->ecid_of.p;
-  P.count_of = (const u32*)c->count_of.p;
-  P.row_len = (const u32*)c->row_len.p;
-  P.row_off = (const u32*)c->row_off.p;
-  P.arena = (const uint2*)c->arena.p;
-  P.n_ec = c->n_ec;
-  P.world = (u32)world;
-  P.slice = (u32)((c->g_n_ec_total + (u64)world - 1) / (u64)world);
-  ArenaTargets A{};
-  for (int r = 0; r < world; ++r)
-    if (!arena_bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
-  arena_targets(&A, world, arena_bases, cap_records, cap_rows);
-  ecb_slice_dispatch_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
-  LAUNCH_CHECK("slice_dispatch");
-  CK(cudaStreamSynchronize(c->stream));
-  return ECB_OK;
-}
-
-int ecb_slice_build(ecb_ctx* c, int rank, int world, ecb_slice* out) {
-  if (!c || !out || !c->xa_base || world < 1 || rank < 0 || rank >= world) return ECB_ERR_INVALID;
-  memset(out, 0, sizeof *out);
-  CK(cudaSetDevice(c->device));
-  unsigned long long hdr[3] = {0, 0, 0};
-  CK(cudaMemcpyAsync(hdr, c->xa_base, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  if (hdr[2]) return fail(c, ECB_ERR_LIMIT, "exchange arena too small for the slice dispatch");
-  const u64 G = c->g_n_ec_total;
-  const u64 slice = (G + (u64)world - 1) / (u64)world;
-  const u64 base = std::min<u64>(G, slice * (u64)rank);
-  const u64 n_local = std::min<u64>(G, base + slice) - base;
-  if (hdr[0] != n_local)
-    return fail(c, ECB_ERR_INVALID, "slice %d expects %llu ECs but %llu arrived", rank, (unsigned long long)n_local, hdr[0]);
-  const char* b = (const char*)c->xa_base;
-  const unsigned long long* rec = (const unsigned long long*)(b + ECB_ARENA_HEADER_BYTES);
-  const int2* rows = (const int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)c->xa_cap_ec * ECB_META_WORDS * 8);
-  CKR(ensure(c, c->r_a_indptr, (n_local + 1) * 4));
-  CKR(ensure(c, c->r_n_data, std::max<u64>(n_local, 1) * 4));
-  CKR(ensure(c, c->first_rel, std::max<u64>(n_local, 1) * 8));   // scratch: record index per id
-  u32* rec_of = (u32*)c->first_rel.p;
-  CK(cudaMemsetAsync((int32_t*)c->r_a_indptr.p + n_local, 0, 4, c->stream));
-  CK(cudaMemsetAsync(&c->d_ctr->scratch[5], 0, sizeof(u32), c->stream));
-  u64 nnz = 0;
-  if (n_local) {
-    ecb_slice_lens_kernel<<<grid_for(n_local, 256, c->sm_count * 8), 256, 0, c->stream>>>(
-        rec, (u32)n_local, (u32)base, (u32)n_local, (int32_t*)c->r_a_indptr.p, (int32_t*)c->r_n_data.p, rec_of,
-        &c->d_ctr->scratch[5]);
-    LAUNCH_CHECK("slice_lens");
-  }
-  CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, n_local + 1, 0, &nnz));
-  CKR(sync_counters(c));
-  if (c->h_ctr->scratch[5]) return fail(c, ECB_ERR_INVALID, "a record outside the slice's id range arrived");
-  if (nnz != hdr[1]) return fail(c, ECB_ERR_INVALID, "slice rows do not add up (%llu vs %llu)", (unsigned long long)nnz, hdr[1]);
-  CKR(ensure(c, c->r_a_indices, std::max<u64>(nnz, 1) * 4));
-  CKR(ensure(c, c->r_a_data, std::max<u64>(nnz, 1) * 4));
-  if (n_local) {
-    ecb_slice_rows_kernel<<<grid_for(n_local, 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        rec, rows, rec_of, (const int32_t*)c->r_a_indptr.p, (u32)n_local, (int32_t*)c->r_a_indices.p,
-        (int32_t*)c->r_a_data.p);
-    LAUNCH_CHECK("slice_rows");
-  }
-  CK(cudaStreamSynchronize(c->stream));
-  out->id_base = (int64_t)base;
-  out->n_ec = (int64_t)n_local;
-  out->nnz = (int64_t)nnz;
-  out->a_indptr = (const int32_t*)c->r_a_indptr.p;
-  out->a_indices = (const int32_t*)c->r_a_indices.p;
-  out->a_data = (const int32_t*)c->r_a_data.p;
-  out->n_data = (const int32_t*)c->r_n_data.p;
-  return ECB_OK;
-}
-
 int ecb_order_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
                        const int64_t* shard_lo, const int64_t* shard_hi) {
   if (!c || !arena_bases || !shard_lo || !shard_hi || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;

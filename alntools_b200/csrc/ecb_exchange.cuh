@@ -197,110 +197,15 @@ __global__ void __launch_bounds__(256) ecb_export_to_arenas_kernel(const ExportP
   }
 }
 
-// ---- second dispatch: final rows to the rank that assembles their EC-id range -------------------------
-// Once global EC ids are known the final CSR is assembled in SLICES: rank j builds the rows of the ids
-// [j * slice, (j + 1) * slice).  Every owner sends each of its ECs to the slice rank - again straight
-// into that rank's arena over NVLink - as a 2-word record {id | count << 32, row offset | len << 40}
-// plus its row.  Per-rank traffic and work stay constant under weak scaling; nothing is ever
-// zero-padded to the global size.
 #define ECB_SLICE_WORDS 2
 
-struct SliceDispatchParams {
-  const u32* ecid_of;     // [n_ec] global id of every owned EC
-  const u32* count_of;    // [n_ec]
-  const u32* row_len;
-  const u32* row_off;
-  const uint2* arena;
-  u32 n_ec;
-  u32 world;
-  u32 slice;              // ids per rank
-};
-
-__global__ void __launch_bounds__(256) ecb_slice_dispatch_kernel(const SliceDispatchParams P, const ArenaTargets A) {
-  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];
-  __shared__ u32 s_off[2 * ECB_MAX_WORLD];
-  __shared__ unsigned long long s_base[2 * ECB_MAX_WORLD];
-  __shared__ u32 s_drop[ECB_MAX_WORLD];
-  __shared__ u32 s_rows_total;
-  __shared__ __align__(16) unsigned long long s_rec[256 * ECB_SLICE_WORDS];
-  __shared__ __align__(16) int2 s_rows[ECB_XT_ROWS];
-  const u32 W = P.world;
-  const u32 tiles = (P.n_ec + blockDim.x - 1) / blockDim.x;
-  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    for (u32 i = threadIdx.x; i < 2 * W; i += blockDim.x) s_cnt[i] = 0u;
-    __syncthreads();
-    const u32 e = tile * blockDim.x + threadIdx.x;
-    u32 id = ECB_NONE, dest = 0, len = 0, idx = 0, roff = 0;
-    if (e < P.n_ec) id = P.ecid_of[e];
-    const bool live = id != ECB_NONE;
-    if (live) {
-      dest = min(id / P.slice, W - 1u);
-      len = P.row_len[e];
-      idx = atomicAdd(&s_cnt[dest], 1u);
-      roff = atomicAdd(&s_cnt[W + dest], len);
-    }
-    __syncthreads();
-    if (threadIdx.x < W) {
-      const u32 o = threadIdx.x;
-      const u32 ce = s_cnt[o], cr = s_cnt[W + o];
-      s_drop[o] = 0u;
-      if (ce) {
-        const unsigned long long be = atomicAdd(A.hdr[o] + 0, (unsigned long long)ce);
-        const unsigned long long br = atomicAdd(A.hdr[o] + 1, (unsigned long long)cr);
-        s_base[o] = be;
-        s_base[W + o] = br;
-        if ((be + ce) * ECB_SLICE_WORDS > A.cap_ec * ECB_META_WORDS || br + cr > A.cap_rows) {
-          atomicExch(A.hdr[o] + 2, 1ull);
-          s_drop[o] = 1u;
-        }
-      }
-    }
-    if (threadIdx.x == 32) {
-      u32 ae = 0, ar = 0;
-      for (u32 o = 0; o < W; ++o) {
-        s_off[o] = ae;
-        s_off[W + o] = ar;
-        ae += s_cnt[o];
-        ar += s_cnt[W + o];
-      }
-      s_rows_total = ar;
-    }
-    __syncthreads();
-    const bool stage_rows = s_rows_total <= ECB_XT_ROWS;
-    if (live && !s_drop[dest]) {
-      const unsigned long long rat = s_base[W + dest] + roff;
-      unsigned long long* r = s_rec + (size_t)(s_off[dest] + idx) * ECB_SLICE_WORDS;
-      r[0] = (unsigned long long)id | ((unsigned long long)P.count_of[e] << 32);
-      r[1] = rat | ((unsigned long long)len << 40);
-      const uint2* src = P.arena + P.row_off[e];
-      int2* dst = stage_rows ? s_rows + s_off[W + dest] + roff : A.rows[dest] + rat;
-      for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
-    }
-    __syncthreads();
-    for (u32 o = 0; o < W; ++o) {
-      if (s_cnt[o] == 0u || s_drop[o]) continue;
-      const u32 n_words = s_cnt[o] * ECB_SLICE_WORDS;
-      const unsigned long long* src = s_rec + (size_t)s_off[o] * ECB_SLICE_WORDS;
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.meta[o]) + s_base[o] * ECB_SLICE_WORDS;
-      for (u32 w = threadIdx.x; w < n_words; w += blockDim.x) dst[w] = src[w];
-      if (stage_rows) {
-        const u32 n_rows = s_cnt[W + o];
-        const long long* rsrc = reinterpret_cast<const long long*>(s_rows + s_off[W + o]);
-        long long* rdst = reinterpret_cast<long long*>(A.rows[o] + s_base[W + o]);
-        for (u32 w = threadIdx.x; w < n_rows; w += blockDim.x) rdst[w] = rsrc[w];
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---- second dispatch, ordering form: every merged EC goes to the rank whose SHARD holds its first
-// occurrence.  EC ids are ranks of first-occurrence positions and the shards partition the positions, so
+// ---- second dispatch: every merged EC goes to the rank whose SHARD holds its first occurrence.  EC ids are ranks of first-occurrence positions and the shards partition the positions, so
 // the ECs that arrive at a rank form one contiguous id range, ordered by their position inside the shard:
 // the receiver ranks them with a bitmap over ITS OWN positions only.  Nothing global is built: no bitmap over
 // all ranks' positions, no all-reduce of it, no padded arrays; the id range of a rank starts where the ranges
 // of the shards in front of it end (one all-gather of a count).  Record: {position inside the shard |
-// count << 32, row offset | len << 40} plus the row - the layout of the id-range dispatch above.
+// count << 32, row offset | len << 40} plus the row.  (Round 1 dispatched by EC-id range after ranking a bitmap
+// over ALL ranks' positions that had been OR-ed by an all-reduce - 61 MB at 8 GPUs; that form is gone.)
 struct OrderDispatchParams {
   const EcbEntry* table;
   const u32* ec_slot;
@@ -397,7 +302,7 @@ __global__ void __launch_bounds__(256) ecb_order_dispatch_kernel(const OrderDisp
   }
 }
 
-// Ordering form of the slice assembly, pass 0: one bit per arrived EC at its position inside the shard.
+// Slice assembly, pass 0: one bit per arrived EC at its position inside the shard.
 __global__ void __launch_bounds__(256) ecb_order_mark_kernel(const unsigned long long* __restrict__ rec, u32 n_rec, u32 span,
                                                             u32* bitmap, u32* bad) {
   for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
@@ -422,23 +327,6 @@ __global__ void __launch_bounds__(256) ecb_order_lens_kernel(const unsigned long
     const u32 w = rel >> 5, b = rel & 31;
     const u32 i = word_rank[w] + (u32)__popc(bitmap[w] & ((1u << b) - 1u));
     if (i >= n_rec) continue;   // (only after a duplicate position, which pass 0 has reported)
-    lens[i] = (int32_t)(w1 >> 40);
-    counts[i] = (int32_t)(w0 >> 32);
-    rec_of[i] = r;
-  }
-}
-
-// Slice assembly, pass 1: row length, count and record index of every id of the slice.
-__global__ void __launch_bounds__(256) ecb_slice_lens_kernel(const unsigned long long* __restrict__ rec, u32 n_rec,
-                                                            u32 id_base, u32 slice_n, int32_t* lens, int32_t* counts,
-                                                            u32* rec_of, u32* bad) {
-  for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-    const unsigned long long w0 = rec[(size_t)r * ECB_SLICE_WORDS], w1 = rec[(size_t)r * ECB_SLICE_WORDS + 1];
-    const u32 i = (u32)(w0 & 0xFFFFFFFFull) - id_base;
-    if (i >= slice_n) {
-      atomicOr(bad, 1u);
-      continue;
-    }
     lens[i] = (int32_t)(w1 >> 40);
     counts[i] = (int32_t)(w0 >> 32);
     rec_of[i] = r;

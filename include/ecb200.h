@@ -164,6 +164,11 @@ const char* ecb_last_error(const ecb_ctx* ctx);
  *   5. ecb_global_lens / all-reduce / ecb_global_indptr / ecb_global_rows / all-reduce: every rank
  *      scatters its owned rows and counts into zero-initialised global arrays; supports are disjoint,
  *      so a SUM all-reduce assembles the final CSR A matrix and the counts on every rank.
+ * That is the form for any transport (NCCL, gloo in the CPU tests).  Where the ranks can map each other's
+ * memory (one process per GPU on an NVLink / NVSwitch box) steps 1-3 are one kernel that stores into the
+ * owners' arenas (ecb_export_to_arenas / ecb_import_arena) and steps 4-5 are replaced by a second dispatch
+ * keyed by the shard that holds an EC's first occurrence (ecb_order_dispatch / ecb_order_build): nothing
+ * global is built and the final matrices stay partitioned, one contiguous EC-id range per rank.
  * All pointers marked "device" are device memory of the context's GPU owned by the caller.
  */
 /* Add `delta` (>= 0) to the order key of everything pushed so far: a rank that decodes one shard of a file
@@ -206,22 +211,14 @@ int ecb_export_to_arenas(ecb_ctx* local_ctx, int world, void* const* arena_bases
                          int64_t cap_rows, int64_t* min_base, int64_t* max_end);
 int ecb_import_arena(ecb_ctx* owner_ctx);
 
-/* ---- slice assembly (after ecb_global_count): instead of steps 5's zero-padded global arrays the final
- * CSR is built in EC-id ranges, rank j holding ids [j * slice, (j + 1) * slice) with
- * slice = ceil(n_ec_total / world).  ecb_slice_dispatch on the OWNER context sends every owned EC (id,
- * count, row) straight into the arena of the rank that assembles its id (the arenas of the first
- * dispatch are reused: reset them after ecb_import_arena); after a barrier ecb_slice_build turns what
- * arrived into that rank's slice: a_indptr[n_ec + 1] (offsets local to the slice), a_indices, a_data
- * and n_data (read counts), all device memory of the context, valid until the next call. */
+/* ---- the final matrices in slices, one per rank -------------------------------------------------------- */
 typedef struct ecb_slice {
   int64_t id_base, n_ec, nnz;
   const int32_t *a_indptr, *a_indices, *a_data, *n_data;
 } ecb_slice;
-int ecb_slice_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, int64_t cap_records,
-                       int64_t cap_rows);
-int ecb_slice_build(ecb_ctx* owner_ctx, int rank, int world, ecb_slice* out);
 
-/* ---- ordering form of the second dispatch (the default of the multi-GPU path): every merged EC goes to the
+/* ---- second dispatch (the multi-GPU path; the arenas of the first dispatch are reused: reset them after
+ * ecb_import_arena): every merged EC goes to the
  * rank whose shard [shard_lo[r], shard_hi[r]) of the global read order holds its first occurrence.  EC ids are
  * ranks of first-occurrence positions and the shards partition the positions, so a rank receives one contiguous
  * id range and orders it with a bitmap over its OWN positions: no global bitmap, no all-reduce, no
