@@ -309,9 +309,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     wl = WORKLOADS[args.workload]
     config = {"workload": args.workload, "reads_per_gpu": wl["n_reads"], "n_targets": wl["n_targets"],
-              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU; N > 1: + dispatch of hash-partitioned local ECs over peer "
-                                                              "memory, owner merge, global ids, final CSR partitioned by "
-                                                              "EC-id range across the ranks (e2e: every rank copies its "
+              "n_haps": wl["n_haps"], "multimapping": str(wl["mode"]), "sharding": "contiguous read chunks per GPU; N > 1: + dispatch of the local ECs to their owner rank (hash of "
+                                                              "the key) over peer memory, owner merge, second dispatch to the rank whose "
+                                                              "shard holds the EC's first occurrence, ids ranked there: the final CSR stays "
+                                                              "partitioned by EC-id range across the ranks (e2e: every rank copies its "
                                                               "range to its host)",
               "l2": "see config.l2_hygiene"}
 
