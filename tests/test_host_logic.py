@@ -178,3 +178,19 @@ def test_sliced_ec_file_writer_reproduces_the_golden_bytes(tmp_path):
                                         data[lo:hi], counts[a:b], create=(r == 0))
             with open(out, "rb") as x, open(src, "rb") as y:
                 assert x.read() == y.read(), (case["name"], world)
+
+
+def test_multi_gpu_convert_fails_loudly_and_promptly_without_gpus(tmp_path):
+    """convert(..., devices=2) starts one worker process per GPU.  Where the GPUs are missing the workers die at
+    once; the call must report that (no CPU fallback) and must not leave a worker waiting for its peers."""
+    import time
+    import torch
+    from alntools_b200 import bam_utils
+    if torch.cuda.is_available() and torch.cuda.device_count() >= 2:
+        pytest.skip("this machine has the GPUs; tests/multigpu_convert_check.py covers the working path")
+    case = [c for c in golden_cases("single")][0]
+    t0 = time.time()
+    with pytest.raises(RuntimeError, match="multi-GPU bam2ec failed"):
+        bam_utils.convert(os.path.join(GOLDEN, case["bam"]), str(tmp_path / "out.bin"), None, devices=2)
+    assert time.time() - t0 < 120
+    assert not os.path.exists(str(tmp_path / "out.bin"))
