@@ -73,17 +73,15 @@ SIGNATURES = {
                                   ctypes.c_int, ctypes.c_int64]),
     "ecb_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64]),
     "ecb_set_stream": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
-    "ecb_arena_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
-                                        ctypes.POINTER(ctypes.c_void_p)]),
+    "ecb_arena_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ecb_arena_open_peer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "ecb_arena_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "ecb_rebase": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64]),
     "ecb_order_dispatch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64,
-                                          ctypes.c_int64, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
-    "ecb_order_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(EcbSlice)]),
-    "ecb_export_to_arenas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
-                                            ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
-                                            ctypes.POINTER(ctypes.c_int64)]),
+                                          ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "ecb_order_build": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(EcbSlice)]),
+    "ecb_export_to_arenas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int64,
+                                            ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
     "ecb_import_arena": (ctypes.c_int, [ctypes.c_void_p]),
     "ecb_push": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
@@ -274,11 +272,11 @@ class EcBuilder(object):
         self._check(self._lib.ecb_import_entries(self._ctx, meta.data_ptr(), rows.data_ptr(), a, b, n))
 
     # ---- exchange over peer memory (CUDA IPC arenas, see include/ecb200.h) -------------------------
-    def arena_create(self, cap_records, cap_rows):
-        """-> (64-byte IPC handle, base address) of this OWNER context's arena."""
+    def arena_create(self, cap_records):
+        """-> (64-byte IPC handle, base address) of this OWNER context's arena (cap_records records of 32 bytes)."""
         handle = ctypes.create_string_buffer(64)
         base = ctypes.c_void_p()
-        self._check(self._lib.ecb_arena_create(self._ctx, int(cap_records), int(cap_rows), handle, ctypes.byref(base)))
+        self._check(self._lib.ecb_arena_create(self._ctx, int(cap_records), handle, ctypes.byref(base)))
         return handle.raw, int(base.value)
 
     def arena_open_peer(self, handle):
@@ -293,32 +291,32 @@ class EcBuilder(object):
         """Shift the order key of everything pushed so far by `delta` (see ecb_rebase in include/ecb200.h)."""
         self._check(self._lib.ecb_rebase(self._ctx, int(delta)))
 
-    def export_to_arenas(self, bases, cap_records, cap_rows):
-        """Partition this LOCAL context's ECs by owner and store them into the owners' arenas.
+    def export_to_arenas(self, bases, cap_records):
+        """Dispatch 1: every EC of this LOCAL context as {key, first, count} into the arena of its owner rank.
         -> (min_base, max_end) of the positions pushed here."""
         arr = (ctypes.c_void_p * len(bases))(*bases)
         lo, hi = ctypes.c_int64(), ctypes.c_int64()
-        self._check(self._lib.ecb_export_to_arenas(self._ctx, len(bases), arr, int(cap_records), int(cap_rows),
-                                                   ctypes.byref(lo), ctypes.byref(hi)))
+        self._check(self._lib.ecb_export_to_arenas(self._ctx, len(bases), arr, int(cap_records), ctypes.byref(lo), ctypes.byref(hi)))
         return int(lo.value), int(hi.value)
 
     def import_arena(self):
         self._check(self._lib.ecb_import_arena(self._ctx))
 
-    def order_dispatch(self, bases, cap_records, cap_rows, shard_lo, shard_hi):
-        """Send every owned EC (position inside its shard, count, row) to the rank whose shard of the read
-        order holds its first occurrence (shard_lo / shard_hi: one entry per rank)."""
+    def order_dispatch(self, bases, cap_records, shard_lo, shard_hi):
+        """Dispatch 2: every merged EC of this OWNER context as {key, position inside its shard, count} to the rank
+        whose shard of the read order holds its first occurrence (shard_lo / shard_hi: one entry per rank)."""
         arr = (ctypes.c_void_p * len(bases))(*bases)
         lo = (ctypes.c_int64 * len(bases))(*[int(x) for x in shard_lo])
         hi = (ctypes.c_int64 * len(bases))(*[int(x) for x in shard_hi])
-        self._check(self._lib.ecb_order_dispatch(self._ctx, len(bases), arr, int(cap_records), int(cap_rows), lo, hi))
+        self._check(self._lib.ecb_order_dispatch(self._ctx, len(bases), arr, int(cap_records), lo, hi))
 
-    def order_build(self, shard_lo, shard_hi):
+    def order_build(self, local, shard_lo, shard_hi):
         """-> dict(n_ec, nnz, a_indptr, a_indices, a_data, n_data): the ECs whose first occurrence lies in this
-        rank's shard, in id order, as torch views of library memory (valid until the next call)."""
+        rank's shard, in id order, rows taken from `local` (the builder that holds this rank's reads), as torch
+        views of library memory (valid until the next call on this context)."""
         import torch
         sl = EcbSlice()
-        self._check(self._lib.ecb_order_build(self._ctx, int(shard_lo), int(shard_hi), ctypes.byref(sl)))
+        self._check(self._lib.ecb_order_build(self._ctx, local._ctx, int(shard_lo), int(shard_hi), ctypes.byref(sl)))
         dev = torch.device("cuda", torch.cuda.current_device())
         view = lambda p, n: _device_view(ctypes.cast(p, ctypes.c_void_p).value, (n,), "<i4", torch.int32, dev)
         return {"n_ec": int(sl.n_ec), "nnz": int(sl.nnz), "a_indptr": view(sl.a_indptr, sl.n_ec + 1),

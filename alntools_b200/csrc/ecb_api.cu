@@ -86,7 +86,7 @@ struct ecb_ctx {
   DevBuf x_meta, x_rows, x_counts, x_base;
   // arena of the peer-memory exchange (plain cudaMalloc: must be exportable through CUDA IPC)
   void* xa_base = nullptr;
-  int64_t xa_cap_ec = 0, xa_cap_rows = 0;
+  int64_t xa_cap_ec = 0;
   std::vector<void*> xa_opened;
   int64_t x_part_ec[ECB_MAX_WORLD], x_part_rows[ECB_MAX_WORLD];
   u64 g_min_base = 0;
@@ -1138,15 +1138,14 @@ int ecb_import_entries(ecb_ctx* c, const int64_t* meta_device, const int32_t* ro
   return ECB_OK;
 }
 
-int ecb_arena_create(ecb_ctx* c, int64_t cap_records, int64_t cap_rows, void* ipc_handle_out, void** base_out) {
-  if (!c || cap_records < 1 || cap_rows < 1 || !base_out) return ECB_ERR_INVALID;
+int ecb_arena_create(ecb_ctx* c, int64_t cap_records, void* ipc_handle_out, void** base_out) {
+  if (!c || cap_records < 1 || !base_out) return ECB_ERR_INVALID;
   if (c->xa_base) return fail(c, ECB_ERR_STATE, "this context already has an arena");
   CK(cudaSetDevice(c->device));
-  const size_t bytes = ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_META_WORDS * 8 + (size_t)cap_rows * 8;
+  const size_t bytes = ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_KEYREC_WORDS * 8;
   CK(cudaMalloc(&c->xa_base, bytes));
   CK(cudaMemset(c->xa_base, 0, ECB_ARENA_HEADER_BYTES));
   c->xa_cap_ec = cap_records;
-  c->xa_cap_rows = cap_rows;
   if (ipc_handle_out) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are documented as 64 bytes");
     cudaIpcMemHandle_t h;
@@ -1179,9 +1178,20 @@ int ecb_arena_reset(ecb_ctx* c) {
   return ECB_OK;
 }
 
-int ecb_export_to_arenas(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
-                         int64_t* min_base, int64_t* max_end) {
-  if (!c || !arena_bases || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;
+static int arena_targets(ecb_ctx* c, ArenaTargets* A, int world, void* const* bases, int64_t cap_records) {
+  for (int r = 0; r < world; ++r) {
+    if (!bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
+    char* b = (char*)bases[r];
+    A->hdr[r] = (unsigned long long*)b;
+    A->rec[r] = (unsigned long long*)(b + ECB_ARENA_HEADER_BYTES);
+  }
+  A->cap_words = (unsigned long long)cap_records * ECB_KEYREC_WORDS;
+  return ECB_OK;
+}
+
+int ecb_export_to_arenas(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t* min_base,
+                         int64_t* max_end) {
+  if (!c || !arena_bases || cap_records < 1) return ECB_ERR_INVALID;
   if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
   if (c->with_cells) return fail(c, ECB_ERR_INVALID, "the multi-GPU exchange covers the single-sample path only");
   CK(cudaSetDevice(c->device));
@@ -1189,25 +1199,14 @@ int ecb_export_to_arenas(ecb_ctx* c, int world, void* const* arena_bases, int64_
   if (min_base) *min_base = c->n_ec ? (int64_t)c->min_base : 0;
   if (max_end) *max_end = c->n_ec ? (int64_t)c->max_end : 0;
   if (c->n_ec == 0) return ECB_OK;
-  ExportParams P{};
+  KeyDispatchParams P{};
   P.table = (const EcbEntry*)c->table.p;
   P.ec_slot = (const u32*)c->ec_slot.p;
-  P.row_len = (const u32*)c->row_len.p;
-  P.row_off = (const u32*)c->row_off.p;
-  P.arena = (const uint2*)c->arena.p;
   P.n_ec = c->n_ec;
   P.world = (u32)world;
   ArenaTargets A{};
-  for (int r = 0; r < world; ++r) {
-    if (!arena_bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
-    char* b = (char*)arena_bases[r];
-    A.hdr[r] = (unsigned long long*)b;
-    A.meta[r] = (long long*)(b + ECB_ARENA_HEADER_BYTES);
-    A.rows[r] = (int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_META_WORDS * 8);
-  }
-  A.cap_ec = (unsigned long long)cap_records;
-  A.cap_rows = (unsigned long long)cap_rows;
-  ecb_export_to_arenas_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
+  CKR(arena_targets(c, &A, world, arena_bases, cap_records));
+  ecb_key_dispatch_kernel<false><<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
   LAUNCH_CHECK("export_to_arenas");
   // remote stores are complete (and visible to the owner) when the kernel is.  On a caller-provided stream the
   // caller's next collective on that stream is the barrier between the stores and the owner's merge - no host
@@ -1222,42 +1221,39 @@ int ecb_import_arena(ecb_ctx* c) {
   unsigned long long hdr[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(hdr, c->xa_base, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (hdr[2] || hdr[0] > (unsigned long long)c->xa_cap_ec || hdr[1] > (unsigned long long)c->xa_cap_rows)
-    return fail(c, ECB_ERR_LIMIT, "exchange arena too small: %llu records / %llu rows arrived, capacity %lld / %lld",
-                hdr[0], hdr[1], (long long)c->xa_cap_ec, (long long)c->xa_cap_rows);
-  const int64_t n_rec = (int64_t)hdr[0], n_rows = (int64_t)hdr[1];
-  const char* b = (const char*)c->xa_base;
-  return ecb_import_entries(c, (const int64_t*)(b + ECB_ARENA_HEADER_BYTES),
-                            (const int32_t*)(b + ECB_ARENA_HEADER_BYTES + (size_t)c->xa_cap_ec * ECB_META_WORDS * 8),
-                            &n_rec, &n_rows, 1);
+  if (hdr[2] || hdr[0] > (unsigned long long)c->xa_cap_ec)
+    return fail(c, ECB_ERR_LIMIT, "exchange arena too small: %llu records arrived, capacity %lld", hdr[0], (long long)c->xa_cap_ec);
+  const u64 n_rec = hdr[0];
+  if (n_rec == 0) return ECB_OK;
+  if (n_rec > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "too many records in one import");
+  if (!c->table_slots) CKR(init_table(c));
+  // the owner table must be able to take every incoming record as a new EC without filling up
+  const u64 need = ((u64)c->n_ec + n_rec) * 2;
+  if (need > c->table_slots) CKR(grow_table(c, pow2_ceil(need)));
+  KeyImportParams P{};
+  P.rec = (const unsigned long long*)((const char*)c->xa_base + ECB_ARENA_HEADER_BYTES);
+  P.n_rec = (u32)n_rec;
+  P.table = (EcbEntry*)c->table.p;
+  P.mask = c->table_slots - 1;
+  P.ec_slot = (u32*)c->ec_slot.p;
+  P.ctr = c->d_ctr;
+  ecb_import_keys_kernel<<<grid_for(n_rec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P);
+  LAUNCH_CHECK("import_keys");
+  CKR(sync_counters(c));   // the one round trip of the merge: the number of merged ECs is known to the host again
+  CKR(check_device_error(c));
+  c->n_ec = c->h_ctr->n_ec;
+  return ECB_OK;
 }
 
-static FinalizeParams global_params(ecb_ctx* c);
-
-static void arena_targets(ArenaTargets* A, int world, void* const* bases, int64_t cap_records, int64_t cap_rows) {
-  for (int r = 0; r < world; ++r) {
-    char* b = (char*)bases[r];
-    A->hdr[r] = (unsigned long long*)b;
-    A->meta[r] = (long long*)(b + ECB_ARENA_HEADER_BYTES);
-    A->rows[r] = (int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)cap_records * ECB_META_WORDS * 8);
-  }
-  A->cap_ec = (unsigned long long)cap_records;
-  A->cap_rows = (unsigned long long)cap_rows;
-}
-
-int ecb_order_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
-                       const int64_t* shard_lo, const int64_t* shard_hi) {
-  if (!c || !arena_bases || !shard_lo || !shard_hi || cap_records < 1 || cap_rows < 1) return ECB_ERR_INVALID;
+int ecb_order_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t cap_records, const int64_t* shard_lo,
+                       const int64_t* shard_hi) {
+  if (!c || !arena_bases || !shard_lo || !shard_hi || cap_records < 1) return ECB_ERR_INVALID;
   if (world < 1 || world > ECB_MAX_WORLD) return fail(c, ECB_ERR_INVALID, "world %d outside [1, %d]", world, ECB_MAX_WORLD);
-  if (cap_rows >= (1ll << 40)) return fail(c, ECB_ERR_LIMIT, "arena rows must stay below 2^40");
   CK(cudaSetDevice(c->device));
   if (c->n_ec == 0) return ECB_OK;
-  OrderDispatchParams P{};
+  KeyDispatchParams P{};
   P.table = (const EcbEntry*)c->table.p;
   P.ec_slot = (const u32*)c->ec_slot.p;
-  P.row_len = (const u32*)c->row_len.p;
-  P.row_off = (const u32*)c->row_off.p;
-  P.arena = (const uint2*)c->arena.p;
   P.n_ec = c->n_ec;
   P.world = (u32)world;
   // shards with alignments, by position; they must not overlap (one read order over all ranks)
@@ -1276,60 +1272,71 @@ int ecb_order_dispatch(ecb_ctx* c, int world, void* const* arena_bases, int64_t 
   }
   P.n_shards = (u32)order.size();
   ArenaTargets A{};
-  for (int r = 0; r < world; ++r)
-    if (!arena_bases[r]) return fail(c, ECB_ERR_INVALID, "arena base of rank %d is NULL", r);
-  arena_targets(&A, world, arena_bases, cap_records, cap_rows);
-  ecb_order_dispatch_kernel<<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
+  CKR(arena_targets(c, &A, world, arena_bases, cap_records));
+  ecb_key_dispatch_kernel<true><<<grid_for(c->n_ec, 256, c->sm_count * 8), 256, 0, c->stream>>>(P, A);
   LAUNCH_CHECK("order_dispatch");
   if (c->stream == c->own_stream) CK(cudaStreamSynchronize(c->stream));   // (as ecb_export_to_arenas)
   return ECB_OK;
 }
 
-int ecb_order_build(ecb_ctx* c, int64_t shard_lo, int64_t shard_hi, ecb_slice* out) {
-  if (!c || !out || !c->xa_base || shard_hi < shard_lo) return ECB_ERR_INVALID;
+int ecb_order_build(ecb_ctx* c, const ecb_ctx* local, int64_t shard_lo, int64_t shard_hi, ecb_slice* out) {
+  if (!c || !local || !out || !c->xa_base || shard_hi < shard_lo) return ECB_ERR_INVALID;
+  if (local->device != c->device) return fail(c, ECB_ERR_INVALID, "the local context lives on another device");
   memset(out, 0, sizeof *out);
   CK(cudaSetDevice(c->device));
   unsigned long long hdr[3] = {0, 0, 0};
   CK(cudaMemcpyAsync(hdr, c->xa_base, sizeof hdr, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (hdr[2]) return fail(c, ECB_ERR_LIMIT, "exchange arena too small for the ordering dispatch");
-  const u64 n_local = hdr[0], nnz = hdr[1];
+  if (hdr[2]) return fail(c, ECB_ERR_LIMIT, "exchange arena too small for the second dispatch");
+  const u64 n_local = hdr[0];
   const u64 span = (u64)(shard_hi - shard_lo);
   if (span > 0xFFFFFFFEull) return fail(c, ECB_ERR_LIMIT, "a rank's alignments span more than 2^32 positions");
   if (n_local > span) return fail(c, ECB_ERR_INVALID, "%llu ECs arrived for a shard of %llu positions", hdr[0], (unsigned long long)span);
-  if (nnz > 0x7FFFFFFFull || n_local + 1 > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "slice exceeds the int32 fields of the EC file");
-  const char* b = (const char*)c->xa_base;
-  const unsigned long long* rec = (const unsigned long long*)(b + ECB_ARENA_HEADER_BYTES);
-  const int2* rows = (const int2*)(b + ECB_ARENA_HEADER_BYTES + (size_t)c->xa_cap_ec * ECB_META_WORDS * 8);
+  if (n_local > local->n_ec) return fail(c, ECB_ERR_INVALID, "%llu ECs arrived but the local context holds %u", hdr[0], local->n_ec);
+  if (n_local + 1 > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "slice exceeds the int32 fields of the EC file");
+  const unsigned long long* rec = (const unsigned long long*)((const char*)c->xa_base + ECB_ARENA_HEADER_BYTES);
   const size_t words = (size_t)(span / 32) + 1;
   CKR(ensure(c, c->bitmap, words * 4));
   CKR(ensure(c, c->word_rank, words * 4));
   CKR(ensure(c, c->r_a_indptr, (n_local + 1) * 4));
   CKR(ensure(c, c->r_n_data, std::max<u64>(n_local, 1) * 4));
-  CKR(ensure(c, c->first_rel, std::max<u64>(n_local, 1) * 8));   // scratch: record index per id
-  CKR(ensure(c, c->r_a_indices, std::max<u64>(nnz, 1) * 4));
-  CKR(ensure(c, c->r_a_data, std::max<u64>(nnz, 1) * 4));
-  u32* rec_of = (u32*)c->first_rel.p;
+  CKR(ensure(c, c->first_rel, std::max<u64>(n_local, 1) * 8));   // scratch: local id per record, then per slice id
+  // every row of the slice is a row of the local context: its arena fill bounds the non-zeros
+  const u64 z_bound = std::max<u64>(local->arena_used, 1);
+  CKR(ensure(c, c->r_a_indices, z_bound * 4));
+  CKR(ensure(c, c->r_a_data, z_bound * 4));
+  u32* lid_of_rec = (u32*)c->first_rel.p;
+  u32* lid_of_id = lid_of_rec + n_local;
   CK(cudaMemsetAsync(c->bitmap.p, 0, words * 4, c->stream));
   CK(cudaMemsetAsync(c->r_a_indptr.p, 0, (n_local + 1) * 4, c->stream));
   CK(cudaMemsetAsync(&c->d_ctr->scratch[5], 0, sizeof(u32), c->stream));
+  u64 nnz = 0;
   if (n_local) {
     const int g = grid_for(n_local, 256, c->sm_count * 8);
-    ecb_order_mark_kernel<<<g, 256, 0, c->stream>>>(rec, (u32)n_local, (u32)span, (u32*)c->bitmap.p, &c->d_ctr->scratch[5]);
+    ecb_order_mark_kernel<<<g, 256, 0, c->stream>>>(rec, (u32)n_local, (u32)span, (const EcbEntry*)local->table.p,
+                                                    local->table_slots - 1, (u32*)c->bitmap.p, lid_of_rec, &c->d_ctr->scratch[5]);
     LAUNCH_CHECK("order_mark");
     CKR(device_scan<true>(c, (const u32*)c->bitmap.p, (u32*)c->word_rank.p, words, 0, nullptr));
     ecb_order_lens_kernel<<<g, 256, 0, c->stream>>>(rec, (u32)n_local, (u32)span, (const u32*)c->bitmap.p,
-                                                    (const u32*)c->word_rank.p, (int32_t*)c->r_a_indptr.p,
-                                                    (int32_t*)c->r_n_data.p, rec_of);
+                                                    (const u32*)c->word_rank.p, lid_of_rec, (const u32*)local->row_len.p,
+                                                    (int32_t*)c->r_a_indptr.p, (int32_t*)c->r_n_data.p, lid_of_id);
     LAUNCH_CHECK("order_lens");
     CKR(device_scan<false>(c, (const u32*)c->r_a_indptr.p, (u32*)c->r_a_indptr.p, n_local + 1, 0, nullptr));
-    ecb_slice_rows_kernel<<<grid_for(n_local, 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        rec, rows, rec_of, (const int32_t*)c->r_a_indptr.p, (u32)n_local, (int32_t*)c->r_a_indices.p,
-        (int32_t*)c->r_a_data.p);
-    LAUNCH_CHECK("slice_rows");
+    {
+      const u32 n_blocks = (u32)((n_local + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK);
+      CK(cudaMemcpyAsync(c->h_total, (const u64*)c->scan_partials.p + n_blocks, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ecb_order_rows_kernel<<<grid_for(n_local, 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        lid_of_id, (const u32*)local->row_len.p, (const u32*)local->row_off.p, (const uint2*)local->arena.p,
+        (const int32_t*)c->r_a_indptr.p, (u32)n_local, (int32_t*)c->r_a_indices.p, (int32_t*)c->r_a_data.p);
+    LAUNCH_CHECK("order_rows");
   }
   CKR(sync_counters(c));
-  if (c->h_ctr->scratch[5]) return fail(c, ECB_ERR_INVALID, "a record outside the shard's positions arrived, or two ECs share a first read");
+  if (c->h_ctr->scratch[5])
+    return fail(c, ECB_ERR_INVALID, "second dispatch: %s", (c->h_ctr->scratch[5] & 4u) ? "an EC arrived that the local context has never seen"
+                : (c->h_ctr->scratch[5] & 2u) ? "two ECs share a first read" : "a record outside the shard's positions arrived");
+  if (n_local) nnz = *c->h_total;
+  if (nnz > 0x7FFFFFFFull) return fail(c, ECB_ERR_LIMIT, "slice exceeds the int32 fields of the EC file");
   out->id_base = 0;   // the caller knows where this rank's id range starts (the ECs of the shards in front)
   out->n_ec = (int64_t)n_local;
   out->nnz = (int64_t)nnz;

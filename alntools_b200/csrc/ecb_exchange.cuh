@@ -90,225 +90,194 @@ __global__ void __launch_bounds__(256) ecb_export_fill_kernel(const ExportParams
   }
 }
 
-// ---- fused partition + dispatch over peer memory ------------------------------------------------------
+// ---- the exchange over peer memory: two dispatches of fixed-size records, no rows ----------------------
 // Every rank owns an ARENA (plain cudaMalloc, mapped into its peers through CUDA IPC): a small header
-// {records, rows, overflow} followed by a record area and a row area.  The kernel below does what
-// ecb_export_* + an all-to-all did, in one pass: it finds the owner of every local EC and stores the
-// record and its row straight into the owner's arena over NVLink (or into its own).  Space in the remote
-// arena is reserved with ONE remote atomicAdd per CTA tile and owner; all other traffic is plain stores.
+// {records, unused, overflow} followed by a record area.
+//
+// Dispatch 1 - by key: every local EC goes as {key_lo, key_hi, first, count} to its OWNER rank (hash of the
+// key), which merges equal keys (counts summed, smallest first-occurrence kept).
+// Dispatch 2 - by first occurrence: every merged EC goes as {key_lo, key_hi, position inside the shard |
+// count << 32} to the rank whose SHARD of the read order holds its first occurrence.  EC ids are ranks of
+// first-occurrence positions and the shards partition the positions, so a rank receives one contiguous id
+// range and orders it with a bitmap over its OWN positions.
+// ROWS NEVER TRAVEL: the rank that holds an EC's first occurrence has met that EC in its own reads, so its
+// local context already holds the row; the receiver finds it by key in its local table.  (Round 1 and the
+// first form of round 2 sent every row twice - 100 bytes per EC on cfg2, kilobytes on heavily multimapping
+// input - and copied it into the owner's arena in between.)
+// Space in a remote arena is reserved with ONE remote atomicAdd per CTA tile and destination; the tile's
+// records are laid out in shared memory grouped by destination and go out with coalesced 8-byte stores -
+// NVLink wants long contiguous writes.
 #define ECB_ARENA_HEADER_BYTES 256
+#define ECB_KEYREC_WORDS 4    // dispatch 1
+#define ECB_ORDREC_WORDS 3    // dispatch 2
 
 struct ArenaTargets {
-  unsigned long long* hdr[ECB_MAX_WORLD];   // [0] records, [1] rows, [2] overflow flag
-  long long* meta[ECB_MAX_WORLD];
-  int2* rows[ECB_MAX_WORLD];
-  unsigned long long cap_ec, cap_rows;
+  unsigned long long* hdr[ECB_MAX_WORLD];   // [0] records, [2] overflow flag
+  unsigned long long* rec[ECB_MAX_WORLD];
+  unsigned long long cap_words;             // 8-byte words of the record area
 };
 
-#define ECB_XT_ROWS 2048   // rows of one tile staged in shared memory (more: stored one by one)
+struct KeyDispatchParams {
+  const EcbEntry* table;
+  const u32* ec_slot;
+  u32 n_ec;
+  u32 world;
+  // dispatch 2 only: shards with alignments, ascending by first position, and the rank that holds each
+  u64 lo[ECB_MAX_WORLD];
+  u32 dest[ECB_MAX_WORLD];
+  u32 n_shards;
+};
 
-// One tile = 256 local ECs.  The tile's records (and rows) are first laid out in shared memory grouped
-// by owner, then each owner's segment goes out with fully coalesced 8-byte stores - NVLink wants long
-// contiguous writes, not one 8-byte word per lane every 40 bytes.
-__global__ void __launch_bounds__(256) ecb_export_to_arenas_kernel(const ExportParams P, const ArenaTargets A) {
-  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];                  // per tile: ECs / rows per owner
-  __shared__ u32 s_off[2 * ECB_MAX_WORLD];                  // ... their exclusive prefix over the owners
-  __shared__ unsigned long long s_base[2 * ECB_MAX_WORLD];  // where the tile's share starts in the owner's arena
+// ORDER = false: dispatch 1 (destination = owner of the key); true: dispatch 2 (destination = rank of the shard
+// that holds the first occurrence).
+template <bool ORDER>
+__global__ void __launch_bounds__(256) ecb_key_dispatch_kernel(const KeyDispatchParams P, const ArenaTargets A) {
+  constexpr u32 WORDS = ORDER ? ECB_ORDREC_WORDS : ECB_KEYREC_WORDS;
+  __shared__ u32 s_cnt[ECB_MAX_WORLD];                  // per tile: records per destination
+  __shared__ u32 s_off[ECB_MAX_WORLD];                  // ... their exclusive prefix over the destinations
+  __shared__ unsigned long long s_base[ECB_MAX_WORLD];  // where the tile's share starts in the destination's arena
   __shared__ u32 s_drop[ECB_MAX_WORLD];
-  __shared__ u32 s_rows_total;
-  __shared__ __align__(16) long long s_meta[256 * ECB_META_WORDS];
-  __shared__ __align__(16) int2 s_rows[ECB_XT_ROWS];
+  __shared__ __align__(16) unsigned long long s_rec[256 * WORDS];
   const u32 W = P.world;
   const u32 tiles = (P.n_ec + blockDim.x - 1) / blockDim.x;
   for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    for (u32 i = threadIdx.x; i < 2 * W; i += blockDim.x) s_cnt[i] = 0u;
+    for (u32 i = threadIdx.x; i < W; i += blockDim.x) s_cnt[i] = 0u;
     __syncthreads();
     const u32 e = tile * blockDim.x + threadIdx.x;
     const bool live = e < P.n_ec;
     EcbEntry en{};
-    u32 owner = 0, len = 0, idx = 0, roff = 0;
-    if (live) {
-      en = P.table[P.ec_slot[e]];
-      owner = ecb_owner_of(Key128{en.key_lo, en.key_hi}, W);
-      len = P.row_len[e];
-      idx = atomicAdd(&s_cnt[owner], 1u);
-      roff = atomicAdd(&s_cnt[W + owner], len);
-    }
-    __syncthreads();
-    if (threadIdx.x < W) {   // reserve space in the owners' arenas: one remote atomic per owner and area
-      const u32 o = threadIdx.x;
-      const u32 ce = s_cnt[o], cr = s_cnt[W + o];
-      s_drop[o] = 0u;
-      if (ce) {
-        const unsigned long long be = atomicAdd(A.hdr[o] + 0, (unsigned long long)ce);
-        const unsigned long long br = atomicAdd(A.hdr[o] + 1, (unsigned long long)cr);
-        s_base[o] = be;
-        s_base[W + o] = br;
-        if (be + ce > A.cap_ec || br + cr > A.cap_rows) {
-          atomicExch(A.hdr[o] + 2, 1ull);
-          s_drop[o] = 1u;
-        }
-      }
-    }
-    if (threadIdx.x == 32) {   // meanwhile: tile-local offsets of the owners' segments
-      u32 ae = 0, ar = 0;
-      for (u32 o = 0; o < W; ++o) {
-        s_off[o] = ae;
-        s_off[W + o] = ar;
-        ae += s_cnt[o];
-        ar += s_cnt[W + o];
-      }
-      s_rows_total = ar;
-    }
-    __syncthreads();
-    const bool stage_rows = s_rows_total <= ECB_XT_ROWS;
-    if (live && !s_drop[owner]) {
-      const unsigned long long rat = s_base[W + owner] + roff;
-      long long* m = s_meta + (size_t)(s_off[owner] + idx) * ECB_META_WORDS;
-      m[0] = (long long)en.key_lo;
-      m[1] = (long long)en.key_hi;
-      m[2] = (long long)en.first;
-      m[3] = (long long)(((u64)(en.countm1 + 1u) << 32) | len);
-      m[4] = (long long)rat;
-      const uint2* src = P.arena + P.row_off[e];
-      if (stage_rows) {
-        int2* dst = s_rows + s_off[W + owner] + roff;
-        for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
-      } else {
-        int2* dst = A.rows[owner] + rat;
-        for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
-      }
-    }
-    __syncthreads();
-    for (u32 o = 0; o < W; ++o) {
-      if (s_cnt[o] == 0u || s_drop[o]) continue;
-      const u32 n_words = s_cnt[o] * ECB_META_WORDS;
-      const long long* src = s_meta + (size_t)s_off[o] * ECB_META_WORDS;
-      long long* dst = A.meta[o] + s_base[o] * ECB_META_WORDS;
-      for (u32 w = threadIdx.x; w < n_words; w += blockDim.x) dst[w] = src[w];
-      if (stage_rows) {
-        const u32 n_rows = s_cnt[W + o];
-        const long long* rsrc = reinterpret_cast<const long long*>(s_rows + s_off[W + o]);
-        long long* rdst = reinterpret_cast<long long*>(A.rows[o] + s_base[W + o]);
-        for (u32 w = threadIdx.x; w < n_rows; w += blockDim.x) rdst[w] = rsrc[w];
-      }
-    }
-    __syncthreads();
-  }
-}
-
-#define ECB_SLICE_WORDS 2
-
-// ---- second dispatch: every merged EC goes to the rank whose SHARD holds its first occurrence.  EC ids are ranks of first-occurrence positions and the shards partition the positions, so
-// the ECs that arrive at a rank form one contiguous id range, ordered by their position inside the shard:
-// the receiver ranks them with a bitmap over ITS OWN positions only.  Nothing global is built: no bitmap over
-// all ranks' positions, no all-reduce of it, no padded arrays; the id range of a rank starts where the ranges
-// of the shards in front of it end (one all-gather of a count).  Record: {position inside the shard |
-// count << 32, row offset | len << 40} plus the row.  (Round 1 dispatched by EC-id range after ranking a bitmap
-// over ALL ranks' positions that had been OR-ed by an all-reduce - 61 MB at 8 GPUs; that form is gone.)
-struct OrderDispatchParams {
-  const EcbEntry* table;
-  const u32* ec_slot;
-  const u32* row_len;
-  const u32* row_off;
-  const uint2* arena;
-  u32 n_ec;
-  u32 world;
-  u64 lo[ECB_MAX_WORLD];      // first position of each shard, ascending; ranks without alignments come last
-  u32 dest[ECB_MAX_WORLD];    // ... and the rank that holds it
-  u32 n_shards;               // shards with alignments
-};
-
-__global__ void __launch_bounds__(256) ecb_order_dispatch_kernel(const OrderDispatchParams P, const ArenaTargets A) {
-  __shared__ u32 s_cnt[2 * ECB_MAX_WORLD];
-  __shared__ u32 s_off[2 * ECB_MAX_WORLD];
-  __shared__ unsigned long long s_base[2 * ECB_MAX_WORLD];
-  __shared__ u32 s_drop[ECB_MAX_WORLD];
-  __shared__ u32 s_rows_total;
-  __shared__ __align__(16) unsigned long long s_rec[256 * ECB_SLICE_WORDS];
-  __shared__ __align__(16) int2 s_rows[ECB_XT_ROWS];
-  const u32 W = P.world;
-  const u32 tiles = (P.n_ec + blockDim.x - 1) / blockDim.x;
-  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    for (u32 i = threadIdx.x; i < 2 * W; i += blockDim.x) s_cnt[i] = 0u;
-    __syncthreads();
-    const u32 e = tile * blockDim.x + threadIdx.x;
-    const bool live = e < P.n_ec;
-    u32 dest = 0, len = 0, idx = 0, roff = 0, count = 0;
+    u32 dest = 0, idx = 0;
     u64 rel = 0;
     if (live) {
-      const EcbEntry en = P.table[P.ec_slot[e]];
-      u32 k = 0;   // the last shard that starts at or before the position
-      while (k + 1 < P.n_shards && P.lo[k + 1] <= en.first) ++k;
-      dest = P.dest[k];
-      rel = en.first - P.lo[k];
-      count = en.countm1 + 1u;
-      len = P.row_len[e];
+      en = P.table[P.ec_slot[e]];
+      if (ORDER) {
+        u32 k = 0;   // the last shard that starts at or before the position
+        while (k + 1 < P.n_shards && P.lo[k + 1] <= en.first) ++k;
+        dest = P.dest[k];
+        rel = en.first - P.lo[k];
+      } else {
+        dest = ecb_owner_of(Key128{en.key_lo, en.key_hi}, W);
+      }
       idx = atomicAdd(&s_cnt[dest], 1u);
-      roff = atomicAdd(&s_cnt[W + dest], len);
     }
     __syncthreads();
-    if (threadIdx.x < W) {
+    if (threadIdx.x < W) {   // reserve space in the destinations' arenas: one remote atomic each
       const u32 o = threadIdx.x;
-      const u32 ce = s_cnt[o], cr = s_cnt[W + o];
+      const u32 ce = s_cnt[o];
       s_drop[o] = 0u;
       if (ce) {
         const unsigned long long be = atomicAdd(A.hdr[o] + 0, (unsigned long long)ce);
-        const unsigned long long br = atomicAdd(A.hdr[o] + 1, (unsigned long long)cr);
         s_base[o] = be;
-        s_base[W + o] = br;
-        if ((be + ce) * ECB_SLICE_WORDS > A.cap_ec * ECB_META_WORDS || br + cr > A.cap_rows) {
+        if ((be + ce) * WORDS > A.cap_words) {
           atomicExch(A.hdr[o] + 2, 1ull);
           s_drop[o] = 1u;
         }
       }
     }
-    if (threadIdx.x == 32) {
-      u32 ae = 0, ar = 0;
+    if (threadIdx.x == 32) {   // meanwhile: tile-local offsets of the destinations' segments
+      u32 ae = 0;
       for (u32 o = 0; o < W; ++o) {
         s_off[o] = ae;
-        s_off[W + o] = ar;
         ae += s_cnt[o];
-        ar += s_cnt[W + o];
       }
-      s_rows_total = ar;
     }
     __syncthreads();
-    const bool stage_rows = s_rows_total <= ECB_XT_ROWS;
     if (live && !s_drop[dest]) {
-      const unsigned long long rat = s_base[W + dest] + roff;
-      unsigned long long* r = s_rec + (size_t)(s_off[dest] + idx) * ECB_SLICE_WORDS;
-      r[0] = (rel > 0xFFFFFFFEull ? 0xFFFFFFFFull : rel) | ((unsigned long long)count << 32);
-      r[1] = rat | ((unsigned long long)len << 40);
-      const uint2* src = P.arena + P.row_off[e];
-      int2* dst = stage_rows ? s_rows + s_off[W + dest] + roff : A.rows[dest] + rat;
-      for (u32 j = 0; j < len; ++j) dst[j] = make_int2((int)src[j].x, (int)src[j].y);
+      unsigned long long* r = s_rec + (size_t)(s_off[dest] + idx) * WORDS;
+      r[0] = en.key_lo;
+      r[1] = en.key_hi;
+      if (ORDER) {
+        r[2] = (rel > 0xFFFFFFFEull ? 0xFFFFFFFFull : rel) | ((unsigned long long)(en.countm1 + 1u) << 32);
+      } else {
+        r[2] = en.first;
+        r[3] = (unsigned long long)(en.countm1 + 1u);
+      }
     }
     __syncthreads();
     for (u32 o = 0; o < W; ++o) {
       if (s_cnt[o] == 0u || s_drop[o]) continue;
-      const u32 n_words = s_cnt[o] * ECB_SLICE_WORDS;
-      const unsigned long long* src = s_rec + (size_t)s_off[o] * ECB_SLICE_WORDS;
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.meta[o]) + s_base[o] * ECB_SLICE_WORDS;
+      const u32 n_words = s_cnt[o] * WORDS;
+      const unsigned long long* src = s_rec + (size_t)s_off[o] * WORDS;
+      unsigned long long* dst = A.rec[o] + s_base[o] * WORDS;
       for (u32 w = threadIdx.x; w < n_words; w += blockDim.x) dst[w] = src[w];
-      if (stage_rows) {
-        const u32 n_rows = s_cnt[W + o];
-        const long long* rsrc = reinterpret_cast<const long long*>(s_rows + s_off[W + o]);
-        long long* rdst = reinterpret_cast<long long*>(A.rows[o] + s_base[W + o]);
-        for (u32 w = threadIdx.x; w < n_rows; w += blockDim.x) rdst[w] = rsrc[w];
-      }
     }
     __syncthreads();
   }
 }
 
-// Slice assembly, pass 0: one bit per arrived EC at its position inside the shard.
+// Owner merge of dispatch 1 (bam_utils.py:693-698: equal keys - counts summed, smallest first occurrence kept).
+// Provisional ids of the new keys are reserved once per CTA tile.
+struct KeyImportParams {
+  const unsigned long long* rec;
+  u32 n_rec;
+  EcbEntry* table;
+  u32 mask;
+  u32* ec_slot;
+  EcbCounters* ctr;
+};
+
+__global__ void __launch_bounds__(256) ecb_import_keys_kernel(const KeyImportParams P) {
+  __shared__ u32 s_scan[10];
+  const u32 tiles = (P.n_rec + blockDim.x - 1) / blockDim.x;
+  for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const u32 i = tile * blockDim.x + threadIdx.x;
+    bool claimed = false;
+    u32 slot = ECB_NONE;
+    if (i < P.n_rec) {
+      const unsigned long long* m = P.rec + (size_t)i * ECB_KEYREC_WORDS;
+      const Key128 key{m[0], m[1]};
+      const u64 first = m[2];
+      u64 seen;
+      slot = table_find_or_claim<true>(P.table, P.mask, key, claimed, seen);
+      if (slot == ECB_NONE) {
+        atomicOr(&P.ctr->error, ECB_DEVERR_EC_CAPACITY);
+        claimed = false;
+      } else {
+        EcbEntry* e = P.table + slot;
+        atomicAdd(&e->countm1, (u32)m[3]);
+        if (first < seen) atomicMin(&e->first, first);
+      }
+    }
+    u32 n_new;
+    const u32 id_excl = block_excl_scan_u32(claimed ? 1u : 0u, s_scan, n_new);
+    if (threadIdx.x == 0) s_scan[9] = n_new ? atomicAdd(&P.ctr->n_ec, n_new) : 0u;
+    __syncthreads();
+    const u32 id = s_scan[9] + id_excl;
+    __syncthreads();
+    if (claimed) {
+      P.table[slot].aux = id;
+      P.ec_slot[id] = slot;
+    }
+  }
+}
+
+// Lookup in an EC table (slot hash of the EC keys); ECB_NONE if absent.
+__device__ __forceinline__ u32 ec_table_find(const EcbEntry* table, u32 mask, const Key128& key) {
+  u32 slot = ec_slot_hash(key) & mask;
+  for (u32 p = 0; p <= mask; ++p) {
+    Key128 k;
+    u64 first;
+    u32 cm1, aux;
+    load_entry_cg(table + slot, k, first, cm1, aux);
+    if (key_eq(k, key)) return slot;
+    if (key_empty(k)) return ECB_NONE;
+    slot = (slot + 1) & mask;
+  }
+  return ECB_NONE;
+}
+
+// Slice assembly at the receiver of dispatch 2, pass 0: one bit per arrived EC at its position inside the shard,
+// and the EC's id in the LOCAL context (found by key: this rank has met the EC in its own reads).
 __global__ void __launch_bounds__(256) ecb_order_mark_kernel(const unsigned long long* __restrict__ rec, u32 n_rec, u32 span,
-                                                            u32* bitmap, u32* bad) {
+                                                            const EcbEntry* __restrict__ local_table, u32 local_mask,
+                                                            u32* bitmap, u32* local_id, u32* bad) {
   for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-    const u32 rel = (u32)(rec[(size_t)r * ECB_SLICE_WORDS] & 0xFFFFFFFFull);
-    if (rel >= span) {
-      atomicOr(bad, 1u);
+    const unsigned long long* m = rec + (size_t)r * ECB_ORDREC_WORDS;
+    const u32 rel = (u32)(m[2] & 0xFFFFFFFFull);
+    const u32 slot = ec_table_find(local_table, local_mask, Key128{m[0], m[1]});
+    local_id[r] = slot == ECB_NONE ? ECB_NONE : local_table[slot].aux;
+    if (rel >= span || slot == ECB_NONE) {
+      atomicOr(bad, slot == ECB_NONE ? 4u : 1u);
       continue;
     }
     const u32 bit = 1u << (rel & 31);
@@ -316,36 +285,39 @@ __global__ void __launch_bounds__(256) ecb_order_mark_kernel(const unsigned long
   }
 }
 
-// ... pass 1: the rank of its bit is an EC's id inside the slice; row length, count and record index go there.
+// ... pass 1: the rank of its bit is an EC's id inside the slice; row length (of the LOCAL row), merged count and
+// local id go there.
 __global__ void __launch_bounds__(256) ecb_order_lens_kernel(const unsigned long long* __restrict__ rec, u32 n_rec, u32 span,
                                                             const u32* __restrict__ bitmap, const u32* __restrict__ word_rank,
-                                                            int32_t* lens, int32_t* counts, u32* rec_of) {
+                                                            const u32* __restrict__ local_id, const u32* __restrict__ local_row_len,
+                                                            int32_t* lens, int32_t* counts, u32* id_of) {
   for (u32 r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
-    const unsigned long long w0 = rec[(size_t)r * ECB_SLICE_WORDS], w1 = rec[(size_t)r * ECB_SLICE_WORDS + 1];
-    const u32 rel = (u32)(w0 & 0xFFFFFFFFull);
-    if (rel >= span) continue;
+    const unsigned long long w2 = rec[(size_t)r * ECB_ORDREC_WORDS + 2];
+    const u32 rel = (u32)(w2 & 0xFFFFFFFFull);
+    const u32 lid = local_id[r];
+    if (rel >= span || lid == ECB_NONE) continue;
     const u32 w = rel >> 5, b = rel & 31;
     const u32 i = word_rank[w] + (u32)__popc(bitmap[w] & ((1u << b) - 1u));
     if (i >= n_rec) continue;   // (only after a duplicate position, which pass 0 has reported)
-    lens[i] = (int32_t)(w1 >> 40);
-    counts[i] = (int32_t)(w0 >> 32);
-    rec_of[i] = r;
+    lens[i] = (int32_t)local_row_len[lid];
+    counts[i] = (int32_t)(w2 >> 32);
+    id_of[i] = lid;
   }
 }
 
-// Slice assembly, pass 2: rows to their CSR position (thread per id).
-__global__ void __launch_bounds__(256) ecb_slice_rows_kernel(const unsigned long long* __restrict__ rec,
-                                                            const int2* __restrict__ rows, const u32* __restrict__ rec_of,
+// ... pass 2: rows from the local arena to their CSR position (thread per id).
+__global__ void __launch_bounds__(256) ecb_order_rows_kernel(const u32* __restrict__ id_of, const u32* __restrict__ local_row_len,
+                                                            const u32* __restrict__ local_row_off, const uint2* __restrict__ local_arena,
                                                             const int32_t* __restrict__ indptr, u32 slice_n,
                                                             int32_t* indices, int32_t* data) {
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < slice_n; i += gridDim.x * blockDim.x) {
-    const unsigned long long w1 = rec[(size_t)rec_of[i] * ECB_SLICE_WORDS + 1];
-    const int2* src = rows + (w1 & ((1ull << 40) - 1ull));
-    const u32 len = (u32)(w1 >> 40);
+    const u32 lid = id_of[i];
+    const uint2* src = local_arena + local_row_off[lid];
+    const u32 len = local_row_len[lid];
     const size_t dst = (size_t)indptr[i];
     for (u32 j = 0; j < len; ++j) {
-      indices[dst + j] = src[j].x;
-      data[dst + j] = src[j].y;
+      indices[dst + j] = (int32_t)src[j].x;
+      data[dst + j] = (int32_t)src[j].y;
     }
   }
 }

@@ -4,13 +4,15 @@ The reference's only parallelism is a process pool over contiguous BAM chunks wh
 merged in chunk order (alntools/bam_utils.py:647-724).  Here every rank builds a local EC table from
 its shard (order_base = global offset of the shard) and the merge becomes:
 
-  dispatch 1   local ECs (key, first, count, row) stored straight into the arena of their OWNER rank
+  dispatch 1   local ECs {key, first, count} stored straight into the arena of their OWNER rank
                (hash of the key) over peer memory by one kernel                          [NVLink]
   owner merge  equal keys: counts summed, smallest first-occurrence kept                [kernel]
-  dispatch 2   every merged EC to the rank whose SHARD holds its first occurrence; there a bitmap over
-               the rank's own positions orders them: ids are ranks of first occurrences and the shards
-               partition the positions, so every rank ends up with one contiguous id range of the
-               final matrices (result_on="slices")                                       [NVLink]
+  dispatch 2   every merged EC {key, position, count} to the rank whose SHARD holds its first
+               occurrence; there a bitmap over the rank's own positions orders them (ids are ranks of
+               first occurrences and the shards partition the positions) and the rows come from the
+               rank's LOCAL context - it has met the EC in its own reads.  Rows never travel; every
+               rank ends up with one contiguous id range of the final matrices
+               (result_on="slices")                                                      [NVLink]
   The barriers between these steps are tiny collectives on the stream the kernels run on: nothing in
   between waits for the host.  (result_on="all" / "rank0" and the NCCL / gloo path keep the first form:
   all-to-all, first-occurrence bitmap OR-ed by an all-reduce, rows scattered at their global ids.)
@@ -92,93 +94,81 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
         local.set_stream(cur)
     ph = _Phases(device)
     me = dist.get_rank(group)
-    p2p = (device.type == "cuda" and world > 1 and hasattr(local, "export_to_arenas")
-           and os.environ.get("ECB_EXCHANGE", "p2p") != "nccl")
+    p2p = result_on == "slices"
+    if p2p and not (device.type == "cuda" and hasattr(local, "export_to_arenas")):
+        raise RuntimeError('result_on="slices" needs the peer-memory exchange (CUDA devices that can map each other)')
     if p2p:
         # ---- fused partition + dispatch: every local EC is stored straight into its owner's arena
         # over NVLink by ONE kernel (peer memory mapped through CUDA IPC); no staging, no all-to-all
         owner = make_owner()
         owner.set_stream(cur)
         arena = getattr(owner, "_exchange_arena", None)
-        if arena is not None and result_on == "slices":
+        if arena is not None:
             # the arenas exist (a later step of the same job): clear the header and put ONE small collective on
             # the stream as the barrier between "every arena is clear" and "peers store" - no host round trip;
             # whether everything fits is decided by the overflow flag in the arena header
             owner.arena_reset()
             _stream_barrier(device, group)
         else:
-            st = local.stats()
-            if arena is not None:
-                owner.arena_reset()
-            info = torch.tensor([st["table_used"], st["row_entries"], 0 if arena is None else arena["cap_ec"],
-                                 0 if arena is None else arena["cap_rows"]], dtype=torch.int64, device=device)
+            # first call of a job: size the arenas (an owner receives about one rank's worth of ECs; twice the
+            # largest local table leaves room for a skewed partition), create them, map the peers'
+            info = torch.tensor([local.stats()["table_used"]], dtype=torch.int64, device=device)
             gathered = [torch.empty_like(info) for _ in range(world)]
-            dist.all_gather(gathered, info, group=group)     # also the barrier between "reset" and "store"
-            g = torch.stack(gathered).tolist()
-            need_ec = 2 * max(r[0] for r in g) + 1024
-            need_rows = 2 * max(r[1] for r in g) + 1024
-            if any(r[2] < need_ec // 2 + 512 or r[3] < need_rows // 2 + 512 for r in g) or arena is None:
-                if arena is not None:
-                    raise RuntimeError("exchange arena too small for this input; create the owner context per job")
-                handle, base = owner.arena_create(need_ec, need_rows)
-                hs = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
-                dist.all_gather(hs, torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device), group=group)
-                bases = [base if r == me else owner.arena_open_peer(bytes(hs[r].cpu().tolist())) for r in range(world)]
-                arena = {"bases": bases, "cap_ec": need_ec, "cap_rows": need_rows}
-                owner._exchange_arena = arena
-                dist.barrier(group=group)                     # every arena exists and is zeroed
+            dist.all_gather(gathered, info, group=group)
+            need_ec = 2 * max(int(t.item()) for t in gathered) + 1024
+            handle, base = owner.arena_create(need_ec)
+            hs = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+            dist.all_gather(hs, torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device), group=group)
+            bases = [base if r == me else owner.arena_open_peer(bytes(hs[r].cpu().tolist())) for r in range(world)]
+            arena = {"bases": bases, "cap_ec": need_ec}
+            owner._exchange_arena = arena
+            dist.barrier(group=group)                     # every arena exists and is zeroed
         ph.mark("setup")
-        min_base, max_end = local.export_to_arenas(arena["bases"], arena["cap_ec"], arena["cap_rows"])
-        ph.mark("export+store")
-        if result_on == "slices":
-            # every rank's shard of the read order; the all-gather is the barrier between "store" and "merge"
-            mine = torch.tensor([min_base, max_end], dtype=torch.int64, device=device)
-            spans = torch.empty(2 * world, dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(spans, mine, group=group)
-            # a rank that fails here (an arena that turned out too small) must not leave its peers waiting in a
-            # collective: it carries on with what it has, the failure travels with the all-gather of the slice
-            # sizes below, and every rank raises
-            failure = None
-            try:
-                owner.import_arena()
-            except Exception as exc:         # noqa: BLE001 - re-raised on every rank below
-                failure = exc
-            owner.arena_reset()              # reused by the second dispatch ...
-            _stream_barrier(device, group)   # ... once every rank has merged what it received
-            ph.mark("import")
-            spans = spans.tolist()
-            lo, hi = spans[0::2], spans[1::2]
-            if not any(h > l for l, h in zip(lo, hi)):
-                raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
-            owner.order_dispatch(arena["bases"], arena["cap_ec"], arena["cap_rows"], lo, hi)
-            _stream_barrier(device, group)   # every rank's ECs have landed
-            ph.mark("order dispatch")
-            sl = None
-            try:
-                sl = owner.order_build(lo[me], hi[me])
-            except Exception as exc:         # noqa: BLE001
-                failure = failure or exc
-            ph.mark("order build")
-            # the id range of a rank starts behind the ECs of the shards in front of it
-            sizes = torch.empty(2 * world, dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(sizes, torch.tensor([sl["n_ec"] if sl else 0, 1 if failure else 0],
-                                                            dtype=torch.int64, device=device), group=group)
-            sizes = sizes.tolist()
-            if failure is not None:
-                raise failure
-            if any(sizes[1::2]):
-                raise RuntimeError("the multi-GPU exchange failed on rank(s) %s" % [r for r in range(world) if sizes[2 * r + 1]])
-            sizes = sizes[0::2]
-            id_base = sum(n for r, n in enumerate(sizes) if hi[r] > lo[r] and (lo[r], r) < (lo[me], me))
-            ph.report()
-            return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
-                    "n_data": sl["n_data"], "n_ec": sum(sizes), "id_base": id_base, "n_ec_local": sl["n_ec"],
-                    "nnz_local": sl["nnz"], "nnz_a": None}
-        span = torch.tensor([-min_base if max_end > min_base else -(1 << 62), max_end], dtype=torch.int64, device=device)
-        dist.all_reduce(span, op=dist.ReduceOp.MAX, group=group)   # the barrier between "store" and "merge"
-        g_min, g_max = -int(span[0].item()), int(span[1].item())
-        owner.import_arena()
-        ph.mark("import")
+        min_base, max_end = local.export_to_arenas(arena["bases"], arena["cap_ec"])
+        ph.mark("dispatch 1")
+        # every rank's shard of the read order; the all-gather is the barrier between "store" and "merge"
+        mine = torch.tensor([min_base, max_end], dtype=torch.int64, device=device)
+        spans = torch.empty(2 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(spans, mine, group=group)
+        # a rank that fails from here on (an arena that turned out too small) must not leave its peers waiting in
+        # a collective: it carries on with what it has, the failure travels with the all-gather of the slice
+        # sizes below, and every rank raises
+        failure = None
+        try:
+            owner.import_arena()
+        except Exception as exc:         # noqa: BLE001 - re-raised on every rank below
+            failure = exc
+        owner.arena_reset()              # reused by the second dispatch ...
+        _stream_barrier(device, group)   # ... once every rank has merged what it received
+        ph.mark("merge")
+        spans = spans.tolist()
+        lo, hi = spans[0::2], spans[1::2]
+        if not any(h > l for l, h in zip(lo, hi)):
+            raise RuntimeError("The shape must be a tuple of three positive integers.")  # zero ECs everywhere
+        owner.order_dispatch(arena["bases"], arena["cap_ec"], lo, hi)
+        _stream_barrier(device, group)   # every rank's ECs have landed
+        ph.mark("dispatch 2")
+        sl = None
+        try:
+            sl = owner.order_build(local, lo[me], hi[me])
+        except Exception as exc:         # noqa: BLE001
+            failure = failure or exc
+        ph.mark("order build")
+        # the id range of a rank starts behind the ECs of the shards in front of it
+        sizes = torch.empty(2 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(sizes, torch.tensor([sl["n_ec"] if sl else 0, 1 if failure else 0],
+                                                        dtype=torch.int64, device=device), group=group)
+        sizes = sizes.tolist()
+        if failure is not None:
+            raise failure
+        if any(sizes[1::2]):
+            raise RuntimeError("the multi-GPU exchange failed on rank(s) %s" % [r for r in range(world) if sizes[2 * r + 1]])
+        sizes = sizes[0::2]
+        id_base = sum(n for r, n in enumerate(sizes) if hi[r] > lo[r] and (lo[r], r) < (lo[me], me))
+        ph.report()
+        return {"a_indptr": sl["a_indptr"], "a_indices": sl["a_indices"], "a_data": sl["a_data"],
+                "n_data": sl["n_data"], "n_ec": sum(sizes), "id_base": id_base, "n_ec_local": sl["n_ec"],
+                "nnz_local": sl["nnz"], "nnz_a": None}
     else:
         meta, rows, ec_counts, row_counts, min_base, max_end = local.export_partition(world)
         ph.mark("export")
@@ -215,8 +205,6 @@ def distributed_finalize(local, make_owner, device, group=None, result_on="all")
     ph.mark("bitmap")
     n_ec = owner.global_count(bitmap)
     ph.mark("count")
-    if result_on == "slices":
-        raise RuntimeError('result_on="slices" needs the peer-memory exchange')
     lens = torch.zeros(n_ec + 1, dtype=torch.int32, device=device)
     counts = torch.zeros(n_ec, dtype=torch.int32, device=device)
     owner.global_lens(lens, counts)

@@ -164,11 +164,9 @@ const char* ecb_last_error(const ecb_ctx* ctx);
  *   5. ecb_global_lens / all-reduce / ecb_global_indptr / ecb_global_rows / all-reduce: every rank
  *      scatters its owned rows and counts into zero-initialised global arrays; supports are disjoint,
  *      so a SUM all-reduce assembles the final CSR A matrix and the counts on every rank.
- * That is the form for any transport (NCCL, gloo in the CPU tests).  Where the ranks can map each other's
- * memory (one process per GPU on an NVLink / NVSwitch box) steps 1-3 are one kernel that stores into the
- * owners' arenas (ecb_export_to_arenas / ecb_import_arena) and steps 4-5 are replaced by a second dispatch
- * keyed by the shard that holds an EC's first occurrence (ecb_order_dispatch / ecb_order_build): nothing
- * global is built and the final matrices stay partitioned, one contiguous EC-id range per rank.
+ * That is the form for any transport (NCCL, gloo in the CPU tests); it leaves the whole matrix on every rank
+ * (or on rank 0).  Where the ranks can map each other's memory the exchange further down replaces all five
+ * steps and leaves the final matrices partitioned, one contiguous EC-id range per rank.
  * All pointers marked "device" are device memory of the context's GPU owned by the caller.
  */
 /* Add `delta` (>= 0) to the order key of everything pushed so far: a rank that decodes one shard of a file
@@ -194,41 +192,51 @@ int ecb_export_partition(ecb_ctx* ctx, int world, ecb_export* out);
 int ecb_import_entries(ecb_ctx* ctx, const int64_t* meta_device, const int32_t* rows_device,
                        const int64_t* part_ec_counts, const int64_t* part_row_counts, int n_parts);
 
-/* ---- fused partition + dispatch over peer memory (replaces steps 1-3 when the ranks can map each
- * other's memory: one process per GPU on an NVLink / NVSwitch box) ------------------------------------
- * Each rank creates an ARENA on its OWNER context (device memory from cudaMalloc, exportable through
- * CUDA IPC), hands the 64-byte IPC handle to its peers and maps theirs.  ecb_export_to_arenas on the
- * LOCAL context then finds the owner of every local EC and stores record and row directly into the
- * owner's arena over NVLink (one remote atomicAdd per CTA tile and owner reserves the space), and
- * ecb_import_arena on the owner merges what arrived.  The caller brackets the stores with barriers:
- *     ecb_arena_reset (every rank) - barrier - ecb_export_to_arenas - barrier - ecb_import_arena.
- * arena_bases[r] = base address of rank r's arena as seen from THIS process (own base for r == rank). */
-int ecb_arena_create(ecb_ctx* owner_ctx, int64_t cap_records, int64_t cap_rows, void* ipc_handle_out /* 64 bytes */,
-                     void** base_out);
+/* ---- the exchange over peer memory (one process per GPU on an NVLink / NVSwitch box; the default of the
+ * multi-GPU path) ---------------------------------------------------------------------------------------
+ * Each rank creates an ARENA on its OWNER context (device memory from cudaMalloc, exportable through CUDA IPC),
+ * hands the 64-byte IPC handle to its peers and maps theirs.  Two dispatches of fixed-size records go through
+ * it, each one kernel that stores straight into the destination ranks' arenas over NVLink (one remote
+ * atomicAdd per CTA tile and destination reserves the space):
+ *   ecb_export_to_arenas (LOCAL context)   every local EC as {key, first, count} to its owner rank (hash of the
+ *                                          key);
+ *   ecb_import_arena     (OWNER context)   the owner merges what arrived: counts summed, smallest first
+ *                                          occurrence kept (alntools/bam_utils.py:693-698);
+ *   ecb_order_dispatch   (OWNER context)   every merged EC as {key, position inside the shard, count} to the rank
+ *                                          whose shard [shard_lo[r], shard_hi[r]) of the global read order holds
+ *                                          its first occurrence;
+ *   ecb_order_build      (OWNER + LOCAL)   EC ids are ranks of first-occurrence positions and the shards
+ *                                          partition the positions, so what arrived is one contiguous id range:
+ *                                          it is ordered with a bitmap over this rank's OWN positions and the
+ *                                          rows are taken from the LOCAL context - the rank that holds an EC's
+ *                                          first occurrence has met the EC in its own reads.  Rows never travel;
+ *                                          nothing global is built (no bitmap over all positions, no all-reduce,
+ *                                          no ecb_global_* call).  id_base of the result is left 0: the slice
+ *                                          starts after the ECs of the shards in front, which the caller learns
+ *                                          from one all-gather of the slice sizes.
+ * The caller brackets the stores with barriers:
+ *     ecb_arena_reset (every rank) - barrier - ecb_export_to_arenas - barrier - ecb_import_arena -
+ *     ecb_arena_reset - barrier - ecb_order_dispatch - barrier - ecb_order_build.
+ * On a caller-provided stream (ecb_set_stream) reset, export and dispatch are stream-ordered and the barriers
+ * are collectives on that stream (the host does not wait); a context on its own stream synchronises in each.
+ * arena_bases[r] = base address of rank r's arena as seen from THIS process (own base for r == rank);
+ * cap_records = records (of 32 bytes) every arena can take. */
+int ecb_arena_create(ecb_ctx* owner_ctx, int64_t cap_records, void* ipc_handle_out /* 64 bytes */, void** base_out);
 int ecb_arena_open_peer(ecb_ctx* owner_ctx, const void* ipc_handle /* 64 bytes */, void** base_out);
 int ecb_arena_reset(ecb_ctx* owner_ctx);
 int ecb_export_to_arenas(ecb_ctx* local_ctx, int world, void* const* arena_bases, int64_t cap_records,
-                         int64_t cap_rows, int64_t* min_base, int64_t* max_end);
+                         int64_t* min_base, int64_t* max_end);
 int ecb_import_arena(ecb_ctx* owner_ctx);
 
-/* ---- the final matrices in slices, one per rank -------------------------------------------------------- */
+/* This rank's slice of the final matrices: a_indptr[n_ec + 1] (offsets local to the slice), a_indices, a_data
+ * and n_data (read counts), all device memory of the owner context, valid until the next call on it. */
 typedef struct ecb_slice {
   int64_t id_base, n_ec, nnz;
   const int32_t *a_indptr, *a_indices, *a_data, *n_data;
 } ecb_slice;
-
-/* ---- second dispatch (the multi-GPU path; the arenas of the first dispatch are reused: reset them after
- * ecb_import_arena): every merged EC goes to the
- * rank whose shard [shard_lo[r], shard_hi[r]) of the global read order holds its first occurrence.  EC ids are
- * ranks of first-occurrence positions and the shards partition the positions, so a rank receives one contiguous
- * id range and orders it with a bitmap over its OWN positions: no global bitmap, no all-reduce, no
- * ecb_global_* call.  ecb_order_dispatch on the OWNER context (after ecb_import_arena and ecb_arena_reset, behind
- * a barrier); after another barrier ecb_order_build turns what arrived into this rank's slice (id_base is left
- * 0: the slice starts after the ECs of the shards in front, which the caller learns from one all-gather).
- * Both calls are stream-ordered on the context's stream; the barriers are collectives on the same stream. */
-int ecb_order_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, int64_t cap_records, int64_t cap_rows,
+int ecb_order_dispatch(ecb_ctx* owner_ctx, int world, void* const* arena_bases, int64_t cap_records,
                        const int64_t* shard_lo, const int64_t* shard_hi);
-int ecb_order_build(ecb_ctx* owner_ctx, int64_t shard_lo, int64_t shard_hi, ecb_slice* out);
+int ecb_order_build(ecb_ctx* owner_ctx, const ecb_ctx* local_ctx, int64_t shard_lo, int64_t shard_hi, ecb_slice* out);
 
 /* Set the first-occurrence bits of the ECs this context owns in bitmap[n_words] (bit i = order key
  * min_base + i).  The caller zero-fills the bitmap and all-reduces it afterwards. */

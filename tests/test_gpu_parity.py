@@ -413,8 +413,8 @@ def test_rebase_moves_the_order_keys(native):
 
 
 def test_exchange_primitives_single_gpu(native):
-    """The export -> import -> global id path with world = 1..3 emulated on ONE GPU: all partitions
-    are imported into owner contexts on the same device and the bitmap 'all-reduce' is a local sum."""
+    """The export -> import -> global id path (the form for any transport) with world = 1..3 emulated on ONE GPU:
+    all partitions are imported into owner contexts on the same device and the bitmap 'all-reduce' is a local sum."""
     import torch
     from alntools_b200 import synth
     cols = synth.make_columns(120000, 4000, 2, seed=41, mode="diploid", dup_rate=0.02)
@@ -422,7 +422,7 @@ def test_exchange_primitives_single_gpu(native):
     want = _oracle(cols)
     dev = torch.device("cuda", 0)
     from alntools_b200 import multi_gpu
-    for world, arenas in ((1, False), (2, False), (3, False), (2, True), (3, True)):
+    for world in (1, 2, 3):
         cuts = multi_gpu.shard_bounds(rg, world)
         exports = []
         locals_ = []
@@ -431,21 +431,9 @@ def test_exchange_primitives_single_gpu(native):
             lb = native.EcBuilder(4000, 2, alignments_hint=b - a)
             lb.push(np.ascontiguousarray(rg[a:b]), np.ascontiguousarray(tg[a:b]), np.ascontiguousarray(hp[a:b]), order_base=a)
             locals_.append(lb)
-            if not arenas:
-                exports.append(lb.export_partition(world))
+            exports.append(lb.export_partition(world))
         owners = []
-        if arenas:   # fused partition + store into the owners' arenas (here all in one process, no IPC)
-            cap_ec, cap_rows = 2 * len(want[3]) + 64, 2 * len(want[1]) + 64
-            owners = [native.EcBuilder(4000, 2, alignments_hint=len(rg)) for _ in range(world)]
-            bases = [ob.arena_create(cap_ec, cap_rows)[1] for ob in owners]
-            for lb in locals_:
-                lb.export_to_arenas(bases, cap_ec, cap_rows)
-            for ob in owners:
-                ob.import_arena()
-        if arenas:
-            for ob in owners:
-                ob.arena_reset()
-        for o in range(world if not arenas else 0):   # what all_to_all would deliver to owner o
+        for o in range(world):   # what all_to_all would deliver to owner o
             metas, rows, ecn, rown = [], [], [], []
             for src in range(world):
                 meta, row, ec_counts, row_counts, _, _ = exports[src]
@@ -485,26 +473,55 @@ def test_exchange_primitives_single_gpu(native):
         assert np.array_equal(indices.cpu().numpy(), want[1])
         assert np.array_equal(data.cpu().numpy(), want[2])
         assert np.array_equal(counts.cpu().numpy(), want[3])
-        if arenas:
-            # ordering form: every EC to the rank whose shard holds its first occurrence; no global bitmap
-            for ob in owners:
-                ob.arena_reset()
-            lo, hi = cuts[:-1], cuts[1:]
-            for ob in owners:
-                ob.order_dispatch(bases, cap_ec, cap_rows, lo, hi)
-            at = 0
-            for r, ob in enumerate(owners):
-                sl = ob.order_build(lo[r], hi[r])
-                a, b = at, at + sl["n_ec"]
-                assert np.array_equal(sl["a_indptr"].cpu().numpy(), want[0][a:b + 1] - want[0][a])
-                assert np.array_equal(sl["a_indices"].cpu().numpy(), want[1][want[0][a]:want[0][b]])
-                assert np.array_equal(sl["a_data"].cpu().numpy(), want[2][want[0][a]:want[0][b]])
-                assert np.array_equal(sl["n_data"].cpu().numpy(), want[3][a:b])
-                at = b
-            assert at == n_ec
-            assert at == n_ec
         for b in locals_ + owners:
             b.close()
+
+
+@pytest.mark.parametrize("world,mode", [(1, "diploid"), (2, "diploid"), (3, "diploid"), (4, "heavy"), (3, "empty-rank")])
+def test_peer_memory_exchange_single_gpu(native, world, mode):
+    """The exchange of the multi-GPU path - dispatch by key, owner merge, dispatch by first occurrence, slices
+    ordered over the rank's own positions with rows from the LOCAL context - with the ranks emulated on ONE GPU
+    (arenas in the same process instead of IPC mappings).  The slices concatenated are the oracle's matrices."""
+    from alntools_b200 import synth, multi_gpu
+    if mode == "heavy":
+        cols, nt, nh = synth.make_columns(6000, 3000, 8, seed=43, mode="heavy", dup_rate=0.02), 3000, 8
+    else:
+        cols, nt, nh = synth.make_columns(120000, 4000, 2, seed=41, mode="diploid", dup_rate=0.02), 4000, 2
+    rg, tg, hp = cols["read_group"], cols["target_idx"], cols["hap_idx"]
+    want = _oracle(cols)
+    cuts = multi_gpu.shard_bounds(rg, world)
+    if mode == "empty-rank":
+        cuts[1] = cuts[2]                                        # rank 1 holds nothing
+    locals_, owners = [], []
+    for r in range(world):
+        a, b = cuts[r], cuts[r + 1]
+        lb = native.EcBuilder(nt, nh, alignments_hint=max(b - a, 1))
+        if b > a:
+            lb.push(np.ascontiguousarray(rg[a:b]), np.ascontiguousarray(tg[a:b]), np.ascontiguousarray(hp[a:b]), order_base=a)
+        locals_.append(lb)
+        owners.append(native.EcBuilder(nt, nh, alignments_hint=len(rg)))
+    cap_ec = 2 * len(want[3]) + 64
+    bases = [ob.arena_create(cap_ec)[1] for ob in owners]
+    spans = [lb.export_to_arenas(bases, cap_ec) for lb in locals_]
+    for ob in owners:
+        ob.import_arena()
+        ob.arena_reset()
+    lo, hi = [s[0] for s in spans], [s[1] for s in spans]
+    assert [h > l for l, h in zip(lo, hi)] == [cuts[r + 1] > cuts[r] for r in range(world)]
+    for ob in owners:
+        ob.order_dispatch(bases, cap_ec, lo, hi)
+    at = 0
+    for r, ob in enumerate(owners):
+        sl = ob.order_build(locals_[r], lo[r], hi[r])
+        a, b = at, at + sl["n_ec"]
+        assert np.array_equal(sl["a_indptr"].cpu().numpy(), want[0][a:b + 1] - want[0][a])
+        assert np.array_equal(sl["a_indices"].cpu().numpy(), want[1][want[0][a]:want[0][b]])
+        assert np.array_equal(sl["a_data"].cpu().numpy(), want[2][want[0][a]:want[0][b]])
+        assert np.array_equal(sl["n_data"].cpu().numpy(), want[3][a:b])
+        at = b
+    assert at == len(want[3])
+    for b in locals_ + owners:
+        b.close()
 
 
 def test_randomised_read_shapes_and_launch_geometry(native):

@@ -55,18 +55,18 @@ for r in range(2):
             np.ascontiguousarray(cols["hap_idx"][a:e]), order_base=a)
     locals_.append(lb)
     owners.append(EcBuilder(2000, 2, alignments_hint=len(cols["read_group"])))
-cap_ec, cap_rows = 2 * max(l.stats()["table_used"] for l in locals_) + 1024, 2 * max(l.stats()["row_entries"] for l in locals_) + 1024
-bases = [o.arena_create(cap_ec, cap_rows)[1] for o in owners]
+cap_ec = 2 * max(l.stats()["table_used"] for l in locals_) + 1024
+bases = [o.arena_create(cap_ec)[1] for o in owners]
 for l in locals_:
-    l.export_to_arenas(bases, cap_ec, cap_rows)
+    l.export_to_arenas(bases, cap_ec)
 for o in owners:
     o.import_arena()
     o.arena_reset()
 for o in owners:
-    o.order_dispatch(bases, cap_ec, cap_rows, cuts[:-1], cuts[1:])
+    o.order_dispatch(bases, cap_ec, cuts[:-1], cuts[1:])
 at = 0
 for r, o in enumerate(owners):
-    sl = o.order_build(cuts[r], cuts[r + 1])
+    sl = o.order_build(locals_[r], cuts[r], cuts[r + 1])
     a, e = at, at + sl["n_ec"]
     assert np.array_equal(sl["a_indptr"].cpu().numpy(), want[0][a:e + 1] - want[0][a])
     assert np.array_equal(sl["a_indices"].cpu().numpy(), want[1][want[0][a]:want[0][e]])
