@@ -35,41 +35,92 @@ def convert_files(bam_files, ec_filename, emase_filename, minimum_count, target_
         cell_names = [None] * len(cell_ids)
         for name, idx in cell_ids.items():
             cell_names[idx] = name
+        with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
+                       alignments_hint=total_valid, device=device) as builder:
+            base = 0
+            for rg, tg, hp, cell in per_file:
+                builder.push(rg, tg, hp, cell, order_base=base, drop_last_group=True)
+                base += len(rg)
+            res = builder.finalize(minimum_count)
     else:
+        # native emitter: a worker thread decodes file i + 1 while file i is pushed (one push = one file: the file
+        # is part of the (file, EC, cell) key and its last read is dropped); at most two files are in host memory
+        import queue
+        import threading
         cells = bamcols.CellDictionary()
-        tables = None
-        range_lo = range_hi = references = section = None
-        for bam_file in bam_files:
-            with bamcols.BamColumnReader(bam_file) as reader:
-                if tables is None:                            # tables from the first file only (:399)
-                    tables = reader.build_tables(target_filename)
-                    section = tables.target_section()         # the EC file's targets block, while the reader lives
-                    if range_filename is not None:
-                        references = reader.references
-                else:
-                    reader.set_tables(tables)
-                if range_filename is not None:
-                    reader.track_ranges(True)
-                c = reader.read_all(cells=cells, chunk=1 << 23)
-                if range_filename is not None:                # merged over the files (:568-576)
-                    lo, hi = reader.ranges()
-                    range_lo = lo if range_lo is None else np.minimum(range_lo, lo)
-                    range_hi = hi if range_hi is None else np.maximum(range_hi, hi)
-            per_file.append((c["read_group"], c["target_idx"], c["hap_idx"], c["cell_idx"]))
-            total_valid += len(c["read_group"])
+        state = {"tables": None, "section": None, "references": None, "lo": None, "hi": None}
+        ready = queue.Queue(maxsize=1)
+        stop = threading.Event()
+        first_tables = threading.Event()
+
+        def decode():
+            try:
+                for bam_file in bam_files:
+                    if stop.is_set():
+                        return
+                    with bamcols.BamColumnReader(bam_file) as reader:
+                        if state["tables"] is None:              # tables from the first file only (:399)
+                            state["tables"] = reader.build_tables(target_filename)
+                            state["section"] = state["tables"].target_section()   # while the reader lives
+                            if range_filename is not None:
+                                state["references"] = reader.references
+                            first_tables.set()
+                        else:
+                            reader.set_tables(state["tables"])
+                        if range_filename is not None:
+                            reader.track_ranges(True)
+                        c = reader.read_all(cells=cells, chunk=1 << 23)
+                        if range_filename is not None:            # merged over the files (:568-576)
+                            lo, hi = reader.ranges()
+                            state["lo"] = lo if state["lo"] is None else np.minimum(state["lo"], lo)
+                            state["hi"] = hi if state["hi"] is None else np.maximum(state["hi"], hi)
+                    item = (c["read_group"], c["target_idx"], c["hap_idx"], c["cell_idx"])
+                    while not stop.is_set():
+                        try:
+                            ready.put(item, timeout=0.05)
+                            break
+                        except queue.Full:
+                            continue
+                ready.put(None)
+            except BaseException as exc:                          # re-raised by the consumer
+                first_tables.set()
+                ready.put(exc)
+
+        worker = threading.Thread(target=decode, daemon=True)
+        worker.start()
+        try:
+            first_tables.wait()
+            first = ready.get()
+            if isinstance(first, BaseException):
+                raise first
+            tables, section = state["tables"], state["section"]
+            with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
+                           alignments_hint=0, device=device) as builder:
+                base = 0
+                item = first
+                while item is not None:
+                    rg, tg, hp, cell = item
+                    builder.push(rg, tg, hp, cell, order_base=base, drop_last_group=True)
+                    base += len(rg)
+                    item = ready.get()
+                    if isinstance(item, BaseException):
+                        raise item
+                total_valid = base
+                res = builder.finalize(minimum_count)
+        finally:
+            # whatever happened, the decode thread has left the native library before the dictionary is closed
+            stop.set()
+            while worker.is_alive():
+                try:
+                    ready.get_nowait()
+                except queue.Empty:
+                    pass
+                worker.join(timeout=0.05)
         cell_names = cells.names()
         cells.close()
         if range_filename is not None:                        # :638-668
             utils.write_range_file(range_filename, list(tables.main_targets.keys()), tables.haplotypes,
-                                   references, range_lo, range_hi)
-
-    with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=True,
-                   alignments_hint=total_valid, device=device) as builder:
-        base = 0
-        for rg, tg, hp, cell in per_file:
-            builder.push(rg, tg, hp, cell, order_base=base, drop_last_group=True)
-            base += len(rg)
-        res = builder.finalize(minimum_count)
+                                   state["references"], state["lo"], state["hi"])
 
     LOG.info("Number of alignments: {:,}".format(total_valid))
     LOG.info("Number of main targets: {:,}".format(tables.num_targets))
