@@ -270,7 +270,7 @@ def convert_rank(bam_filename, ec_filename, emase_filename, num_chunks=0, number
             opts = dict(with_cells=False, alignments_hint=0, device=local_rank, result_on_device=1)
             with EcBuilder(tables.num_targets, tables.num_haplotypes, **opts) as builder, \
                     EcBuilder(tables.num_targets, tables.num_haplotypes, **opts) as owner:
-                chunk_rows = int(min(1 << 23, max(1 << 16, os.path.getsize(bam_filename) // 2)))
+                chunk_rows = int(min(1 << 21, max(1 << 16, os.path.getsize(bam_filename) // 2)))   # 24 MB of columns per piece
                 valid = emitter.stream_single(reader, builder, chunk_rows=chunk_rows, pinned=True)
                 mine = torch.tensor([valid, reader.all_alignments], dtype=torch.int64, device=device)
                 every = [torch.empty_like(mine) for _ in range(world)]
@@ -432,7 +432,7 @@ def convert(bam_filename, ec_filename, emase_filename, num_chunks=0, number_proc
         # grows it ahead of later ones; one finalize per context, so results skip the pinning cost
         with EcBuilder(tables.num_targets, tables.num_haplotypes, with_cells=False, alignments_hint=0,
                        device=device, pageable_results=1) as builder:
-            chunk_rows = int(min(1 << 23, max(1 << 16, os.path.getsize(bam_filename) // 2)))
+            chunk_rows = int(min(1 << 21, max(1 << 16, os.path.getsize(bam_filename) // 2)))   # 24 MB of columns per piece
             valid = emitter.stream_single(reader, builder, chunk_rows=chunk_rows, pinned=torch.cuda.is_available())
             if valid == 0:
                 # the reference ends up with zero ECs and APM() raises (Sparse3DMatrix.py:45-46)

@@ -109,15 +109,31 @@ def use_python_emitter():
     return os.environ.get("ALNTOOLS_B200_EMITTER", "native").lower() == "python"
 
 
+_PINNED_POOL = []      # pinned buffer sets of finished conversions, reused by the next one in this process
+
+
 def _column_buffers(rows, with_cells, pinned):
     n = 4 if with_cells else 3
     if pinned:
         import torch
+        # pinning host memory costs about as much as decoding it: a set that an earlier convert() of this
+        # process has pinned is taken again when it is large enough
+        for i, bufs in enumerate(_PINNED_POOL):
+            if len(bufs) == n and int(bufs[0].shape[0]) >= rows:
+                return _PINNED_POOL.pop(i)
         return [torch.empty(rows, dtype=torch.int32, pin_memory=True) for _ in range(n)]
     return [np.empty(rows, dtype=np.int32) for _ in range(n)]
 
 
-def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
+def _release_buffers(sets, pinned):
+    """Buffer sets of a finished stream go back to the pool (at most 8 sets are kept)."""
+    if pinned:
+        for bufs in sets:
+            if len(_PINNED_POOL) < 8:
+                _PINNED_POOL.append(bufs)
+
+
+def stream_single(reader, builder, chunk_rows=1 << 21, pinned=True, depth=3):
     """Decode `reader` (bamcols.BamColumnReader, tables set) on a worker thread into a small ring of
     pinned buffers and push every filled buffer to the GPU while the next one is being decoded.
     Chunks end on read boundaries (bamcols_emit never splits a read), order_base = rows pushed so far,
@@ -126,6 +142,7 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
     import threading
     free, full = queue.Queue(), queue.Queue()
     allocated = [0]
+    all_sets = []
     stop = threading.Event()
     rows = [int(chunk_rows)]
 
@@ -137,7 +154,9 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
             except queue.Empty:
                 if allocated[0] < depth:
                     allocated[0] += 1
-                    return _column_buffers(rows[0], False, pinned)
+                    bufs = _column_buffers(rows[0], False, pinned)
+                    all_sets.append(bufs)
+                    return bufs
                 try:
                     bufs = free.get(timeout=0.05)
                 except queue.Empty:
@@ -186,6 +205,7 @@ def stream_single(reader, builder, chunk_rows=1 << 23, pinned=True, depth=3):
         # bamcols_close frees what bamcols_emit is working on
         stop.set()
         worker.join()
+        _release_buffers(all_sets, pinned)
     return pushed
 
 

@@ -272,7 +272,8 @@ def run_bam_e2e(wl_name, sample_reads, device, passes=3):
     best = min(times)
     return {"value": n_aln / best, "unit": "alignments/s", "ms": 1e3 * best, "threads": os.cpu_count(),
             "sample": "%d reads / %d alignments of %s as one BAM file; bam_utils.convert: BGZF inflate + record "
-                      "pass (libbamcols) -> pinned columns -> GPU EC build -> EC file (%d bytes); best of %d"
+                      "pass (libbamcols) -> pinned columns -> GPU EC build -> EC file (%d bytes); best of %d after one warm-up "
+                      "pass (the pinned column buffers of a finished convert() are reused by the next one in the process)"
                       % (sample_reads, n_aln, wl_name, size, passes)}
 
 
