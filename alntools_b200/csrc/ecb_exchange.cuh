@@ -3,11 +3,14 @@
 // Reads shard across GPUs by contiguous chunk (the reference's utils.partition + ordered imap,
 // alntools/bam_utils.py:647-680); every GPU builds a local EC table.  Global dedup = the chunk merge
 // of alntools/bam_utils.py:680-698 (sum the counts of equal keys, EC id = rank of the GLOBAL first
-// occurrence): local ECs are hash-partitioned to an owner GPU (all-to-all), the owner merges them,
-// and the global ids come from the same first-occurrence bitmap as on one GPU, OR-ed across ranks.
-//
-// Record layout of an exported EC ("meta", 5 x int64): key_lo, key_hi, first,
-// count << 32 | row_len, row offset inside the partition (in (target, mask) pairs).
+// occurrence).  Two forms:
+//   * any transport (NCCL all-to-all, gloo in the CPU tests): ecb_export_* pack the local ECs WITH their rows
+//     into partitions by owner rank, the owner merges them (ecb_import_insert_kernel), global ids come from
+//     a first-occurrence bitmap OR-ed across ranks, the matrices are assembled on every rank.  Record layout
+//     of an exported EC ("meta", 5 x int64): key_lo, key_hi, first, count << 32 | row_len, row offset inside
+//     the partition (in (target, mask) pairs);
+//   * peer memory (the multi-GPU product path): two dispatches of fixed-size records through IPC-mapped
+//     arenas, rows never travel, nothing global is built - see "the exchange over peer memory" below.
 #pragma once
 #include "ecb_common.cuh"
 #include "ecb_group.cuh"
